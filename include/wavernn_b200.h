@@ -1,0 +1,144 @@
+/* wavernn_b200.h -- C ABI of the Blackwell-native WaveRNN generate() engine.
+ *
+ * Drop-in boundary.  The reference (fatchord/WaveRNN) has no
+ * native interface of its own: its hot path is the Python loop
+ *     models/fatchord_version.py:201-241   (per-sample: I, rnn1, rnn2, fc1, fc2, fc3)
+ *     utils/distribution.py:87-123         (MoL sampling)      /  :231-237 (RAW softmax head)
+ * run between `self.upsample(...)` (:186) and the numpy epilogue (:243).  These entry
+ * points are what a Python/ctypes (or any FFI) binding of that span binds; the
+ * reference-side stub is shown in INTEGRATION.md and implemented in
+ * wavernn_b200/cabi.py.
+ *
+ * Conventions: plain C types only; every function returns 0 on success or a negative
+ * WRNN_E_* code and never throws; `wrnn_last_error()` gives a thread-local message.
+ * The caller owns every buffer it passes; a handle owns only its packed weights and
+ * scratch.  One handle per device; one generate in flight per handle.  All device
+ * work is enqueued on the given stream; no host synchronisation inside
+ * `wrnn_generate` (errors detected on the device -- e.g. a watchdog abort -- are
+ * reported by `wrnn_check`, to be called after the stream has been synchronised).
+ */
+#ifndef WAVERNN_B200_H_
+#define WAVERNN_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WRNN_ABI_VERSION 1
+
+enum {
+  WRNN_OK = 0,
+  WRNN_E_INVALID = -1,      /* bad argument / unsupported configuration            */
+  WRNN_E_CUDA = -2,         /* a CUDA runtime call failed (see wrnn_last_error)     */
+  WRNN_E_NO_DEVICE = -3,    /* no sm_100 device: there is NO CPU fallback           */
+  WRNN_E_WATCHDOG = -4,     /* the persistent kernel aborted on its spin watchdog   */
+  WRNN_E_BUSY = -5
+};
+
+enum { WRNN_MODE_MOL = 0, WRNN_MODE_RAW = 1 };   /* fatchord_version.py:98-104 */
+
+/* Arithmetic of the dense contractions.
+ *   BF16: weights and activations rounded to bf16 as tensor-core operands, fp32
+ *         accumulate, everything else (state, gates, sampler) fp32.  The product path.
+ *   FP32: strict mode -- fp32 weights/activations on CUDA cores; a debugging and
+ *         parity tool (matches the reference to reassociation error).               */
+enum { WRNN_PREC_BF16 = 0, WRNN_PREC_FP32 = 1 };
+
+/* Which kernel family executes the job.  AUTO picks the fastest that supports it. */
+enum { WRNN_ENGINE_AUTO = 0, WRNN_ENGINE_SIMT = 1, WRNN_ENGINE_TCGEN05 = 2 };
+
+typedef struct wrnn_handle wrnn_t;
+
+/* Mirrors the WaveRNN ctor arguments that size the hot path
+ * (fatchord_version.py:93-123; hparams.py:44-50).                                  */
+typedef struct {
+  int32_t rnn_dims;     /* 512 */
+  int32_t fc_dims;      /* 512 */
+  int32_t feat_dims;    /* 80  */
+  int32_t aux_dims;     /* res_out_dims / 4 = 32 */
+  int32_t n_classes;    /* 30 (MOL) or 2**bits (RAW) */
+  int32_t mode;         /* WRNN_MODE_* */
+  int32_t precision;    /* WRNN_PREC_* */
+  int32_t engine;       /* WRNN_ENGINE_* */
+} wrnn_cfg;
+
+/* The 16 hot-path tensors exactly as they sit in the reference state_dict
+ * (fp32, row-major [out, in]); host or device pointers (resolved with UVA).
+ *   I.weight (rnn, 1+feat+aux)            col 0 = previous sample, 1..feat = mel, rest = aux[0:d]
+ *   rnn1.weight_ih_l0 (3*rnn, rnn)        gate rows [r, z, n]   (fatchord_version.py:273-279)
+ *   rnn2.weight_ih_l0 (3*rnn, rnn+aux)    cols rnn.. = aux[d:2d]
+ *   fc1.weight (fc, rnn+aux)              cols rnn.. = aux[2d:3d]
+ *   fc2.weight (fc, fc+aux)               cols fc..  = aux[3d:4d]
+ *   fc3.weight (n_classes, fc)                                                     */
+typedef struct {
+  const float *I_weight, *I_bias;
+  const float *rnn1_weight_ih, *rnn1_weight_hh, *rnn1_bias_ih, *rnn1_bias_hh;
+  const float *rnn2_weight_ih, *rnn2_weight_hh, *rnn2_bias_ih, *rnn2_bias_hh;
+  const float *fc1_weight, *fc1_bias, *fc2_weight, *fc2_bias, *fc3_weight, *fc3_bias;
+} wrnn_weights;
+
+/* One generate call == the loop fatchord_version.py:194-241 over `n_seg` folds.
+ * Folds are strided windows of the UN-folded conditioning stream: fold b, step t
+ * reads row  b*seg_stride + t  of mels_up / aux; rows >= L read as zeros, which is
+ * what fold_with_overlap's right padding produces (fatchord_version.py:319-338).
+ * Unbatched generation is n_seg = 1, seg_len = L.                                  */
+typedef struct {
+  const float *mels_up;   /* device, [L, feat_dims]                                  */
+  const float *aux;       /* device, [L, 4*aux_dims]                                 */
+  int64_t L;
+  int64_t seg_stride;     /* target + overlap                                        */
+  int32_t n_seg;          /* folds handled by this call (this rank)                  */
+  int32_t seg_len;        /* target + 2*overlap == steps per fold                    */
+  int32_t seg_first;      /* global index of fold 0 (keys the in-kernel Philox)      */
+  int32_t steps;          /* 0 = seg_len; otherwise generate only the first `steps`  */
+  /* Randomness.  Parity mode: the caller supplies the draws the reference would have
+   * made from torch's generator (utils/distribution.py:106,118):
+   *   uniforms [seg_len, 11*n_seg], row t = [n_seg*10 mixture draws, fold-major |
+   *   n_seg logistic draws], values in [1e-5, 1-1e-5].
+   *   expo     [seg_len, n_seg, n_classes] Exp(1) draws (RAW head: Categorical.sample()
+   *   == argmax(p / e), fatchord_version.py:233-235).
+   * NULL selects the in-kernel counter-based Philox4x32-10 keyed by
+   * (philox_seed, philox_offset, global fold, step).                               */
+  const float *uniforms;
+  const float *expo;
+  uint64_t philox_seed;
+  uint64_t philox_offset;
+  float *out;             /* device, [n_seg, seg_len] generated samples (pre-xfade)  */
+  /* Instrumentation (NULL when unused) */
+  const float *x_force;   /* [seg_len, n_seg] teacher forcing: step t consumes
+                             x_force[t-1] instead of its own previous sample        */
+  float *logits_out;      /* [seg_len, n_seg, n_classes] fc3 outputs per step        */
+} wrnn_job;
+
+int wrnn_abi_version(void);
+const char *wrnn_last_error(void);
+
+/* Packs the weights for the chosen engine on `device` (bf16 tiles + folded
+ * conditioning matrices) and allocates per-handle scratch.                         */
+int wrnn_create(wrnn_t **out, const wrnn_cfg *cfg, const wrnn_weights *w, int device);
+void wrnn_destroy(wrnn_t *h);
+
+/* Enqueues the persistent kernel on `stream` (a cudaStream_t; NULL = default).     */
+int wrnn_generate(wrnn_t *h, const wrnn_job *job, void *stream);
+
+/* After the stream has been synchronised: 0, or WRNN_E_WATCHDOG / WRNN_E_CUDA if the
+ * last job aborted on the device.                                                  */
+int wrnn_check(wrnn_t *h);
+
+/* Convenience for non-torch callers: same job but mels_up / aux / uniforms / expo /
+ * out / x_force / logits_out are HOST pointers; copies in, runs, copies out and
+ * synchronises.                                                                    */
+int wrnn_generate_host(wrnn_t *h, const wrnn_job *job);
+
+/* Introspection: name of the engine serving the handle ("simt", "tcgen05"), number
+ * of CTAs of the persistent grid, and kernel launches issued so far.               */
+const char *wrnn_engine_name(const wrnn_t *h);
+int wrnn_grid_ctas(const wrnn_t *h);
+int64_t wrnn_launch_count(const wrnn_t *h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WAVERNN_B200_H_ */

@@ -1,0 +1,129 @@
+"""Import the UNMODIFIED reference (fatchord/WaveRNN) from /root/reference.
+
+TEST INFRASTRUCTURE ONLY.  Nothing in the product path (wavernn_b200/) may
+import this file.  It only works in the build container, where the reference
+checkout is mounted read-only at /root/reference; the GPU box has no such
+directory, so everything here is used solely to (a) pin `oracle/wavernn_oracle.py`
+against the real reference and (b) generate the committed fixtures under
+`tests/golden/` (see `tests/golden/make_golden.py`).
+
+The reference star-imports matplotlib and librosa (models/fatchord_version.py:5-6
+-> utils/display.py:1-3, utils/dsp.py:3) which are absent here, and uses
+`np.cumproduct` (fatchord_version.py:68) which NumPy 2 removed.  Three in-process
+shims make it importable without touching its files.
+
+Because the reference's top-level packages are called `models` and `utils`,
+always run this in a subprocess / fresh interpreter that does not have a
+same-named package of ours on sys.path.
+"""
+import io
+import os
+import sys
+import types
+import zipfile
+
+import numpy as np
+
+REF_ROOT = os.environ.get("WAVERNN_REFERENCE", "/root/reference")
+
+
+def available() -> bool:
+    return os.path.isfile(os.path.join(REF_ROOT, "models", "fatchord_version.py"))
+
+
+_ref_mod = None
+_captured_wavs = []
+
+
+def load_reference():
+    """Returns the reference module `models.fatchord_version` (cached)."""
+    global _ref_mod
+    if _ref_mod is not None:
+        return _ref_mod
+    if not available():
+        raise RuntimeError(f"reference checkout not found at {REF_ROOT}")
+    sys.path.insert(0, REF_ROOT)
+    lib = types.ModuleType("librosa")
+    lib.output = types.SimpleNamespace(
+        write_wav=lambda path, x, sr: _captured_wavs.append((str(path), np.array(x), sr)))
+    mpl = types.ModuleType("matplotlib")
+    mpl.use = lambda *a, **k: None
+    mpl.interactive = lambda *a, **k: None
+    plt = types.ModuleType("matplotlib.pyplot")
+    mpl.pyplot = plt
+    sys.modules.update({"librosa": lib, "matplotlib": mpl, "matplotlib.pyplot": plt})
+    if not hasattr(np, "cumproduct"):
+        np.cumproduct = np.cumprod
+    import models.fatchord_version as ref  # noqa: E402  (unmodified reference)
+    from utils import hparams as hp  # noqa: E402
+    if not hp.is_configured():
+        hp.configure(os.path.join(REF_ROOT, "hparams.py"))
+    ref.stream = lambda msg: None  # silence gen_display
+    _ref_mod = ref
+    return ref
+
+
+def default_kwargs(mode="MOL", bits=9):
+    """ctor kwargs as gen_wavernn.py:112-123 builds them from hparams.py:20-60."""
+    return dict(rnn_dims=512, fc_dims=512, bits=bits, pad=2, upsample_factors=(5, 5, 11),
+                feat_dims=80, compute_dims=128, res_out_dims=128, res_blocks=10,
+                hop_length=275, sample_rate=22050, mode=mode)
+
+
+def build_reference_model(seed=0, mode="MOL", bits=9, pretrained=False):
+    import contextlib
+    import torch
+    ref = load_reference()
+    torch.manual_seed(seed)
+    with contextlib.redirect_stdout(io.StringIO()):
+        model = ref.WaveRNN(**default_kwargs(mode, bits))
+    if pretrained:
+        sd = load_pretrained_state_dict()
+        model.load_state_dict(sd, strict=False)
+    return model
+
+
+def load_pretrained_state_dict():
+    import torch
+    zpath = os.path.join(REF_ROOT, "pretrained", "ljspeech.wavernn.mol.800k.zip")
+    with zipfile.ZipFile(zpath) as z:
+        blob = z.read("latest_weights.pyt")
+    return torch.load(io.BytesIO(blob), map_location="cpu")
+
+
+def ref_generate(model, mels, batched, target, overlap, mu_law=False, seed=1234,
+                 capture=True):
+    """Runs the reference's own generate() on CPU under torch.manual_seed(seed).
+
+    Returns dict(wav=final float64 waveform, pre=(B,S) float64 pre-xfade samples
+    (post mu-law decode, as handed to xfade_and_unfold, fatchord_version.py:250-251),
+    raw=(B,S) float32 samples exactly as stacked at :243).
+    """
+    import torch
+    ref = load_reference()
+    grabbed = {}
+    if capture:
+        orig_xfade = model.xfade_and_unfold
+
+        def spy(y, target, overlap):
+            grabbed["pre"] = y.copy()
+            return orig_xfade(y, target, overlap)
+        model.xfade_and_unfold = spy
+        orig_stack = torch.stack
+
+        def stack_spy(tensors, *a, **k):
+            out = orig_stack(tensors, *a, **k)
+            grabbed["raw"] = out.transpose(0, 1).detach().cpu().numpy().copy()
+            return out
+        ref.torch.stack = stack_spy
+    try:
+        torch.manual_seed(seed)
+        wav = model.generate(mels, "/dev/null.wav", batched, target, overlap, mu_law)
+    finally:
+        if capture:
+            del model.xfade_and_unfold
+            ref.torch.stack = orig_stack
+    model.eval()
+    out = dict(wav=np.asarray(wav), raw=grabbed.get("raw"))
+    out["pre"] = grabbed.get("pre")
+    return out

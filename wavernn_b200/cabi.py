@@ -1,0 +1,173 @@
+"""ctypes binding of include/wavernn_b200.h -- the only way the Python host reaches the
+CUDA engine.  No torch types cross this boundary: raw pointers (tensor.data_ptr())
+and a raw cudaStream_t.  Import never fails (so CPU-only tools can load the package)
+but `load()` raises if the shared library has not been built: there is no fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+LIB_NAME = "libwavernn_b200.so"
+LIB_PATH = Path(__file__).with_name(LIB_NAME)
+
+WRNN_OK, WRNN_E_INVALID, WRNN_E_CUDA, WRNN_E_NO_DEVICE, WRNN_E_WATCHDOG, WRNN_E_BUSY = 0, -1, -2, -3, -4, -5
+MODE_MOL, MODE_RAW = 0, 1
+PREC_BF16, PREC_FP32 = 0, 1
+ENGINE_AUTO, ENGINE_SIMT, ENGINE_TCGEN05 = 0, 1, 2
+ABI_VERSION = 1
+
+EXPORTS = ("wrnn_abi_version", "wrnn_last_error", "wrnn_create", "wrnn_destroy", "wrnn_generate",
+           "wrnn_check", "wrnn_generate_host", "wrnn_engine_name", "wrnn_grid_ctas", "wrnn_launch_count")
+
+_fp = C.POINTER(C.c_float)
+
+
+class WrnnCfg(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("rnn_dims", "fc_dims", "feat_dims", "aux_dims", "n_classes",
+                                         "mode", "precision", "engine")]
+
+
+WEIGHT_FIELDS = ("I_weight", "I_bias",
+                 "rnn1_weight_ih", "rnn1_weight_hh", "rnn1_bias_ih", "rnn1_bias_hh",
+                 "rnn2_weight_ih", "rnn2_weight_hh", "rnn2_bias_ih", "rnn2_bias_hh",
+                 "fc1_weight", "fc1_bias", "fc2_weight", "fc2_bias", "fc3_weight", "fc3_bias")
+# state_dict key for each field (reference models/fatchord_version.py:115-123)
+WEIGHT_KEYS = ("I.weight", "I.bias",
+               "rnn1.weight_ih_l0", "rnn1.weight_hh_l0", "rnn1.bias_ih_l0", "rnn1.bias_hh_l0",
+               "rnn2.weight_ih_l0", "rnn2.weight_hh_l0", "rnn2.bias_ih_l0", "rnn2.bias_hh_l0",
+               "fc1.weight", "fc1.bias", "fc2.weight", "fc2.bias", "fc3.weight", "fc3.bias")
+
+
+class WrnnWeights(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in WEIGHT_FIELDS]
+
+
+class WrnnJob(C.Structure):
+    _fields_ = [("mels_up", C.c_void_p), ("aux", C.c_void_p), ("L", C.c_int64), ("seg_stride", C.c_int64),
+                ("n_seg", C.c_int32), ("seg_len", C.c_int32), ("seg_first", C.c_int32), ("steps", C.c_int32),
+                ("uniforms", C.c_void_p), ("expo", C.c_void_p),
+                ("philox_seed", C.c_uint64), ("philox_offset", C.c_uint64),
+                ("out", C.c_void_p), ("x_force", C.c_void_p), ("logits_out", C.c_void_p)]
+
+
+_lib = None
+
+
+def is_built() -> bool:
+    return LIB_PATH.is_file()
+
+
+def load() -> C.CDLL:
+    """dlopen the engine.  Raises RuntimeError if it is missing (no CPU fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = os.environ.get("WAVERNN_B200_LIB", str(LIB_PATH))
+    if not os.path.isfile(path):
+        raise RuntimeError(
+            f"wavernn_b200: CUDA engine {path} is not built. Run `python -c 'import __graft_entry__ as g; "
+            f"g.build()'` (or `make -C wavernn_b200/csrc`). There is no CPU fallback for generate().")
+    lib = C.CDLL(path, mode=C.RTLD_GLOBAL)
+    lib.wrnn_abi_version.restype = C.c_int
+    lib.wrnn_last_error.restype = C.c_char_p
+    lib.wrnn_create.restype = C.c_int
+    lib.wrnn_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(WrnnCfg), C.POINTER(WrnnWeights), C.c_int]
+    lib.wrnn_destroy.restype = None
+    lib.wrnn_destroy.argtypes = [C.c_void_p]
+    lib.wrnn_generate.restype = C.c_int
+    lib.wrnn_generate.argtypes = [C.c_void_p, C.POINTER(WrnnJob), C.c_void_p]
+    lib.wrnn_check.restype = C.c_int
+    lib.wrnn_check.argtypes = [C.c_void_p]
+    lib.wrnn_generate_host.restype = C.c_int
+    lib.wrnn_generate_host.argtypes = [C.c_void_p, C.POINTER(WrnnJob)]
+    lib.wrnn_engine_name.restype = C.c_char_p
+    lib.wrnn_engine_name.argtypes = [C.c_void_p]
+    lib.wrnn_grid_ctas.restype = C.c_int
+    lib.wrnn_grid_ctas.argtypes = [C.c_void_p]
+    lib.wrnn_launch_count.restype = C.c_int64
+    lib.wrnn_launch_count.argtypes = [C.c_void_p]
+    if lib.wrnn_abi_version() != ABI_VERSION:
+        raise RuntimeError(f"wavernn_b200: ABI mismatch (lib {lib.wrnn_abi_version()} != binding {ABI_VERSION})")
+    _lib = lib
+    return lib
+
+
+class EngineError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"wavernn_b200 engine error {code}: {msg}")
+        self.code = code
+
+
+def _check(lib, rc: int):
+    if rc != 0:
+        raise EngineError(rc, (lib.wrnn_last_error() or b"").decode(errors="replace"))
+
+
+class Engine:
+    """Owns one `wrnn_t*`.  `weights` maps WEIGHT_KEYS -> object with .data_ptr()
+    (torch tensors, fp32, contiguous, host or device) or raw ints."""
+
+    def __init__(self, weights: dict, *, rnn_dims=512, fc_dims=512, feat_dims=80, aux_dims=32, n_classes=30,
+                 mode="MOL", precision="bf16", engine="auto", device: int = 0):
+        self._h = C.c_void_p()
+        self.lib = load()
+        cfg = WrnnCfg(rnn_dims, fc_dims, feat_dims, aux_dims, n_classes,
+                      {"MOL": MODE_MOL, "RAW": MODE_RAW}[mode],
+                      {"bf16": PREC_BF16, "fp32": PREC_FP32}[precision],
+                      {"auto": ENGINE_AUTO, "simt": ENGINE_SIMT, "tcgen05": ENGINE_TCGEN05}[engine])
+        w = WrnnWeights()
+        keep = []
+        for field, key in zip(WEIGHT_FIELDS, WEIGHT_KEYS):
+            t = weights[key]
+            if hasattr(t, "data_ptr"):
+                t = t.detach()
+                if t.dtype is not _torch().float32 or not t.is_contiguous():
+                    t = t.float().contiguous()
+                keep.append(t)
+                setattr(w, field, t.data_ptr())
+            else:
+                setattr(w, field, int(t))
+        _check(self.lib, self.lib.wrnn_create(C.byref(self._h), C.byref(cfg), C.byref(w), int(device)))
+        del keep
+        self.n_classes, self.mode, self.precision, self.device = n_classes, mode, precision, device
+
+    @property
+    def name(self) -> str:
+        return self.lib.wrnn_engine_name(self._h).decode()
+
+    @property
+    def grid_ctas(self) -> int:
+        return self.lib.wrnn_grid_ctas(self._h)
+
+    @property
+    def launch_count(self) -> int:
+        return self.lib.wrnn_launch_count(self._h)
+
+    def generate(self, *, mels_up: int, aux: int, L: int, n_seg: int, seg_len: int, seg_stride: int, out: int,
+                 seg_first: int = 0, steps: int = 0, uniforms: int = 0, expo: int = 0, philox_seed: int = 0,
+                 philox_offset: int = 0, x_force: int = 0, logits_out: int = 0, stream: int = 0):
+        """All buffer arguments are raw device addresses (ints).  Asynchronous."""
+        job = WrnnJob(mels_up, aux, L, seg_stride, n_seg, seg_len, seg_first, steps, uniforms or None,
+                      expo or None, philox_seed, philox_offset, out, x_force or None, logits_out or None)
+        _check(self.lib, self.lib.wrnn_generate(self._h, C.byref(job), C.c_void_p(stream or None)))
+
+    def check(self):
+        _check(self.lib, self.lib.wrnn_check(self._h))
+
+    def close(self):
+        if self._h:
+            self.lib.wrnn_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _torch():
+    import torch
+    return torch

@@ -1,0 +1,435 @@
+"""Host side of the drop-in: a `WaveRNN` with the reference's constructor, state_dict
+layout and `generate(mels, save_path, batched, target, overlap, mu_law)` signature
+(reference models/fatchord_version.py:92-264), whose sample loop is the persistent
+sm_100a kernel behind include/wavernn_b200.h instead of ~43 PyTorch launches per
+sample.
+
+What stays in PyTorch (run once per call, as the reference does): the
+UpsampleNetwork (:64-89).  What stays in numpy float64 on the host: mu-law expansion,
+cross-fade/unfold, the fade-out and the wav write (:243-260).  Everything between
+`self.upsample(...)` (:186) and `torch.stack(output)` (:243) is the CUDA engine; there
+is no CPU fallback.
+
+RNG contract.  `gen_rng='torch'` (default) reproduces the reference's consumption of
+torch's default CPU generator: the two throw-away nn.GRUCell constructions of
+:178-179, then per step a (1,B,10) and a (1,B) uniform_(1e-5, 1-1e-5) draw
+(utils/distribution.py:106,118) -- drawn here in one call (the CPU stream is
+split-invariant) and handed to the kernel, so that under the same torch.manual_seed
+the output tracks the reference's CPU output within the tolerance stated in
+DESIGN.md.  `gen_rng='philox'` draws inside the kernel (counter-based, keyed by
+global fold and step, independent of the rank count).
+"""
+from __future__ import annotations
+
+import time
+from pathlib import Path
+from typing import Sequence, Union
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import cabi
+from .display import progbar, stream
+from .dsp import decode_mu_law, save_wav
+from .sharding import FoldGeometry, fold_geometry, gather_segments, shard_folds, unbatched_geometry
+
+LOG_SCALE_MIN = float(np.log(1e-14))
+
+
+# --------------------------------------------------------------------------------------
+# Conditioning network (torch; module / parameter names are the checkpoint wire format)
+# --------------------------------------------------------------------------------------
+class ResBlock(nn.Module):
+    def __init__(self, dims):
+        super().__init__()
+        self.conv1 = nn.Conv1d(dims, dims, kernel_size=1, bias=False)
+        self.conv2 = nn.Conv1d(dims, dims, kernel_size=1, bias=False)
+        self.batch_norm1 = nn.BatchNorm1d(dims)
+        self.batch_norm2 = nn.BatchNorm1d(dims)
+
+    def forward(self, x):
+        y = F.relu(self.batch_norm1(self.conv1(x)))
+        return self.batch_norm2(self.conv2(y)) + x
+
+
+class MelResNet(nn.Module):
+    def __init__(self, res_blocks, in_dims, compute_dims, res_out_dims, pad):
+        super().__init__()
+        self.conv_in = nn.Conv1d(in_dims, compute_dims, kernel_size=2 * pad + 1, bias=False)
+        self.batch_norm = nn.BatchNorm1d(compute_dims)
+        self.layers = nn.ModuleList([ResBlock(compute_dims) for _ in range(res_blocks)])
+        self.conv_out = nn.Conv1d(compute_dims, res_out_dims, kernel_size=1)
+
+    def forward(self, x):
+        x = F.relu(self.batch_norm(self.conv_in(x)))
+        for block in self.layers:
+            x = block(x)
+        return self.conv_out(x)
+
+
+class Stretch2d(nn.Module):
+    """Nearest-neighbour repeat of the last two axes (reference :51-61)."""
+
+    def __init__(self, x_scale, y_scale):
+        super().__init__()
+        self.x_scale, self.y_scale = x_scale, y_scale
+
+    def forward(self, x):
+        if self.y_scale != 1:
+            x = x.repeat_interleave(self.y_scale, dim=2)
+        return x.repeat_interleave(self.x_scale, dim=3)
+
+
+class UpsampleNetwork(nn.Module):
+    def __init__(self, feat_dims, upsample_scales, compute_dims, res_blocks, res_out_dims, pad):
+        super().__init__()
+        total_scale = int(np.prod(upsample_scales))
+        self.total_scale = total_scale
+        self.indent = pad * total_scale
+        self.resnet = MelResNet(res_blocks, feat_dims, compute_dims, res_out_dims, pad)
+        self.resnet_stretch = Stretch2d(total_scale, 1)
+        self.up_layers = nn.ModuleList()
+        for scale in upsample_scales:          # ModuleList indices 1,3,5 hold the convs (checkpoint keys)
+            conv = nn.Conv2d(1, 1, kernel_size=(1, 2 * scale + 1), padding=(0, scale), bias=False)
+            conv.weight.data.fill_(1. / (2 * scale + 1))
+            self.up_layers.append(Stretch2d(scale, 1))
+            self.up_layers.append(conv)
+
+    def stretch_mel(self, m):
+        """(b, feat, t) -> (b, feat, t*total_scale), un-cropped."""
+        m = m.unsqueeze(1)
+        for layer in self.up_layers:
+            m = layer(m)
+        return m.squeeze(1)
+
+    def forward(self, m):
+        aux = self.resnet(m).repeat_interleave(self.total_scale, dim=2)
+        m = self.stretch_mel(m)[:, :, self.indent:-self.indent]
+        return m.transpose(1, 2), aux.transpose(1, 2)
+
+
+# --------------------------------------------------------------------------------------
+class WaveRNN(nn.Module):
+    def __init__(self, rnn_dims, fc_dims, bits, pad, upsample_factors, feat_dims, compute_dims, res_out_dims,
+                 res_blocks, hop_length, sample_rate, mode='RAW'):
+        super().__init__()
+        self.mode = mode
+        self.pad = pad
+        if mode == 'RAW':
+            self.n_classes = 2 ** bits
+        elif mode == 'MOL':
+            self.n_classes = 30
+        else:
+            # the reference builds this error without raising it (:103-104); generate() raises it (:239)
+            raise RuntimeError("Unknown model mode value - ", mode)
+        self._to_flatten = []
+        self.rnn_dims = rnn_dims
+        self.fc_dims = fc_dims
+        self.feat_dims = feat_dims
+        self.aux_dims = res_out_dims // 4
+        self.hop_length = hop_length
+        self.sample_rate = sample_rate
+
+        self.upsample = UpsampleNetwork(feat_dims, upsample_factors, compute_dims, res_blocks, res_out_dims, pad)
+        self.I = nn.Linear(feat_dims + self.aux_dims + 1, rnn_dims)
+        self.rnn1 = nn.GRU(rnn_dims, rnn_dims, batch_first=True)
+        self.rnn2 = nn.GRU(rnn_dims + self.aux_dims, rnn_dims, batch_first=True)
+        self._to_flatten += [self.rnn1, self.rnn2]
+        self.fc1 = nn.Linear(rnn_dims + self.aux_dims, fc_dims)
+        self.fc2 = nn.Linear(fc_dims + self.aux_dims, fc_dims)
+        self.fc3 = nn.Linear(fc_dims, self.n_classes)
+        self.register_buffer('step', torch.zeros(1, dtype=torch.long))
+        self.num_params()
+        self._flatten_parameters()
+
+        # ---- knobs of the B200 engine (not part of the reference surface) ----
+        self.gen_rng = 'torch'          # 'torch' (reference-compatible CPU draws) | 'philox' (in-kernel)
+        self.gen_precision = 'bf16'     # 'bf16' tensor-core operands | 'fp32' strict SIMT mode
+        self.gen_engine = 'auto'        # 'auto' | 'simt' | 'tcgen05'
+        self.gen_philox_seed = 0
+        self.gen_upsample_chunk = 2048  # mel frames per UpsampleNetwork call (bounds HBM intermediates)
+        self.gen_verbose = True
+        self.gen_stats = {}             # filled by generate(): timings, engine name, ...
+        self._engine = None
+        self._engine_key = None
+
+    # ------------------------------------------------------------------ training forward (torch)
+    def forward(self, x, mels):
+        """Teacher-forced forward (reference :131-167); plain PyTorch, not the hot path."""
+        device = next(self.parameters()).device
+        self._flatten_parameters()
+        self.step += 1
+        bsize = x.size(0)
+        h1 = torch.zeros(1, bsize, self.rnn_dims, device=device)
+        h2 = torch.zeros(1, bsize, self.rnn_dims, device=device)
+        mels, aux = self.upsample(mels)
+        d = self.aux_dims
+        a1, a2, a3, a4 = (aux[:, :, d * i:d * (i + 1)] for i in range(4))
+        x = self.I(torch.cat([x.unsqueeze(-1), mels, a1], dim=2))
+        res = x
+        x, _ = self.rnn1(x, h1)
+        x = x + res
+        res = x
+        x, _ = self.rnn2(torch.cat([x, a2], dim=2), h2)
+        x = x + res
+        x = F.relu(self.fc1(torch.cat([x, a3], dim=2)))
+        x = F.relu(self.fc2(torch.cat([x, a4], dim=2)))
+        return self.fc3(x)
+
+    # ------------------------------------------------------------------ engine plumbing
+    def hot_state(self) -> dict:
+        """The 16 tensors the kernel consumes, keyed as in the checkpoint."""
+        sd = {k: v for k, v in self.named_parameters() if not k.startswith('upsample.')}
+        return {k: sd[k] for k in cabi.WEIGHT_KEYS}
+
+    def _get_engine(self, device: torch.device) -> 'cabi.Engine':
+        hot = self.hot_state()
+        key = (str(device), self.gen_precision, self.gen_engine, self.mode, self.n_classes,
+               tuple((t.data_ptr(), t._version) for t in hot.values()))
+        if self._engine is None or key != self._engine_key:
+            if self._engine is not None:
+                self._engine.close()
+            self._engine = cabi.Engine(hot, rnn_dims=self.rnn_dims, fc_dims=self.fc_dims,
+                                       feat_dims=self.feat_dims, aux_dims=self.aux_dims,
+                                       n_classes=self.n_classes, mode=self.mode, precision=self.gen_precision,
+                                       engine=self.gen_engine, device=device.index or 0)
+            self._engine_key = key
+        return self._engine
+
+    def _require_cuda(self) -> torch.device:
+        device = next(self.parameters()).device
+        if device.type != 'cuda':
+            raise RuntimeError(
+                "wavernn_b200: WaveRNN.generate() runs only on a CUDA (sm_100a) device -- move the model with "
+                ".to('cuda'). There is deliberately no CPU fallback.")
+        return device
+
+    # ------------------------------------------------------------------ conditioning
+    def conditioning(self, mels_padded: torch.Tensor, frame_lo: int, frame_hi: int):
+        """Upsampled conditioning rows for OUTPUT frames [frame_lo, frame_hi) -- i.e. samples
+        [frame_lo*hop, frame_hi*hop) of what `self.upsample(mels_padded)` (:186) returns --
+        computed from a slice of the padded mel with a halo, in chunks of
+        `gen_upsample_chunk` frames so the x275 intermediates stay small.
+        mels_padded: (1, feat, T + 2*pad).  Returns (rows, feat), (rows, 4*aux) fp32."""
+        up, pad, hop = self.upsample, self.pad, self.hop_length
+        Tp = mels_padded.size(-1)
+        halo = 1
+        outs_m, outs_a = [], []
+        chunk = max(int(self.gen_upsample_chunk), 8)
+        for lo in range(frame_lo, frame_hi, chunk):
+            hi = min(lo + chunk, frame_hi)
+            lo_p = max(0, lo - halo)
+            hi_p = min(Tp, hi + 2 * pad + halo)
+            piece = mels_padded[:, :, lo_p:hi_p]
+            aux = up.resnet(piece)[:, :, lo - lo_p: hi - lo_p]
+            aux = aux.repeat_interleave(up.total_scale, dim=2)
+            m = up.stretch_mel(piece)[:, :, (lo + pad - lo_p) * hop:(hi + pad - lo_p) * hop]
+            outs_m.append(m[0].transpose(0, 1))
+            outs_a.append(aux[0].transpose(0, 1))
+        m = torch.cat(outs_m, dim=0) if len(outs_m) > 1 else outs_m[0]
+        a = torch.cat(outs_a, dim=0) if len(outs_a) > 1 else outs_a[0]
+        return m.contiguous().float(), a.contiguous().float()
+
+    # ------------------------------------------------------------------ randomness
+    def _reference_draws(self, geo: FoldGeometry, steps: int):
+        """Consumes torch's default CPU generator exactly as the reference's generate() does."""
+        nn.GRUCell(self.rnn1.input_size, self.rnn1.hidden_size)     # :178 get_gru_cell(self.rnn1)
+        nn.GRUCell(self.rnn2.input_size, self.rnn2.hidden_size)     # :179
+        B = geo.n_seg
+        if self.mode == 'MOL':
+            u = torch.empty(steps, 11 * B).uniform_(1e-5, 1.0 - 1e-5)   # distribution.py:106,118
+            return u, None
+        # RAW: Categorical.sample() -> torch.multinomial -> one exponential_() per step (:233-235)
+        e = torch.empty(steps, B, self.n_classes)
+        for t in range(steps):
+            e[t].exponential_()
+        return None, e
+
+    # ------------------------------------------------------------------ the hot path
+    def generate(self, mels, save_path: Union[str, Path, None], batched, target, overlap, mu_law):
+        """Same contract as reference :169-264: returns the float64 waveform of length
+        (T-1)*hop_length, writes it as a float32 wav to `save_path`, leaves the module in
+        train() mode."""
+        t_start = time.time()
+        self.eval()
+        device = self._require_cuda()
+        if self.mode not in ('MOL', 'RAW'):
+            raise RuntimeError("Unknown model mode value - ", self.mode)
+        mu_law = mu_law if self.mode == 'RAW' else False
+        dist_on = torch.distributed.is_available() and torch.distributed.is_initialized()
+        rank = torch.distributed.get_rank() if dist_on else 0
+        world = torch.distributed.get_world_size() if dist_on else 1
+
+        with torch.no_grad():
+            mels = torch.as_tensor(mels, device=device).float()
+            T = mels.size(-1)
+            wave_len = (T - 1) * self.hop_length
+            total_len = T * self.hop_length
+            mels_padded = F.pad(mels, (self.pad, self.pad))                      # :185
+            geo = fold_geometry(total_len, target, overlap) if batched else unbatched_geometry(total_len)
+            if not batched:
+                world_eff, rank_eff = 1, 0      # a single segment does not shard: replicas only
+            else:
+                world_eff, rank_eff = world, rank
+            shard = shard_folds(geo, rank_eff, world_eff, self.hop_length)
+
+            out_local = self._run_segments(mels_padded, geo, shard, device)
+            t_kernel_done = time.time()
+            if world_eff > 1:
+                out_all = gather_segments(out_local, shard, geo)
+            else:
+                out_all = out_local
+            output = out_all.cpu().numpy().astype(np.float64)                    # :243-245
+
+        wav = self._epilogue(output, geo, batched, wave_len, mu_law)
+        if save_path is not None:
+            save_wav(wav, save_path, self.sample_rate)                           # :260
+        self.train()                                                             # :262
+        elapsed = time.time() - t_start
+        self.gen_stats.update(wall_s=elapsed, loop_wall_s=t_kernel_done - t_start, n_seg=geo.n_seg,
+                              seg_len=geo.seg_len, wave_len=wave_len, world=world_eff)
+        if self.gen_verbose and rank == 0:
+            self.gen_display(geo.seg_len - 1, geo.seg_len, geo.n_seg, t_start)
+        return wav
+
+    def _run_segments(self, mels_padded, geo: FoldGeometry, shard, device, *, steps: int = 0,
+                      x_force=None, want_logits: bool = False, draws=None):
+        """Conditioning for this rank's folds + one persistent-kernel launch.
+        Returns the (n_seg_local, S) float32 device tensor of samples (pre-xfade)."""
+        S = steps or geo.seg_len
+        uniforms = expo = None
+        if self.gen_rng == 'torch' or draws is not None:
+            u_all, e_all = draws if draws is not None else self._reference_draws(geo, S)
+            f0, n = shard.seg_first, shard.n_seg
+            B = geo.n_seg
+            if u_all is not None:
+                u_loc = torch.cat([u_all[:, 10 * f0:10 * (f0 + n)], u_all[:, 10 * B + f0:10 * B + f0 + n]], dim=1)
+                uniforms = u_loc.contiguous().to(device, non_blocking=True)
+            if e_all is not None:
+                expo = e_all[:, f0:f0 + n].contiguous().to(device, non_blocking=True)
+        elif self.gen_rng != 'philox':
+            raise ValueError(f"gen_rng must be 'torch' or 'philox', got {self.gen_rng!r}")
+        if shard.n_seg == 0:
+            return torch.zeros((0, S), dtype=torch.float32, device=device)
+        engine = self._get_engine(device)
+        m_up, aux = self.conditioning(mels_padded, shard.frame_lo, shard.frame_hi)
+        off = shard.row_lo - shard.frame_lo * self.hop_length
+        n_rows = shard.row_hi - shard.row_lo
+        m_up = m_up[off:off + n_rows]
+        aux = aux[off:off + n_rows]
+        if off:
+            m_up, aux = m_up.contiguous(), aux.contiguous()
+        out = torch.empty((shard.n_seg, S), dtype=torch.float32, device=device)
+        logits = (torch.empty((S, shard.n_seg, self.n_classes), dtype=torch.float32, device=device)
+                  if want_logits else None)
+        xf = None
+        if x_force is not None:
+            xf = torch.as_tensor(x_force, dtype=torch.float32, device=device).contiguous()
+        engine.generate(mels_up=m_up.data_ptr(), aux=aux.data_ptr(), L=n_rows, n_seg=shard.n_seg,
+                        seg_len=geo.seg_len, seg_stride=geo.seg_stride, out=out.data_ptr(),
+                        seg_first=shard.seg_first, steps=steps,
+                        uniforms=uniforms.data_ptr() if uniforms is not None else 0,
+                        expo=expo.data_ptr() if expo is not None else 0,
+                        philox_seed=int(self.gen_philox_seed), philox_offset=0,
+                        x_force=xf.data_ptr() if xf is not None else 0,
+                        logits_out=logits.data_ptr() if logits is not None else 0,
+                        stream=torch.cuda.current_stream(device).cuda_stream)
+        torch.cuda.current_stream(device).synchronize()
+        engine.check()
+        self.gen_stats.update(engine=engine.name, grid_ctas=engine.grid_ctas, launches=engine.launch_count)
+        del m_up, aux, uniforms, expo, xf
+        return (out, logits) if want_logits else out
+
+    def _epilogue(self, output: np.ndarray, geo: FoldGeometry, batched, wave_len, mu_law) -> np.ndarray:
+        """numpy float64 tail of the reference (:247-258)."""
+        if mu_law:
+            output = decode_mu_law(output, self.n_classes, False)
+        output = self.xfade_and_unfold(output, geo.target, geo.overlap) if batched else output[0]
+        fade_out = np.linspace(1, 0, 20 * self.hop_length)
+        output = output[:wave_len]
+        output[-20 * self.hop_length:] *= fade_out
+        return output
+
+    def generate_many(self, mels_list: Sequence, save_paths: Sequence, target, overlap, mu_law):
+        """Extension: vocode several utterances; each keeps the exact
+        per-utterance result of generate(..., batched=True, ...)."""
+        return [self.generate(m, p, True, target, overlap, mu_law) for m, p in zip(mels_list, save_paths)]
+
+    # ------------------------------------------------------------------ reference helpers kept for callers
+    def gen_display(self, i, seq_len, b_size, start):
+        gen_rate = (i + 1) / (time.time() - start) * b_size / 1000
+        msg = f'| {progbar(i, seq_len)} {i * b_size}/{seq_len * b_size} | Batch Size: {b_size} | ' \
+              f'Gen Rate: {gen_rate:.1f}kHz | '
+        stream(msg)
+
+    def get_gru_cell(self, gru):
+        cell = nn.GRUCell(gru.input_size, gru.hidden_size)
+        cell.weight_hh.data = gru.weight_hh_l0.data
+        cell.weight_ih.data = gru.weight_ih_l0.data
+        cell.bias_hh.data = gru.bias_hh_l0.data
+        cell.bias_ih.data = gru.bias_ih_l0.data
+        return cell
+
+    def pad_tensor(self, x, pad, side='both'):
+        b, t, c = x.size()
+        total = t + 2 * pad if side == 'both' else t + pad
+        padded = torch.zeros(b, total, c, device=x.device)
+        if side in ('before', 'both'):
+            padded[:, pad:pad + t, :] = x
+        elif side == 'after':
+            padded[:, :t, :] = x
+        return padded
+
+    def fold_with_overlap(self, x, target, overlap):
+        """(1, L, F) -> (num_folds, target + 2*overlap, F); materialised form of the strided
+        windows the kernel indexes directly (reference :293-340)."""
+        _, total_len, features = x.size()
+        geo = fold_geometry(total_len, target, overlap)
+        if geo.padded_len != total_len:
+            x = self.pad_tensor(x, geo.padded_len - total_len, side='after')
+        return x[0].unfold(0, geo.seg_len, geo.seg_stride).permute(0, 2, 1).contiguous()
+
+    def xfade_and_unfold(self, y, target, overlap):
+        """Equal-power cross-fade + overlap-add (reference :342-405); mutates y in place like
+        the reference does."""
+        num_folds, length = y.shape
+        target = length - 2 * overlap
+        total_len = num_folds * (target + overlap) + overlap
+        silence_len = overlap // 2
+        fade_len = overlap - silence_len
+        t = np.linspace(-1, 1, fade_len, dtype=np.float64)
+        fade_in = np.concatenate([np.zeros(silence_len), np.sqrt(0.5 * (1 + t))])
+        fade_out = np.concatenate([np.ones(silence_len), np.sqrt(0.5 * (1 - t))])
+        y[:, :overlap] *= fade_in
+        y[:, -overlap:] *= fade_out
+        unfolded = np.zeros(total_len, dtype=np.float64)
+        step = target + overlap
+        for i in range(num_folds):
+            unfolded[i * step:i * step + length] += y[i]
+        return unfolded
+
+    def get_step(self):
+        return self.step.data.item()
+
+    def log(self, path, msg):
+        with open(path, 'a') as f:
+            print(msg, file=f)
+
+    def load(self, path: Union[str, Path]):
+        device = next(self.parameters()).device
+        self.load_state_dict(torch.load(path, map_location=device), strict=False)
+
+    def save(self, path: Union[str, Path]):
+        torch.save(self.state_dict(), path)
+
+    def num_params(self, print_out=True):
+        n = sum(int(np.prod(p.size())) for p in self.parameters() if p.requires_grad) / 1_000_000
+        if print_out:
+            print('Trainable Parameters: %.3fM' % n)
+        return n
+
+    def _flatten_parameters(self):
+        for m in self._to_flatten:
+            m.flatten_parameters()
