@@ -1,0 +1,118 @@
+"""Host-side mirror of the reference interface: WaveRNN surface, hparams singleton, fold /
+xfade helpers, sliced conditioning, failure modes.  CPU only."""
+import inspect
+import io
+import contextlib
+
+import numpy as np
+import pytest
+import torch
+
+import helpers
+from oracle import wavernn_oracle as O
+from oracle import ref_shim
+
+
+def test_ctor_state_dict_layout():
+    m = helpers.make_model(0, "MOL")
+    sd = m.state_dict()
+    assert len(sd) == 148
+    for k, shape in {"I.weight": (512, 113), "rnn1.weight_ih_l0": (1536, 512), "rnn2.weight_ih_l0": (1536, 544),
+                     "fc1.weight": (512, 544), "fc2.weight": (512, 544), "fc3.weight": (30, 512),
+                     "upsample.up_layers.5.weight": (1, 1, 1, 23), "step": (1,)}.items():
+        assert tuple(sd[k].shape) == shape, k
+    assert helpers.make_model(0, "RAW").state_dict()["fc3.weight"].shape == (512, 512)
+    with pytest.raises(RuntimeError):
+        helpers.make_model(0, "nope")
+    assert m.training is True
+    sig = list(inspect.signature(m.generate).parameters)
+    assert sig == ["mels", "save_path", "batched", "target", "overlap", "mu_law"]
+
+
+def test_generate_without_cuda_fails_loudly():
+    m = helpers.make_model(0, "MOL")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m.generate(helpers.make_mel(30), None, True, 2750, 275, False)
+
+
+def test_fold_and_xfade_helpers_match_oracle():
+    m = helpers.make_model(0, "MOL")
+    x = torch.arange(1000 * 3, dtype=torch.float32).reshape(1, 1000, 3)
+    np.testing.assert_array_equal(m.fold_with_overlap(x, 300, 30).numpy(), O.fold_with_overlap(x[0].numpy(), 300, 30))
+    np.testing.assert_array_equal(m.fold_with_overlap(x[:, :1020], 300, 30).numpy(),
+                                  O.fold_with_overlap(x[0, :1020].numpy(), 300, 30))
+    y = np.random.RandomState(0).randn(5, 360)
+    np.testing.assert_allclose(m.xfade_and_unfold(y.copy(), 300, 30), O.xfade_and_unfold(y, 300, 30), atol=1e-15)
+
+
+def test_sliced_conditioning_equals_full_upsample():
+    """Per-rank / chunked conditioning (halo slices) == one UpsampleNetwork call (:186)."""
+    m = helpers.make_model(0, "MOL").eval()
+    mel = helpers.make_mel(61)
+    mp = torch.nn.functional.pad(mel, (2, 2))
+    with torch.no_grad():
+        full_m, full_a = m.upsample(mp)
+        m.gen_upsample_chunk = 16
+        cm, ca = m.conditioning(mp, 0, 61)
+        sm, sa = m.conditioning(mp, 20, 45)
+    np.testing.assert_allclose(cm.numpy(), full_m[0].numpy(), atol=5e-6)
+    np.testing.assert_array_equal(ca.numpy(), full_a[0].numpy())
+    np.testing.assert_allclose(sm.numpy(), full_m[0, 20 * 275:45 * 275].numpy(), atol=5e-6)
+    np.testing.assert_array_equal(sa.numpy(), full_a[0, 20 * 275:45 * 275].numpy())
+    sd = helpers.state_numpy(m)
+    om, oa = O.upsample_network(sd, mp[0].numpy(), pad=2)
+    np.testing.assert_allclose(full_m[0].numpy(), om, atol=5e-6)
+    np.testing.assert_allclose(full_a[0].numpy(), oa, atol=5e-6)
+
+
+def test_forward_training_path_runs():
+    m = helpers.make_model(0, "MOL")
+    x = torch.rand(2, 275 * 3) * 2 - 1
+    mel = torch.rand(2, 80, 3 + 4)
+    out = m(x, mel)
+    assert out.shape == (2, 825, 30) and m.get_step() == 1
+
+
+def test_hparams_singleton_contract(tmp_path):
+    from wavernn_b200.hp import _HParams, DEFAULT_HPARAMS_FILE
+    hp = _HParams()
+    with pytest.raises(AttributeError, match="not configured"):
+        hp.sample_rate
+    hp.configure(DEFAULT_HPARAMS_FILE)
+    assert hp.sample_rate == 22050 and hp.voc_target == 11000 and hp.voc_overlap == 550 and hp.voc_mode == "MOL"
+    with pytest.raises(RuntimeError, match="Cannot reconfigure"):
+        hp.configure(DEFAULT_HPARAMS_FILE)
+    with pytest.raises(FileNotFoundError):
+        _HParams().configure(tmp_path / "nope.py")
+    bad = tmp_path / "x.txt"; bad.write_text("a=1")
+    with pytest.raises(ValueError):
+        _HParams().configure(bad)
+
+
+def test_save_load_roundtrip_and_wav(tmp_path):
+    from wavernn_b200.dsp import save_wav, decode_mu_law
+    m = helpers.make_model(0, "MOL")
+    p = tmp_path / "w.pyt"
+    m.save(p)
+    m2 = helpers.make_model(1, "MOL")
+    m2.load(p)
+    for (k, a), (_, b) in zip(m.state_dict().items(), m2.state_dict().items()):
+        assert torch.equal(a, b), k
+    save_wav(np.linspace(-1, 1, 100), tmp_path / "a.wav", 22050)
+    from scipy.io import wavfile
+    sr, data = wavfile.read(tmp_path / "a.wav")
+    assert sr == 22050 and data.dtype == np.float32 and len(data) == 100
+    g = helpers.load_golden("functions.npz")
+    np.testing.assert_allclose(decode_mu_law(g["mulaw_in"], 512, False), g["mulaw_out"], rtol=1e-15)
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason="reference checkout not mounted")
+def test_public_surface_matches_reference_class():
+    ref = ref_shim.load_reference()
+    import wavernn_b200 as W
+    for name in ("forward", "generate", "get_gru_cell", "pad_tensor", "fold_with_overlap", "xfade_and_unfold",
+                 "get_step", "log", "load", "save", "num_params", "gen_display"):
+        a = inspect.signature(getattr(ref.WaveRNN, name))
+        b = inspect.signature(getattr(W.WaveRNN, name))
+        assert list(a.parameters) == list(b.parameters), name
+    assert list(inspect.signature(ref.WaveRNN.__init__).parameters) == list(inspect.signature(W.WaveRNN.__init__).parameters)

@@ -1,0 +1,154 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle, the engine-arithmetic
+emulation and the committed reference fixtures.  Run on the GPU box: pytest -m gpu.
+
+Stated tolerances (see DESIGN.md "Parity"):
+  * fp32 strict engine vs reference-order oracle, free running: <= 1e-4 (re-association only)
+  * fp16 engine vs its CPU emulation (same rounding points), free running: <= 1e-3
+  * fp16 engine, teacher-forced logits vs reference logits: <= 5e-3
+  * fp16 engine free-running vs reference samples (random-init model, non-chaotic): <= 2e-2
+"""
+import numpy as np
+import pytest
+import torch
+
+import helpers
+from gpu_helpers import run_engine
+from oracle import contract as C
+from oracle import wavernn_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def mol():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    model = helpers.make_model(0, "MOL", "cuda")
+    sd = helpers.state_numpy(model)
+    w = O.hot_weights(sd)
+    mel_p = O.pad_time(helpers.make_mel(30, 0)[0].numpy().T, 2).T
+    m_up, aux = O.upsample_network(sd, mel_p, pad=2)
+    U = helpers.replay_uniforms(1234, 3300, 3)
+    g = helpers.load_golden("mol_batched.npz")
+    return dict(model=model, sd=sd, w=w, m_up=m_up, aux=aux, U=U, g=g,
+                kw=dict(n_seg=3, seg_len=3300, seg_stride=3025))
+
+
+def test_fp32_strict_engine_matches_reference_fixture(mol):
+    out, name = run_engine(mol["model"], mol["m_up"], mol["aux"], uniforms=mol["U"], precision="fp32", **mol["kw"])
+    assert name == "simt-fp32"
+    d = np.abs(out - mol["g"]["raw"])
+    print("fp32 strict vs reference raw: max", d.max())
+    assert d.max() <= 1e-4
+
+
+def test_fp16_engine_matches_its_emulation_and_reference(mol):
+    out, lg, name = run_engine(mol["model"], mol["m_up"], mol["aux"], uniforms=mol["U"], want_logits=True, **mol["kw"])
+    emu, lemu = C.generate_segments(mol["w"], mol["m_up"], mol["aux"], uniforms=mol["U"], precision="fp16",
+                                    want_logits=True, **mol["kw"])
+    d_emu, d_ref = np.abs(out - emu), np.abs(out - mol["g"]["raw"])
+    print(f"{name}: vs emulation max {d_emu.max():.3e}; vs reference max {d_ref.max():.3e}; "
+          f"logits vs emulation {np.abs(lg - lemu).max():.3e}")
+    assert d_emu.max() <= 1e-3
+    assert d_ref.max() <= 2e-2
+    assert np.isfinite(out).all() and np.abs(out).max() <= 1.0
+
+
+@pytest.mark.parametrize("precision,tol", [("fp16", 5e-3), ("bf16", 3e-2), ("fp32", 1e-4)])
+def test_teacher_forced_logits(mol, precision, tol):
+    g = mol["g"]
+    out, lg, name = run_engine(mol["model"], mol["m_up"], mol["aux"], uniforms=mol["U"], x_force=g["raw"].T.copy(),
+                               want_logits=True, steps=600, precision=precision, **mol["kw"])
+    err = np.abs(lg - g["logits"]).max()
+    print(f"{name} teacher-forced logits max err {err:.3e}")
+    assert err <= tol
+
+
+def test_unbatched_matches_reference_fixture():
+    g = helpers.load_golden("mol_unbatched.npz")
+    model = helpers.make_model(0, "MOL", "cuda")
+    sd = helpers.state_numpy(model)
+    mel_p = O.pad_time(helpers.make_mel(22, 1)[0].numpy().T, 2).T
+    m_up, aux = O.upsample_network(sd, mel_p, pad=2)
+    L = 22 * 275
+    U = helpers.replay_uniforms(77, L, 1)
+    for prec, tol in (("fp32", 1e-4), ("fp16", 2e-2)):
+        out, name = run_engine(model, m_up, aux, n_seg=1, seg_len=L, seg_stride=L, uniforms=U, precision=prec)
+        d = np.abs(out - g["raw"]).max()
+        print(name, "unbatched vs reference", d)
+        assert d <= tol
+
+
+def test_generate_api_end_to_end_matches_reference_wav(mol, tmp_path):
+    """The public call: WaveRNN.generate(mels, save_path, batched, target, overlap, mu_law)."""
+    model, g = mol["model"], mol["g"]
+    torch.manual_seed(1234)
+    path = tmp_path / "out.wav"
+    wav = model.generate(helpers.make_mel(30, 0), path, True, 2750, 275, True)   # mu_law ignored for MOL
+    assert wav.dtype == np.float64 and wav.shape == g["wav"].shape and model.training
+    d = np.abs(wav - g["wav"]).max()
+    print("generate() vs reference wav: max", d, "engine", model.gen_stats["engine"])
+    assert d <= 2e-2
+    from scipy.io import wavfile
+    sr, data = wavfile.read(path)
+    assert sr == 22050 and len(data) == len(wav)
+    model.gen_precision = "fp32"
+    torch.manual_seed(1234)
+    wav32 = model.generate(helpers.make_mel(30, 0), None, True, 2750, 275, False)
+    model.gen_precision = "fp16"
+    assert np.abs(wav32 - g["wav"]).max() <= 1e-4
+
+
+def test_raw_head_matches_reference_fixture():
+    g = helpers.load_golden("raw_batched.npz")
+    expo = helpers.replay_expo(1234, 3300, 3, 512)
+    if not np.array_equal(expo[:8], g["expo_head"]):
+        pytest.skip("torch exponential_() stream differs on this host")
+    model = helpers.make_model(0, "RAW", "cuda")
+    sd = helpers.state_numpy(model)
+    mel_p = O.pad_time(helpers.make_mel(30, 0)[0].numpy().T, 2).T
+    m_up, aux = O.upsample_network(sd, mel_p, pad=2)
+    for prec, frac in (("fp32", 0.995), ("fp16", 0.97)):
+        out, lg, name = run_engine(model, m_up, aux, n_seg=3, seg_len=3300, seg_stride=3025, expo=expo,
+                                   x_force=g["raw"].T.copy(), want_logits=True, precision=prec)
+        same = (out == g["raw"]).mean()
+        lerr = np.abs(lg[:64] - g["logits"]).max()
+        print(f"{name} RAW teacher-forced: identical class picks {same:.4f}, logits err {lerr:.3e}")
+        assert same >= frac and lerr <= (1e-4 if prec == "fp32" else 5e-3)
+    # free running through the public API incl. mu-law expansion
+    torch.manual_seed(1234)
+    wav = model.generate(helpers.make_mel(30, 0), None, True, 2750, 275, True)
+    assert wav.shape == g["wav"].shape and np.isfinite(wav).all() and np.abs(wav).max() <= 1.0
+
+
+def test_many_folds_multiple_tiles_and_zero_padded_tail():
+    """70 folds (3 tiles of 32, sampler tiles on different CTAs), stream shorter than the last
+    folds need (rows >= L read as zero, like fold_with_overlap's padding)."""
+    model = helpers.make_model(3, "MOL", "cuda")
+    w = O.hot_weights(helpers.state_numpy(model))
+    rs = np.random.RandomState(0)
+    n_seg, seg_len, stride = 70, 96, 64
+    L = 69 * stride + 40                       # last fold runs 56 rows past the end
+    m_up = rs.rand(L, 80).astype(np.float32)
+    aux = rs.randn(L, 128).astype(np.float32)
+    U = helpers.replay_uniforms(5, seg_len, n_seg)
+    kw = dict(n_seg=n_seg, seg_len=seg_len, seg_stride=stride, uniforms=U)
+    ref = O.generate_segments(w, m_up, aux, **kw)
+    out32, _ = run_engine(model, m_up, aux, precision="fp32", **kw)
+    assert np.abs(out32 - ref).max() <= 1e-4
+    out16, name = run_engine(model, m_up, aux, precision="fp16", **kw)
+    emu = C.generate_segments(w, m_up, aux, precision="fp16", **kw)
+    print(name, "70 folds: vs emulation", np.abs(out16 - emu).max(), "vs oracle", np.abs(out16 - ref).max())
+    assert np.abs(out16 - emu).max() <= 1e-3
+
+
+def test_philox_mode_is_deterministic_and_shard_invariant(mol):
+    kw = dict(n_seg=3, seg_len=3300, seg_stride=3025, steps=400)
+    a, _ = run_engine(mol["model"], mol["m_up"], mol["aux"], philox_seed=42, **kw)
+    b, _ = run_engine(mol["model"], mol["m_up"], mol["aux"], philox_seed=42, **kw)
+    c, _ = run_engine(mol["model"], mol["m_up"], mol["aux"], philox_seed=43, **kw)
+    assert np.array_equal(a, b) and not np.array_equal(a, c)
+    assert np.isfinite(a).all() and np.abs(a).max() <= 1.0 and a.std() > 0.05
+    # folds [1,3) run on their own (as another rank would) reproduce rows 1..2
+    sub, _ = run_engine(mol["model"], mol["m_up"][3025:], mol["aux"][3025:], philox_seed=42, seg_first=1,
+                        n_seg=2, seg_len=3300, seg_stride=3025, steps=400)
+    assert np.array_equal(sub, a[1:])

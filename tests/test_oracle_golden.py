@@ -1,0 +1,108 @@
+"""Pins the numpy oracle against fixtures produced by the unmodified reference
+(tests/golden/make_golden.py).  CPU only."""
+import numpy as np
+import pytest
+import torch
+
+import helpers
+from oracle import wavernn_oracle as O
+
+
+def test_fold_matches_reference_fixture():
+    g = helpers.load_golden("functions.npz")
+    x = np.arange(1000 * 3, dtype=np.float32).reshape(1000, 3)
+    np.testing.assert_array_equal(O.fold_with_overlap(x, 300, 30), g["fold_pad"])       # padded last fold
+    np.testing.assert_array_equal(O.fold_with_overlap(x[:3 * 330 + 30], 300, 30), g["fold_exact"])
+    # the reference over-pads (target + 2*overlap - remaining = 50 rows) although 20 would do (:322-330)
+    assert O.fold_geometry(1000, 300, 30) == (g["fold_pad"].shape[0], 1050)
+
+
+def test_xfade_and_mulaw_match_reference_fixture():
+    g = helpers.load_golden("functions.npz")
+    np.testing.assert_allclose(O.xfade_and_unfold(g["xfade_in"], 300, 30), g["xfade_out"], rtol=0, atol=1e-15)
+    np.testing.assert_allclose(O.decode_mu_law(g["mulaw_in"], 512), g["mulaw_out"], rtol=1e-15, atol=0)
+
+
+def test_mol_sampler_matches_reference_fixture():
+    g = helpers.load_golden("functions.npz")
+    logits = g["mol_logits"][0].T                                  # (T=64, 30)
+    s = O.mol_sample(logits.astype(np.float32), g["mol_u_mix"][0], g["mol_u_log"][0])
+    np.testing.assert_allclose(s, g["mol_sample"][0], rtol=0, atol=2e-6)
+
+
+def _oracle_run(mode, g, mel_T, mel_seed, batched, target, overlap, seed, **kw):
+    model = helpers.make_model(0, mode)
+    sd = helpers.state_numpy(model)
+    w = O.hot_weights(sd)
+    mel = helpers.make_mel(mel_T, mel_seed)[0].numpy()
+    L = mel_T * 275
+    B = O.fold_geometry(L, target, overlap)[0] if batched else 1
+    S = target + 2 * overlap if batched else L
+    if mode == "MOL":
+        kw["uniforms"] = helpers.replay_uniforms(seed, S, B)
+    else:
+        kw["expo"] = helpers.replay_expo(seed, S, B, 512)
+        kw["uniforms"] = None
+    return O.generate(w, sd, mel, batched=batched, target=target, overlap=overlap, mode=mode,
+                      return_pre=True, **kw), sd
+
+
+@pytest.mark.parametrize("mode", ["MOL", "RAW"])
+def test_init_weights_equal_reference_init(mode):
+    """Our module, built under the same seed, holds exactly the reference's initial weights --
+    the precondition for regenerating weights on the GPU box instead of shipping them."""
+    fp = helpers.load_golden(f"weights_{mode.lower()}_seed0.npz")
+    mine = helpers.weight_fingerprint(helpers.state_numpy(helpers.make_model(0, mode)))
+    assert set(fp.files) == set(mine)
+    for k in fp.files:
+        np.testing.assert_array_equal(fp[k], mine[k], err_msg=k)
+
+
+def test_oracle_mol_batched_matches_reference_run():
+    g = helpers.load_golden("mol_batched.npz")
+    (wav, pre), sd = _oracle_run("MOL", g, 30, 0, True, 2750, 275, 1234)
+    assert pre.shape == g["raw"].shape == (3, 3300)
+    np.testing.assert_allclose(pre, g["raw"], rtol=0, atol=2e-6)
+    np.testing.assert_allclose(wav, g["wav"], rtol=0, atol=2e-6)
+    # conditioning network restatement
+    mel_p = O.pad_time(helpers.make_mel(30, 0)[0].numpy().T, 2).T
+    m_up, aux = O.upsample_network(sd, mel_p, pad=2)
+    np.testing.assert_allclose(m_up[::97], g["mels_up_rows"], atol=5e-6)
+    np.testing.assert_allclose(aux[::97], g["aux_rows"], atol=5e-6)
+
+
+def test_oracle_mol_unbatched_matches_reference_run():
+    g = helpers.load_golden("mol_unbatched.npz")
+    (wav, pre), _ = _oracle_run("MOL", g, 22, 1, False, 11000, 550, 77)
+    np.testing.assert_allclose(pre, g["raw"], rtol=0, atol=2e-6)
+    np.testing.assert_allclose(wav, g["wav"], rtol=0, atol=2e-6)
+
+
+def test_oracle_raw_head_matches_reference_run():
+    g = helpers.load_golden("raw_batched.npz")
+    expo = helpers.replay_expo(1234, 3300, 3, 512)
+    if abs(float(expo.astype(np.float64).sum()) - float(g["expo_sum"])) > 1e-6 or not np.array_equal(expo[:8], g["expo_head"]):
+        pytest.skip("torch exponential_() stream differs on this host: RAW draws cannot be replayed")
+    (wav, pre), _ = _oracle_run("RAW", g, 30, 0, True, 2750, 275, 1234, mu_law=True)
+    assert (pre == g["raw"]).mean() > 0.999        # class picks are exact except fp near-ties
+    np.testing.assert_allclose(wav, g["wav"], rtol=0, atol=1e-2)
+
+
+def test_teacher_forced_logits_match_reference():
+    g = helpers.load_golden("mol_batched.npz")
+    model = helpers.make_model(0, "MOL")
+    sd = helpers.state_numpy(model)
+    w = O.hot_weights(sd)
+    mel_p = O.pad_time(helpers.make_mel(30, 0)[0].numpy().T, 2).T
+    m_up, aux = O.upsample_network(sd, mel_p, pad=2)
+    U = helpers.replay_uniforms(1234, 3300, 3)
+    _, logits = O.generate_segments(w, m_up, aux, n_seg=3, seg_len=3300, seg_stride=3025, uniforms=U,
+                                    x_force=g["raw"].T.copy(), want_logits=True, steps=600)
+    np.testing.assert_allclose(logits, g["logits"], rtol=0, atol=5e-6)
+
+
+def test_short_input_raises_like_reference():
+    """T=18 frames -> wave_len < 20*hop: the fade-out broadcast fails."""
+    with pytest.raises(ValueError):
+        O.epilogue(np.zeros((1, 18 * 275), np.float32), batched=False, target=0, overlap=0, wave_len=17 * 275,
+                   hop_length=275, mode="MOL", mu_law=False, n_classes=30)

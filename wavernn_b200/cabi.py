@@ -14,7 +14,7 @@ LIB_PATH = Path(__file__).with_name(LIB_NAME)
 
 WRNN_OK, WRNN_E_INVALID, WRNN_E_CUDA, WRNN_E_NO_DEVICE, WRNN_E_WATCHDOG, WRNN_E_BUSY = 0, -1, -2, -3, -4, -5
 MODE_MOL, MODE_RAW = 0, 1
-PREC_BF16, PREC_FP32 = 0, 1
+PREC_F16, PREC_FP32, PREC_BF16 = 0, 1, 2
 ENGINE_AUTO, ENGINE_SIMT, ENGINE_TCGEN05 = 0, 1, 2
 ABI_VERSION = 1
 
@@ -110,12 +110,12 @@ class Engine:
     (torch tensors, fp32, contiguous, host or device) or raw ints."""
 
     def __init__(self, weights: dict, *, rnn_dims=512, fc_dims=512, feat_dims=80, aux_dims=32, n_classes=30,
-                 mode="MOL", precision="bf16", engine="auto", device: int = 0):
+                 mode="MOL", precision="fp16", engine="auto", device: int = 0):
         self._h = C.c_void_p()
         self.lib = load()
         cfg = WrnnCfg(rnn_dims, fc_dims, feat_dims, aux_dims, n_classes,
                       {"MOL": MODE_MOL, "RAW": MODE_RAW}[mode],
-                      {"bf16": PREC_BF16, "fp32": PREC_FP32}[precision],
+                      {"fp16": PREC_F16, "bf16": PREC_BF16, "fp32": PREC_FP32}[precision],
                       {"auto": ENGINE_AUTO, "simt": ENGINE_SIMT, "tcgen05": ENGINE_TCGEN05}[engine])
         w = WrnnWeights()
         keep = []

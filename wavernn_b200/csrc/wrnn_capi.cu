@@ -1,0 +1,164 @@
+// wrnn_capi.cu -- the extern "C" surface declared in include/wavernn_b200.h.
+#include <cuda_runtime.h>
+
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "wrnn_engine.h"
+
+namespace wrnn {
+static thread_local std::string g_last_error;
+void set_error(const std::string& msg) { g_last_error = msg; }
+
+static int fetch(std::vector<float>& dst, const float* src, size_t n, const char* what) {
+  if (!src) { set_error(std::string("null weight pointer: ") + what); return WRNN_E_INVALID; }
+  dst.resize(n);
+  // cudaMemcpyDefault resolves host or device pointers through UVA
+  cudaError_t e = cudaMemcpy(dst.data(), src, n * sizeof(float), cudaMemcpyDefault);
+  if (e != cudaSuccess) { set_error(std::string("copying ") + what + ": " + cudaGetErrorString(e)); return WRNN_E_CUDA; }
+  return WRNN_OK;
+}
+}  // namespace wrnn
+
+using namespace wrnn;
+
+extern "C" {
+
+int wrnn_abi_version(void) { return WRNN_ABI_VERSION; }
+const char* wrnn_last_error(void) { return g_last_error.c_str(); }
+
+int wrnn_create(wrnn_t** out, const wrnn_cfg* cfg, const wrnn_weights* w, int device) {
+  if (!out || !cfg || !w) { set_error("null argument"); return WRNN_E_INVALID; }
+  *out = nullptr;
+  if (cfg->rnn_dims != H || cfg->fc_dims != H || cfg->feat_dims != FEAT || cfg->aux_dims != AUXD) {
+    set_error("unsupported dims: the kernels are specialised for rnn_dims=fc_dims=512, feat_dims=80, "
+              "aux_dims=32 (hparams.py:46-50)");
+    return WRNN_E_INVALID;
+  }
+  if (cfg->mode != WRNN_MODE_MOL && cfg->mode != WRNN_MODE_RAW) { set_error("Unknown model mode value"); return WRNN_E_INVALID; }
+  if (cfg->n_classes <= 0) { set_error("n_classes must be positive"); return WRNN_E_INVALID; }
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev <= 0 || device < 0 || device >= n_dev) {
+    cudaGetLastError();
+    set_error("no CUDA device: wavernn_b200 has no CPU fallback");
+    return WRNN_E_NO_DEVICE;
+  }
+  WRNN_CUDA_OK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  WRNN_CUDA_OK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    set_error(std::string("device '") + prop.name + "' is sm_" + std::to_string(prop.major * 10 + prop.minor) +
+              "; this library is built for sm_100a only");
+    return WRNN_E_NO_DEVICE;
+  }
+  HostWeights hw;
+  hw.n_classes = cfg->n_classes;
+  const size_t W2W = H + AUXD;
+  int rc;
+#define FETCH(field, src, n) if ((rc = fetch(hw.field, w->src, (n), #src)) != WRNN_OK) return rc
+  FETCH(I_w, I_weight, (size_t)H * (1 + F1IN)); FETCH(I_b, I_bias, H);
+  FETCH(w1i, rnn1_weight_ih, (size_t)G3 * H); FETCH(w1h, rnn1_weight_hh, (size_t)G3 * H);
+  FETCH(b1i, rnn1_bias_ih, G3); FETCH(b1h, rnn1_bias_hh, G3);
+  FETCH(w2i, rnn2_weight_ih, (size_t)G3 * W2W); FETCH(w2h, rnn2_weight_hh, (size_t)G3 * H);
+  FETCH(b2i, rnn2_bias_ih, G3); FETCH(b2h, rnn2_bias_hh, G3);
+  FETCH(f1w, fc1_weight, (size_t)H * W2W); FETCH(f1b, fc1_bias, H);
+  FETCH(f2w, fc2_weight, (size_t)H * W2W); FETCH(f2b, fc2_bias, H);
+  FETCH(f3w, fc3_weight, (size_t)cfg->n_classes * H); FETCH(f3b, fc3_bias, cfg->n_classes);
+#undef FETCH
+  Engine* eng = nullptr;
+  int engine = cfg->engine;
+  if (cfg->precision == WRNN_PREC_FP32) {
+    if (engine == WRNN_ENGINE_TCGEN05) { set_error("fp32 strict arithmetic is served by the SIMT engine only"); return WRNN_E_INVALID; }
+    engine = WRNN_ENGINE_SIMT;
+  }
+  if (engine == WRNN_ENGINE_AUTO) engine = WRNN_ENGINE_TCGEN05;
+  if (engine == WRNN_ENGINE_TCGEN05) {
+    rc = make_tc_engine(*cfg, hw, device, &eng);
+    if (rc != WRNN_OK && cfg->engine == WRNN_ENGINE_AUTO && rc == WRNN_E_INVALID) {
+      // configuration outside the tensor-core engine's envelope: AUTO may pick the SIMT engine
+      rc = make_simt_engine(*cfg, hw, device, &eng);
+    }
+  } else {
+    rc = make_simt_engine(*cfg, hw, device, &eng);
+  }
+  if (rc != WRNN_OK) return rc;
+  wrnn_handle* h = new (std::nothrow) wrnn_handle();
+  if (!h) { delete eng; set_error("out of host memory"); return WRNN_E_INVALID; }
+  h->engine = eng;
+  *out = h;
+  return WRNN_OK;
+}
+
+void wrnn_destroy(wrnn_t* h) {
+  if (!h) return;
+  if (h->d_stage) cudaFree(h->d_stage);
+  delete h->engine;
+  delete h;
+}
+
+static int validate(const wrnn_t* h, const wrnn_job* job, bool host) {
+  if (!h || !h->engine || !job) { set_error("null handle or job"); return WRNN_E_INVALID; }
+  if (!job->mels_up || !job->aux || !job->out) { set_error("mels_up, aux and out are required"); return WRNN_E_INVALID; }
+  if (job->n_seg <= 0 || job->seg_len <= 0 || job->L <= 0 || job->seg_stride <= 0) {
+    set_error("n_seg, seg_len, L and seg_stride must be positive"); return WRNN_E_INVALID;
+  }
+  if (job->steps < 0 || job->steps > job->seg_len) { set_error("steps must be in [0, seg_len]"); return WRNN_E_INVALID; }
+  (void)host;
+  return WRNN_OK;
+}
+
+int wrnn_generate(wrnn_t* h, const wrnn_job* job, void* stream) {
+  int rc = validate(h, job, false);
+  if (rc != WRNN_OK) return rc;
+  return h->engine->generate(*job, static_cast<cudaStream_t>(stream));
+}
+
+int wrnn_check(wrnn_t* h) {
+  if (!h || !h->engine) { set_error("null handle"); return WRNN_E_INVALID; }
+  return h->engine->check();
+}
+
+int wrnn_generate_host(wrnn_t* h, const wrnn_job* job) {
+  int rc = validate(h, job, true);
+  if (rc != WRNN_OK) return rc;
+  Engine* e = h->engine;
+  WRNN_CUDA_OK(cudaSetDevice(e->device));
+  const size_t S = job->steps > 0 ? job->steps : job->seg_len;
+  const size_t B = job->n_seg, NC = e->cfg.n_classes;
+  const size_t n_mel = (size_t)job->L * FEAT, n_aux = (size_t)job->L * 4 * AUXD;
+  const size_t n_uni = job->uniforms ? S * 11 * B : 0, n_exp = job->expo ? S * B * NC : 0;
+  const size_t n_xf = job->x_force ? S * B : 0, n_out = B * S, n_log = job->logits_out ? S * B * NC : 0;
+  const size_t total = (n_mel + n_aux + n_uni + n_exp + n_xf + n_out + n_log) * sizeof(float);
+  if (total > h->stage_bytes) {
+    if (h->d_stage) cudaFree(h->d_stage);
+    h->d_stage = nullptr; h->stage_bytes = 0;
+    WRNN_CUDA_OK(cudaMalloc(&h->d_stage, total));
+    h->stage_bytes = total;
+  }
+  float* d = static_cast<float*>(h->d_stage);
+  wrnn_job dj = *job;
+  auto up = [&](const float* src, size_t n) -> float* {
+    if (!n) return nullptr;
+    float* p = d; d += n;
+    cudaMemcpyAsync(p, src, n * sizeof(float), cudaMemcpyHostToDevice, 0);
+    return p;
+  };
+  dj.mels_up = up(job->mels_up, n_mel); dj.aux = up(job->aux, n_aux);
+  dj.uniforms = up(job->uniforms, n_uni); dj.expo = up(job->expo, n_exp); dj.x_force = up(job->x_force, n_xf);
+  dj.out = d; d += n_out;
+  dj.logits_out = n_log ? d : nullptr;
+  rc = e->generate(dj, 0);
+  if (rc != WRNN_OK) return rc;
+  WRNN_CUDA_OK(cudaMemcpyAsync(job->out, dj.out, n_out * sizeof(float), cudaMemcpyDeviceToHost, 0));
+  if (n_log) WRNN_CUDA_OK(cudaMemcpyAsync(job->logits_out, dj.logits_out, n_log * sizeof(float), cudaMemcpyDeviceToHost, 0));
+  WRNN_CUDA_OK(cudaStreamSynchronize(0));
+  return e->check();
+}
+
+const char* wrnn_engine_name(const wrnn_t* h) { return (h && h->engine) ? h->engine->name() : ""; }
+int wrnn_grid_ctas(const wrnn_t* h) { return (h && h->engine) ? h->engine->grid_ctas() : 0; }
+int64_t wrnn_launch_count(const wrnn_t* h) { return (h && h->engine) ? h->engine->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,47 @@
+// wrnn_engine.h -- internal C++ interface between the C ABI (wrnn_capi.cu) and the engines.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <string>
+
+#include "../../include/wavernn_b200.h"
+#include "wrnn_fold.h"
+
+namespace wrnn {
+
+void set_error(const std::string& msg);          // thread-local last error (wrnn_capi.cu)
+
+#define WRNN_CUDA_OK(expr)                                                                   \
+  do {                                                                                        \
+    cudaError_t _e = (expr);                                                                  \
+    if (_e != cudaSuccess) {                                                                  \
+      ::wrnn::set_error(std::string(#expr) + " failed: " + cudaGetErrorString(_e));           \
+      return WRNN_E_CUDA;                                                                     \
+    }                                                                                         \
+  } while (0)
+
+class Engine {
+ public:
+  virtual ~Engine() {}
+  virtual int generate(const wrnn_job& job, cudaStream_t stream) = 0;   // async
+  virtual int check() = 0;                                              // after stream sync
+  virtual const char* name() const = 0;
+  virtual int grid_ctas() const = 0;
+  int64_t launches = 0;
+  int device = 0;
+  wrnn_cfg cfg{};
+};
+
+// SIMT engine: CUDA-core FMA contractions, fp32-strict or bf16-operand arithmetic.
+int make_simt_engine(const wrnn_cfg& cfg, const HostWeights& w, int device, Engine** out);
+// tcgen05 engine: 5th-gen tensor-core contractions with TMEM accumulators (bf16 operands).
+int make_tc_engine(const wrnn_cfg& cfg, const HostWeights& w, int device, Engine** out);
+
+}  // namespace wrnn
+
+struct wrnn_handle {
+  wrnn::Engine* engine = nullptr;
+  // staging for wrnn_generate_host
+  void* d_stage = nullptr;
+  size_t stage_bytes = 0;
+};
