@@ -1,0 +1,104 @@
+// xchg_probe.cu -- measures the inter-SM exchange primitives the persistent kernel is built on
+// (128 co-resident CTAs, L2-resident buffers):
+//   A  counter barrier: red.release.gpu + ld.acquire.gpu polling by one thread per CTA
+//   B  publish (19 x 8 B per CTA) + counter barrier + gather of the 24 KB image by all threads
+//   C  like B but the gather is one cp.async.bulk (TMA 1-D) issued by one thread
+//   D  flag-in-data: every 16 B chunk carries the step tag; consumers poll the data itself
+// Prints average cycles per round seen by CTA 0.  GPU only.
+#include <cooperative_groups.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__); exit(2); } } while (0)
+
+constexpr int P = 128, NT = 256, ROUNDS = 2000, IMG = 24576;   // 3 row groups x 8 KB
+
+__device__ __forceinline__ unsigned ld_acq(const unsigned* p) { unsigned v; asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ void red_rel(unsigned* p) { asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p) : "memory"); }
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ bool barrier(unsigned* ctr, unsigned target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    red_rel(ctr);
+    long long t0 = clock64();
+    while (ld_acq(ctr) < target) if (clock64() - t0 > (1ll << 31)) break;
+  }
+  __syncthreads();
+  return true;
+}
+
+__global__ void __launch_bounds__(NT, 1) probe(unsigned* ctr, unsigned char* img, long long* result, int mode) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ uint64_t mbar;
+  const int cta = blockIdx.x, tid = threadIdx.x;
+  unsigned nb = 0;
+  if (tid == 0) { asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&mbar))); asm volatile("fence.mbarrier_init.release.cluster;"); }
+  barrier(ctr, ++nb * P);
+  const long long t0 = clock64();
+  unsigned acc = 0;
+  for (int r = 0; r < ROUNDS; ++r) {
+    unsigned char* buf = img + (size_t)(r & 1) * IMG * 2;
+    if (mode == 0) {
+      barrier(ctr, ++nb * P);
+    } else if (mode == 1 || mode == 2) {
+      // publish: 19 folds x 8 bytes (4 halfs of this CTA's units)
+      if (tid < 19) *reinterpret_cast<uint2*>(buf + (tid / 8) * 8192 + (cta / 2) * 128 + (tid % 8) * 16 + (cta % 2) * 8) = make_uint2(r, cta);
+      barrier(ctr, ++nb * P);
+      if (mode == 1) {
+        for (int i = tid; i < IMG / 16; i += NT) reinterpret_cast<int4*>(smem)[i] = __ldcg(reinterpret_cast<const int4*>(buf) + i);
+        __syncthreads();
+      } else {
+        if (tid == 0) {
+          asm volatile("fence.proxy.async.global;" ::: "memory");
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(&mbar)), "r"(IMG) : "memory");
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                       :: "r"(smem_u32(smem)), "l"(buf), "r"(IMG), "r"(smem_u32(&mbar)) : "memory");
+        }
+        asm volatile("{\n\t.reg .pred p;\n\tW_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra D_%=;\n\tbra W_%=;\n\tD_%=:\n\t}\n"
+                     :: "r"(smem_u32(&mbar)), "r"(r & 1) : "memory");
+      }
+      acc += reinterpret_cast<unsigned*>(smem)[(tid * 4) % (IMG / 4)];
+    } else {
+      // flag-in-data: each 16 B chunk = {payload x3, tag}; every CTA owns chunks cta*12 .. cta*12+11 (12*128 = 1536 = IMG/16)
+      const unsigned tag = (unsigned)r + 1;
+      if (tid < 12) {
+        int4 v = make_int4(cta, tid, r, (int)tag);
+        asm volatile("st.global.cg.v4.s32 [%0], {%1,%2,%3,%4};" :: "l"(reinterpret_cast<int4*>(buf) + cta * 12 + tid), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+      }
+      for (int i = tid; i < IMG / 16; i += NT) {
+        int4 v;
+        long long tw = clock64();
+        do {
+          asm volatile("ld.global.cg.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(reinterpret_cast<const int4*>(buf) + i) : "memory");
+        } while ((unsigned)v.w != tag && clock64() - tw < (1ll << 31));
+        reinterpret_cast<int4*>(smem)[i] = v;
+      }
+      __syncthreads();
+      acc += reinterpret_cast<unsigned*>(smem)[(tid * 4) % (IMG / 4)];
+    }
+  }
+  const long long t1 = clock64();
+  if (cta == 0 && tid == 0) { result[mode] = (t1 - t0) / ROUNDS; result[8 + mode] = acc; }
+}
+
+int main() {
+  unsigned* ctr; unsigned char* img; long long* res;
+  CK(cudaMalloc(&ctr, 64)); CK(cudaMalloc(&img, IMG * 4)); CK(cudaMalloc(&res, 256));
+  CK(cudaMemset(res, 0, 256));
+  CK(cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, IMG + 1024));
+  const char* names[] = {"A counter barrier only", "B publish + barrier + LDG gather 24KB", "C publish + barrier + TMA bulk gather 24KB",
+                         "D flag-in-data gather 24KB (no barrier)"};
+  for (int mode = 0; mode < 4; ++mode) {
+    CK(cudaMemset(ctr, 0, 64)); CK(cudaMemset(img, 0, IMG * 4));
+    void* args[] = {&ctr, &img, &res, &mode};
+    CK(cudaLaunchCooperativeKernel((const void*)probe, dim3(P), dim3(NT), args, IMG + 1024, 0));
+    CK(cudaDeviceSynchronize());
+    long long h[16]; CK(cudaMemcpy(h, res, 128, cudaMemcpyDeviceToHost));
+    printf("%-45s : %6lld cycles/round\n", names[mode], h[mode]);
+  }
+  int clk = 0; cudaDeviceGetAttribute(&clk, cudaDevAttrClockRate, 0);
+  printf("(SM clock attr %d kHz)\n", clk);
+  return 0;
+}

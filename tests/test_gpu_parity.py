@@ -155,3 +155,60 @@ def test_philox_mode_is_deterministic_and_shard_invariant(mol):
     sub, _ = run_engine(mol["model"], mol["m_up"][3025:], mol["aux"][3025:], philox_seed=42, seg_first=1,
                         n_seg=2, seg_len=3300, seg_stride=3025, steps=400)
     assert np.array_equal(sub, a[1:])
+
+
+# ---------------------------------------------------------------------------------------------
+# tcgen05 engine (explicitly selected, so a silent fall-through to the SIMT engine cannot pass)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("precision", ["fp16", "bf16"])
+def test_tcgen05_engine_matches_emulation_and_reference(mol, precision):
+    out, lg, name = run_engine(mol["model"], mol["m_up"], mol["aux"], uniforms=mol["U"], want_logits=True,
+                               precision=precision, engine="tcgen05", **mol["kw"])
+    assert name == f"tcgen05-{precision}"
+    emu, lemu = C.generate_segments(mol["w"], mol["m_up"], mol["aux"], uniforms=mol["U"], precision=precision,
+                                    want_logits=True, **mol["kw"])
+    d_emu, d_ref = np.abs(out - emu), np.abs(out - mol["g"]["raw"])
+    print(f"{name}: vs emulation max {d_emu.max():.3e} (logits {np.abs(lg - lemu).max():.3e}); vs reference max {d_ref.max():.3e}")
+    tol_emu, tol_ref = (1e-3, 2e-2) if precision == "fp16" else (2e-2, 5e-2)
+    assert np.isfinite(out).all()
+    assert d_emu.max() <= tol_emu and d_ref.max() <= tol_ref
+
+
+def test_tcgen05_teacher_forced_logits_and_simt_agreement(mol):
+    g = mol["g"]
+    kw = dict(uniforms=mol["U"], x_force=g["raw"].T.copy(), want_logits=True, steps=600, **mol["kw"])
+    out_t, lg_t, name = run_engine(mol["model"], mol["m_up"], mol["aux"], engine="tcgen05", **kw)
+    out_s, lg_s, _ = run_engine(mol["model"], mol["m_up"], mol["aux"], engine="simt", **kw)
+    print(f"{name} teacher-forced logits: vs reference {np.abs(lg_t - g['logits']).max():.3e}, vs simt-fp16 {np.abs(lg_t - lg_s).max():.3e}")
+    assert np.abs(lg_t - g["logits"]).max() <= 5e-3
+    assert np.abs(lg_t - lg_s).max() <= 1e-3          # same rounding contract, different accumulation order
+
+
+@pytest.mark.parametrize("n_seg", [1, 20, 33, 64])
+def test_tcgen05_fold_counts_and_zero_padded_tail(n_seg):
+    model = helpers.make_model(3, "MOL", "cuda")
+    w = O.hot_weights(helpers.state_numpy(model))
+    rs = np.random.RandomState(n_seg)
+    seg_len, stride = 160, 100
+    L = (n_seg - 1) * stride + 90                      # the last fold runs 70 rows past the end
+    m_up = rs.rand(L, 80).astype(np.float32)
+    aux = rs.randn(L, 128).astype(np.float32)
+    U = helpers.replay_uniforms(5, seg_len, n_seg)
+    kw = dict(n_seg=n_seg, seg_len=seg_len, seg_stride=stride, uniforms=U)
+    out, name = run_engine(model, m_up, aux, engine="tcgen05", **kw)
+    emu = C.generate_segments(w, m_up, aux, precision="fp16", **kw)
+    ref = O.generate_segments(w, m_up, aux, **kw)
+    print(f"{name} n_seg={n_seg}: vs emulation {np.abs(out - emu).max():.3e}, vs oracle {np.abs(out - ref).max():.3e}")
+    assert np.abs(out - emu).max() <= 1e-3
+
+
+def test_auto_engine_picks_tcgen05_for_small_jobs_and_falls_back_for_large(mol):
+    out, name = run_engine(mol["model"], mol["m_up"], mol["aux"], uniforms=mol["U"], steps=50, **mol["kw"])
+    assert name.startswith("tcgen05")
+    rs = np.random.RandomState(0)
+    n_seg, seg_len, stride = 70, 40, 30
+    L = 69 * stride + 40
+    m_up, aux = rs.rand(L, 80).astype(np.float32), rs.randn(L, 128).astype(np.float32)
+    U = helpers.replay_uniforms(5, seg_len, n_seg)
+    out, name = run_engine(mol["model"], m_up, aux, n_seg=n_seg, seg_len=seg_len, seg_stride=stride, uniforms=U)
+    assert name.startswith("simt")

@@ -87,7 +87,25 @@ int wrnn_create(wrnn_t** out, const wrnn_cfg* cfg, const wrnn_weights* w, int de
   wrnn_handle* h = new (std::nothrow) wrnn_handle();
   if (!h) { delete eng; set_error("out of host memory"); return WRNN_E_INVALID; }
   h->engine = eng;
+  h->last = eng;
+  h->auto_engine = (cfg->engine == WRNN_ENGINE_AUTO);
+  if (h->auto_engine && engine == WRNN_ENGINE_TCGEN05) h->host_weights = new HostWeights(hw);   // for a lazy SIMT fallback
   *out = h;
+  return WRNN_OK;
+}
+
+// ENGINE_AUTO: jobs outside the tensor-core engine's envelope go to the SIMT engine (same arithmetic contract).
+static int pick_engine(wrnn_t* h, const wrnn_job* job, Engine** out) {
+  if (h->engine->supports(*job)) { *out = h->engine; return WRNN_OK; }
+  if (!h->auto_engine || !h->host_weights) {
+    set_error(std::string("job is outside the envelope of engine '") + h->engine->name() + "'");
+    return WRNN_E_INVALID;
+  }
+  if (!h->fallback) {
+    int rc = make_simt_engine(h->engine->cfg, *h->host_weights, h->engine->device, &h->fallback);
+    if (rc != WRNN_OK) return rc;
+  }
+  *out = h->fallback;
   return WRNN_OK;
 }
 
@@ -95,6 +113,8 @@ void wrnn_destroy(wrnn_t* h) {
   if (!h) return;
   if (h->d_stage) cudaFree(h->d_stage);
   delete h->engine;
+  delete h->fallback;
+  delete h->host_weights;
   delete h;
 }
 
@@ -112,18 +132,23 @@ static int validate(const wrnn_t* h, const wrnn_job* job, bool host) {
 int wrnn_generate(wrnn_t* h, const wrnn_job* job, void* stream) {
   int rc = validate(h, job, false);
   if (rc != WRNN_OK) return rc;
-  return h->engine->generate(*job, static_cast<cudaStream_t>(stream));
+  Engine* e = nullptr;
+  if ((rc = pick_engine(h, job, &e)) != WRNN_OK) return rc;
+  h->last = e;
+  return e->generate(*job, static_cast<cudaStream_t>(stream));
 }
 
 int wrnn_check(wrnn_t* h) {
   if (!h || !h->engine) { set_error("null handle"); return WRNN_E_INVALID; }
-  return h->engine->check();
+  return h->last->check();
 }
 
 int wrnn_generate_host(wrnn_t* h, const wrnn_job* job) {
   int rc = validate(h, job, true);
   if (rc != WRNN_OK) return rc;
-  Engine* e = h->engine;
+  Engine* e = nullptr;
+  if ((rc = pick_engine(h, job, &e)) != WRNN_OK) return rc;
+  h->last = e;
   WRNN_CUDA_OK(cudaSetDevice(e->device));
   const size_t S = job->steps > 0 ? job->steps : job->seg_len;
   const size_t B = job->n_seg, NC = e->cfg.n_classes;
@@ -157,8 +182,10 @@ int wrnn_generate_host(wrnn_t* h, const wrnn_job* job) {
   return e->check();
 }
 
-const char* wrnn_engine_name(const wrnn_t* h) { return (h && h->engine) ? h->engine->name() : ""; }
-int wrnn_grid_ctas(const wrnn_t* h) { return (h && h->engine) ? h->engine->grid_ctas() : 0; }
-int64_t wrnn_launch_count(const wrnn_t* h) { return (h && h->engine) ? h->engine->launches : 0; }
+const char* wrnn_engine_name(const wrnn_t* h) { return (h && h->last) ? h->last->name() : ""; }
+int wrnn_grid_ctas(const wrnn_t* h) { return (h && h->last) ? h->last->grid_ctas() : 0; }
+int64_t wrnn_launch_count(const wrnn_t* h) {
+  return (h && h->engine) ? h->engine->launches + (h->fallback ? h->fallback->launches : 0) : 0;
+}
 
 }  // extern "C"

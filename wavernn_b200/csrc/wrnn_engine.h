@@ -25,6 +25,7 @@ class Engine {
   virtual ~Engine() {}
   virtual int generate(const wrnn_job& job, cudaStream_t stream) = 0;   // async
   virtual int check() = 0;                                              // after stream sync
+  virtual bool supports(const wrnn_job& job) const { (void)job; return true; }   // job inside this engine's envelope?
   virtual const char* name() const = 0;
   virtual int grid_ctas() const = 0;
   int64_t launches = 0;
@@ -40,7 +41,11 @@ int make_tc_engine(const wrnn_cfg& cfg, const HostWeights& w, int device, Engine
 }  // namespace wrnn
 
 struct wrnn_handle {
-  wrnn::Engine* engine = nullptr;
+  wrnn::Engine* engine = nullptr;          // engine chosen at create time
+  wrnn::Engine* fallback = nullptr;        // ENGINE_AUTO only: SIMT engine, created on first job outside `engine`'s envelope
+  wrnn::Engine* last = nullptr;            // engine that served the most recent job
+  wrnn::HostWeights* host_weights = nullptr;
+  bool auto_engine = false;
   // staging for wrnn_generate_host
   void* d_stage = nullptr;
   size_t stage_bytes = 0;

@@ -1,8 +1,592 @@
-// wrnn_tc.cu -- tcgen05 engine (placeholder until the tensor-core kernel lands).
+// wrnn_tc.cu -- tcgen05 engine: the generate() loop (reference models/fatchord_version.py:
+// 201-241 + utils/distribution.py:87-123) as ONE persistent kernel whose dense contractions
+// run on the 5th-generation tensor cores with accumulators in TMEM.
+//
+// Decomposition (same row ownership as the SIMT engine, wrnn_fold.h): P = 128 CTAs, CTA c
+// owns hidden units [4c, 4c+4) of every layer.  Its weight slices are staged ONCE into shared
+// memory as UMMA K-major (no-swizzle) operand images and stay there for the whole sequence:
+//     S1 = [W2x ; W1h ; F1x] rows (N=32, K=512)   consumes h1'
+//     S2 = [F1x ; W2h] rows      (N=16, K=512)   consumes h2'
+//     S3 = F2x rows              (N=8,  K=512)   consumes y1
+//     F3 = fc3 (all 30 rows)     (N=32, K=512)   consumes y2 (replicated in every CTA)
+//     Q  = folded conditioning rows (N=32, K=208) consumes cond_t, runs one step ahead
+// The folds are the M dimension ("swap-AB"): tile of M=64 folds, so in TMEM lane == fold and
+// every epilogue (GRU gates, relu, MoL sampling) is thread-local: one thread owns one fold,
+// reads its accumulator columns with tcgen05.ld and keeps that fold's hidden state in
+// registers for the whole sequence.
+//
+// Per step only the four 512-wide activation vectors cross SMs.  They are exchanged through
+// L2-resident buffers that are byte images of the UMMA A-operand layout, so a consumer's
+// gather is a flat coalesced 16-byte copy into shared memory; completion is a release/acquire
+// counter per vector.  fc3 + sampling is replicated in every CTA (same inputs, same
+// arithmetic => bitwise identical samples), which removes the fifth exchange of the step.
+//
+// This first version serves n_seg <= 64 (one M tile) and the MoL head; other jobs are served
+// by the SIMT engine (ENGINE_AUTO falls through).
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <vector>
+
+#include "wrnn_device.cuh"
 #include "wrnn_engine.h"
+
 namespace wrnn {
-int make_tc_engine(const wrnn_cfg&, const HostWeights&, int, Engine**) {
-  set_error("tcgen05 engine not available in this build");
-  return WRNN_E_INVALID;
+namespace {
+
+constexpr int P = 128;             // CTAs == weight shards
+constexpr int U = H / P;           // 4 hidden units per CTA
+constexpr int NT = 256;            // 8 warps: 0-3 own folds (TMEM lane quarters), 4-7 stage operands / issue MMAs
+constexpr int MT = 64;             // folds per M tile
+constexpr int KC = H / 8;          // 64 16-byte chunks per activation row
+constexpr int SBO_H = KC * 128;    // 8192: byte stride between 8-row groups, K = 512 images
+constexpr int KQ = CDIM / 8;       // 26 chunks per conditioning row
+constexpr int SBO_Q = KQ * 128;    // 3328
+
+constexpr int N_S1 = 32, N_S2 = 16, N_S3 = 8, N_F3 = 32, N_Q = 32;
+// shared memory map (bytes).  sA first: its don't-care row groups alias what follows.
+constexpr int OFF_A = 0;                                  // activation A image, up to 8 row groups
+constexpr int OFF_COND = OFF_A + 8 * SBO_H;               // 65536: conditioning A image (8 groups x 3328)
+constexpr int OFF_S1 = OFF_COND + 8 * SBO_Q;              // 92160
+constexpr int OFF_S2 = OFF_S1 + (N_S1 / 8) * SBO_H;
+constexpr int OFF_S3 = OFF_S2 + (N_S2 / 8) * SBO_H;
+constexpr int OFF_F3 = OFF_S3 + (N_S3 / 8) * SBO_H;
+constexpr int OFF_Q = OFF_F3 + (N_F3 / 8) * SBO_H;
+constexpr int OFF_VEC = OFF_Q + (N_Q / 8) * SBO_Q;        // fp32: qk[32] vq[32] b1h[12] b2h[12] b3[32] pad -> 128 floats
+constexpr int NVEC = 128;
+constexpr int OFF_BAR = OFF_VEC + NVEC * 4;               // 2 mbarriers + tmem base + flags
+constexpr int SMEM_BYTES = OFF_BAR + 64;
+constexpr int WEIGHT_BYTES = OFF_VEC + NVEC * 4 - OFF_S1; // per-CTA blob == smem[OFF_S1, OFF_BAR)
+static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+
+// TMEM columns (fp32 accumulators; M=64 => lanes 0-15 of each lane quarter)
+constexpr int TC_S1 = 0, TC_S2 = 32, TC_S3 = 48, TC_F3 = 64, TC_Q0 = 96, TC_Q1 = 128, TMEM_COLS = 256;
+
+struct TcParams {
+  const unsigned char* blob;
+  const float* mels_up; const float* aux; long long L; long long seg_stride;
+  int n_seg, steps, out_pitch, seg_first, fmt;          // fmt: 0 = fp16, 1 = bf16 operands
+  const float* uniforms; unsigned long long seed, offset;
+  float* out; const float* x_force; float* logits_out;
+  unsigned char* xch;        // [4 vectors][2 parities][n_groups * SBO_H] activation images
+  unsigned* counters;        // [4] monotonically increasing arrival counters
+  int* abort_flag;
+  long long* prof;           // optional per-phase cycle counters of CTA 0 (may be null)
+};
+
+// ------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  // SM100 shared-memory matrix descriptor: start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48)
+  // layout_type [61,64) = 0 (SWIZZLE_NONE / interleaved 8x16B core matrices), K-major
+  return (uint64_t)((saddr >> 4) & 0x3fff) | ((uint64_t)((lbo >> 4) & 0x3fff) << 16) |
+         ((uint64_t)((sbo >> 4) & 0x3fff) << 32) | ((uint64_t)1 << 46);
 }
+__device__ __forceinline__ uint32_t umma_idesc(int M, int N, int fmt) {
+  // c_format F32 [4,6)=1 | a_format [7,10) | b_format [10,13) | K-major A,B | N>>3 [17,23) | M>>4 [24,29)
+  return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+               "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+               :: "r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t mbar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(mbar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void proxy_fence_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, float* v) {
+  uint32_t a, b, c, d;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(taddr));
+  v[0] = __uint_as_float(a); v[1] = __uint_as_float(b); v[2] = __uint_as_float(c); v[3] = __uint_as_float(d);
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+               : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(nthreads) : "memory"); }
+
+// bounded waits: a protocol bug must end in an error code, never in a hung GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* abort_flag) {
+  if (mbar_try(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try(bar, parity)) {
+    if (clock64() - t0 > kWatchdogCycles) { atomicExch(abort_flag, 2); return; }
+  }
+}
+__device__ __forceinline__ void counter_wait(const unsigned* ctr, unsigned target, int* abort_flag) {
+  if (ld_acquire_u32(ctr) >= target) return;
+  const long long t0 = clock64();
+  while (ld_acquire_u32(ctr) < target) {
+    if (clock64() - t0 > kWatchdogCycles || ld_relaxed_s32(abort_flag) != 0) { atomicExch(abort_flag, 1); return; }
+  }
+}
+
+template <int FMT> __device__ __forceinline__ uint32_t pack2(float a, float b);
+template <> __device__ __forceinline__ uint32_t pack2<0>(float a, float b) {      // fp16, RNE, saturating
+  uint32_t r;
+  asm("{\n\t.reg .b16 lo, hi;\n\tcvt.rn.satfinite.f16.f32 lo, %1;\n\tcvt.rn.satfinite.f16.f32 hi, %2;\n\tmov.b32 %0, {lo, hi};\n\t}\n"
+      : "=r"(r) : "f"(a), "f"(b));
+  return r;
+}
+template <> __device__ __forceinline__ uint32_t pack2<1>(float a, float b) {      // bf16, RNE
+  const __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&v);
+}
+
+// ------------------------------------------------------------------------------------------
+// the kernel
+// ------------------------------------------------------------------------------------------
+template <int FMT>
+__global__ void __launch_bounds__(NT, 1) wrnn_tc_kernel(const TcParams p) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const float* fv = reinterpret_cast<const float*>(smem + OFF_VEC);
+  const float* qk = fv; const float* vq = fv + 32; const float* b1h = fv + 64; const float* b2h = fv + 76;
+  const float* b3 = fv + 88;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 16);
+  const uint32_t bar_mma = smem_u32(&bars[0]), bar_q = smem_u32(&bars[1]);
+
+  const int cta = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int B = p.n_seg, S = p.steps, u0 = cta * U;
+  const int n_groups = (B + 7) / 8;                    // real 8-row groups of the A images
+  const int img_bytes = n_groups * SBO_H;
+  const int gather_chunks = img_bytes / 16;
+  const bool issuer = (tid == 4 * 32);                 // warp 4 lane 0 issues every tcgen05.mma
+  // fold ownership: M=64 accumulators put fold f in TMEM lane 32*(f/16) + f%16
+  const int fold = warp * 16 + lane;
+  const bool fold_warp = warp < 4;
+  const bool owns_fold = fold_warp && lane < 16 && fold < B;
+  const uint32_t idesc_s1 = umma_idesc(MT, N_S1, FMT), idesc_s2 = umma_idesc(MT, N_S2, FMT),
+                 idesc_s3 = umma_idesc(MT, N_S3, FMT), idesc_f3 = umma_idesc(MT, N_F3, FMT),
+                 idesc_q = umma_idesc(MT, N_Q, FMT);
+
+  // ---- one-time setup: weights -> smem images, barriers, TMEM --------------------------------
+  {
+    const int4* src = reinterpret_cast<const int4*>(p.blob + (size_t)cta * WEIGHT_BYTES);
+    int4* dst = reinterpret_cast<int4*>(smem + OFF_S1);
+    for (int i = tid; i < WEIGHT_BYTES / 16; i += NT) dst[i] = src[i];
+    int4* z = reinterpret_cast<int4*>(smem);
+    for (int i = tid; i < OFF_S1 / 16; i += NT) z[i] = make_int4(0, 0, 0, 0);   // A images start as zeros
+  }
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar_mma));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar_q));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "n"(TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  proxy_fence_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16);       // this warp's lane quarter
+
+  // conditioning rows for step `ts` -> registers of the staging warps (4-7), then -> smem image
+  // Fast path (n_seg <= 24): each staging thread keeps <= 5 chunk tasks in registers, fetched a full
+  // phase before they are converted and stored, so the HBM latency never sits on a barrier.
+  constexpr int COND_TASKS = 5;
+  const bool cond_deferred = (B * KQ <= COND_TASKS * 128);
+  float4 creg[COND_TASKS][2];
+  auto cond_fetch = [&](int ts) {
+    const int n_tasks = B * KQ;
+    if (!cond_deferred) return;
+#pragma unroll
+    for (int j = 0; j < COND_TASKS; ++j) {
+      const int task = (tid - 128) + j * 128;
+      creg[j][0] = make_float4(0.f, 0.f, 0.f, 0.f); creg[j][1] = creg[j][0];
+      if (task < n_tasks) {
+        const int f = task / KQ, c8 = task % KQ;
+        const long long row = (long long)f * p.seg_stride + ts;
+        if (row < p.L) {
+          const float* src = (c8 < FEAT / 8) ? p.mels_up + row * FEAT + c8 * 8 : p.aux + row * (4 * AUXD) + (c8 - FEAT / 8) * 8;
+          creg[j][0] = __ldg(reinterpret_cast<const float4*>(src));
+          creg[j][1] = __ldg(reinterpret_cast<const float4*>(src) + 1);
+        }
+      }
+    }
+  };
+  auto cond_store = [&](int ts) {
+    const int n_tasks = B * KQ;
+    if (!cond_deferred) {                                // larger tiles: fetch + convert + store in place
+      for (int task = tid - 128; task < n_tasks; task += 128) {
+        const int f = task / KQ, c8 = task % KQ;
+        const long long row = (long long)f * p.seg_stride + ts;
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+        if (row < p.L) {
+          const float* src = (c8 < FEAT / 8) ? p.mels_up + row * FEAT + c8 * 8 : p.aux + row * (4 * AUXD) + (c8 - FEAT / 8) * 8;
+          a = __ldg(reinterpret_cast<const float4*>(src)); b = __ldg(reinterpret_cast<const float4*>(src) + 1);
+        }
+        uint4 v;
+        v.x = pack2<FMT>(a.x, a.y); v.y = pack2<FMT>(a.z, a.w); v.z = pack2<FMT>(b.x, b.y); v.w = pack2<FMT>(b.z, b.w);
+        *reinterpret_cast<uint4*>(smem + OFF_COND + (f >> 3) * SBO_Q + c8 * 128 + (f & 7) * 16) = v;
+      }
+      return;
+    }
+#pragma unroll
+    for (int j = 0; j < COND_TASKS; ++j) {
+      const int task = (tid - 128) + j * 128;
+      if (task < n_tasks) {
+        const int f = task / KQ, c8 = task % KQ;
+        uint4 v;
+        v.x = pack2<FMT>(creg[j][0].x, creg[j][0].y); v.y = pack2<FMT>(creg[j][0].z, creg[j][0].w);
+        v.z = pack2<FMT>(creg[j][1].x, creg[j][1].y); v.w = pack2<FMT>(creg[j][1].z, creg[j][1].w);
+        *reinterpret_cast<uint4*>(smem + OFF_COND + (f >> 3) * SBO_Q + c8 * 128 + (f & 7) * 16) = v;
+      }
+    }
+  };
+  auto issue_chain = [&](int off_b, int sbo_b, int off_a, int sbo_a, int ksteps, uint32_t d_col, uint32_t idesc, uint32_t bar) {
+    // D[64 folds, N] = A[64, K] * B[N, K]^T, K = 16 per instruction (two 8-element core-matrix columns = 256 B)
+    tc_fence_after();
+    const uint32_t a0 = smem_u32(smem + off_a), b0 = smem_u32(smem + off_b);
+    for (int k = 0; k < ksteps; ++k)
+      umma_f16(tmem + d_col, umma_desc(a0 + k * 256, 128, sbo_a), umma_desc(b0 + k * 256, 128, sbo_b), idesc, k > 0);
+    umma_commit(bar);
+  };
+  auto gather = [&](const unsigned char* img) {       // L2 image -> smem A image, flat 16-byte copy
+    const int4* src = reinterpret_cast<const int4*>(img);
+    int4* dst = reinterpret_cast<int4*>(smem + OFF_A);
+    for (int i = tid; i < gather_chunks; i += NT) dst[i] = __ldcg(src + i);
+    proxy_fence_smem();
+  };
+  auto publish = [&](unsigned char* img, const float* v) {   // this fold's 4 values of this CTA's units
+    uint2 w;
+    w.x = pack2<FMT>(v[0], v[1]); w.y = pack2<FMT>(v[2], v[3]);
+    *reinterpret_cast<uint2*>(img + (fold >> 3) * SBO_H + (u0 >> 3) * 128 + (fold & 7) * 16 + (u0 & 7) * 2) = w;
+  };
+  auto signal = [&](int v) {                           // fold warps have stored; one release increment per CTA
+    named_bar_sync(1, 128);
+    if (tid == 0) red_release_add_u32(p.counters + v, 1u);
+  };
+  auto wait_vec = [&](int v, unsigned target) {
+    if (tid == 0) counter_wait(p.counters + v, target, p.abort_flag);
+    tc_fence_before();
+    __syncthreads();
+  };
+
+  // ---- prologue: pre_0 = Q cond_0 ------------------------------------------------------------
+  if (!fold_warp) { cond_fetch(0); cond_store(0); proxy_fence_smem(); }
+  tc_fence_before();
+  __syncthreads();
+  if (issuer) issue_chain(OFF_Q, SBO_Q, OFF_COND, SBO_Q, CDIM / 16, TC_Q0, idesc_q, bar_q);
+  if (!fold_warp && S > 1) cond_fetch(1);
+
+  float h1[U] = {0.f, 0.f, 0.f, 0.f}, h2[U] = {0.f, 0.f, 0.f, 0.f};
+  float x = 0.f;
+  unsigned n_mma = 0;                                   // completed uses of bar_mma (parity)
+  const size_t xch_stride = (size_t)2 * img_bytes;      // per vector: two parities
+  long long tprof[6] = {0, 0, 0, 0, 0, 0};
+  const bool profiling = (p.prof != nullptr) && cta == 0 && tid == 0;
+
+  for (int t = 0; t < S; ++t) {
+    const int par = t & 1;
+    const uint32_t tq = (par ? TC_Q1 : TC_Q0);
+    unsigned char* img_h1 = p.xch + 0 * xch_stride + (size_t)par * img_bytes;
+    unsigned char* img_h2 = p.xch + 1 * xch_stride + (size_t)par * img_bytes;
+    unsigned char* img_y1 = p.xch + 2 * xch_stride + (size_t)par * img_bytes;
+    unsigned char* img_y2 = p.xch + 3 * xch_stride + (size_t)par * img_bytes;
+    const unsigned target = (unsigned)P * (unsigned)(t + 1);
+    long long tp0 = 0;
+    if (profiling) tp0 = clock64();
+
+    // draws for this step, fetched early so their latency hides under the step
+    float ur[11];
+#pragma unroll
+    for (int i = 0; i < 11; ++i) ur[i] = 0.5f;
+    if (owns_fold) {
+      if (p.uniforms) {
+        const float* u = p.uniforms + (size_t)t * 11 * B;
+#pragma unroll
+        for (int i = 0; i < 10; ++i) ur[i] = __ldg(u + fold * 10 + i);
+        ur[10] = __ldg(u + 10 * B + fold);
+      } else {
+        const unsigned g = (unsigned)(p.seg_first + fold), k0 = (unsigned)p.seed, k1 = (unsigned)(p.seed >> 32), o0 = (unsigned)p.offset;
+        const Philox4 r0 = philox4x32_10((unsigned)t, g, 0u, o0, k0, k1), r1 = philox4x32_10((unsigned)t, g, 1u, o0, k0, k1),
+                      r2 = philox4x32_10((unsigned)t, g, 2u, o0, k0, k1);
+        const unsigned rv[12] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, r2.y, r2.z, r2.w};
+#pragma unroll
+        for (int i = 0; i < 11; ++i) ur[i] = u_ref_range(rv[i]);
+      }
+    }
+    float xf = 0.f;
+    if (owns_fold && p.x_force && t > 0) xf = __ldg(p.x_force + (size_t)(t - 1) * B + fold);
+
+    // ---- A: GRU1.  gi1 = pre_t (conditioning, D_Q) + x * v1 ; gh1 = W1h h1 + b1h (D_S1 of step t-1)
+    float pre[32];                                      // this fold's 32 conditioning rows (+ qk + x*vq)
+    if (fold_warp) {
+      mbar_wait(bar_q, (uint32_t)(t & 1), p.abort_flag);           // pre_t landed in D_Q[par]
+      tc_fence_after();
+      if (p.x_force && t > 0) x = xf;
+#pragma unroll
+      for (int c = 0; c < 32; c += 4) tmem_ld4(tlane + tq + c, pre + c);
+      float gh[12];
+      if (t > 0) {
+#pragma unroll
+        for (int c = 0; c < 12; c += 4) tmem_ld4(tlane + TC_S1 + 12 + c, gh + c);
+      }
+      tmem_ld_wait();
+#pragma unroll
+      for (int q = 0; q < 32; ++q) pre[q] += qk[q] + x * vq[q];
+      float hv[U];
+#pragma unroll
+      for (int j = 0; j < U; ++j) {
+        const float ghr = (t > 0 ? gh[j] : 0.f) + b1h[j], ghz = (t > 0 ? gh[U + j] : 0.f) + b1h[U + j],
+                    ghn = (t > 0 ? gh[2 * U + j] : 0.f) + b1h[2 * U + j];
+        h1[j] = gru_unit(pre[j], pre[U + j], pre[2 * U + j], ghr, ghz, ghn, h1[j]);
+        hv[j] = h1[j];
+      }
+      if (owns_fold) publish(img_h1, hv);
+      signal(0);
+    }
+    if (profiling) { tprof[0] += clock64() - tp0; tp0 = clock64(); }
+
+    // ---- B: [W2x ; W1h ; F1x] h1'  ->  GRU2, gh1 for step t+1, fc1 partial ---------------------
+    wait_vec(0, target);
+    gather(img_h1);
+    tc_fence_before();
+    __syncthreads();
+    if (issuer) issue_chain(OFF_S1, SBO_H, OFF_A, SBO_H, H / 16, TC_S1, idesc_s1, bar_mma);
+    if (fold_warp) {
+      mbar_wait(bar_mma, n_mma & 1, p.abort_flag);
+      tc_fence_after();
+      float gi[12], gh[12];
+#pragma unroll
+      for (int c = 0; c < 12; c += 4) tmem_ld4(tlane + TC_S1 + c, gi + c);
+      if (t > 0) {
+#pragma unroll
+        for (int c = 0; c < 12; c += 4) tmem_ld4(tlane + TC_S2 + 4 + c, gh + c);
+      }
+      tmem_ld_wait();
+      float hv[U];
+#pragma unroll
+      for (int j = 0; j < U; ++j) {
+        const float ghr = (t > 0 ? gh[j] : 0.f) + b2h[j], ghz = (t > 0 ? gh[U + j] : 0.f) + b2h[U + j],
+                    ghn = (t > 0 ? gh[2 * U + j] : 0.f) + b2h[2 * U + j];
+        h2[j] = gru_unit(gi[j] + pre[3 * U + j], gi[U + j] + pre[4 * U + j], gi[2 * U + j] + pre[5 * U + j], ghr, ghz, ghn, h2[j]);
+        hv[j] = h2[j];
+      }
+      if (owns_fold) publish(img_h2, hv);
+      signal(1);
+    }
+    ++n_mma;
+    if (profiling) { tprof[1] += clock64() - tp0; tp0 = clock64(); }
+
+    // ---- C: [F1x ; W2h] h2'  ->  y1 = relu(fc1), gh2 for step t+1 ------------------------------
+    wait_vec(1, target);
+    gather(img_h2);
+    tc_fence_before();
+    __syncthreads();
+    if (issuer) issue_chain(OFF_S2, SBO_H, OFF_A, SBO_H, H / 16, TC_S2, idesc_s2, bar_mma);
+    if (!fold_warp) {
+      // staging warps: conditioning of step t+1 (fetched one phase ago) -> smem image -> Q chain
+      if (t + 1 < S) {
+        cond_store(t + 1);
+        proxy_fence_smem();
+        tc_fence_before();
+        named_bar_sync(2, 128);
+        if (issuer) issue_chain(OFF_Q, SBO_Q, OFF_COND, SBO_Q, CDIM / 16, par ? TC_Q0 : TC_Q1, idesc_q, bar_q);
+      }
+    } else {
+      mbar_wait(bar_mma, n_mma & 1, p.abort_flag);
+      tc_fence_after();
+      float a[4], b4[4];
+      tmem_ld4(tlane + TC_S2, a);                      // F1x h2'
+      tmem_ld4(tlane + TC_S1 + 24, b4);                // F1x h1' (phase B)
+      tmem_ld_wait();
+      float yv[U];
+#pragma unroll
+      for (int j = 0; j < U; ++j) yv[j] = fmaxf(a[j] + b4[j] + pre[6 * U + j], 0.f);
+      if (owns_fold) publish(img_y1, yv);
+      signal(2);
+    }
+    ++n_mma;
+    if (profiling) { tprof[2] += clock64() - tp0; tp0 = clock64(); }
+
+    // ---- D: F2x y1 -> y2 = relu(fc2) --------------------------------------------------------------
+    wait_vec(2, target);
+    gather(img_y1);
+    tc_fence_before();
+    __syncthreads();
+    if (issuer) issue_chain(OFF_S3, SBO_H, OFF_A, SBO_H, H / 16, TC_S3, idesc_s3, bar_mma);
+    if (!fold_warp) {
+      if (t + 2 < S) cond_fetch(t + 2);                // lands in registers while phases D, E, A, B run
+    } else {
+      mbar_wait(bar_mma, n_mma & 1, p.abort_flag);
+      tc_fence_after();
+      float a[4];
+      tmem_ld4(tlane + TC_S3, a);
+      tmem_ld_wait();
+      float yv[U];
+#pragma unroll
+      for (int j = 0; j < U; ++j) yv[j] = fmaxf(a[j] + pre[7 * U + j], 0.f);
+      if (owns_fold) publish(img_y2, yv);
+      signal(3);
+    }
+    ++n_mma;
+    if (profiling) { tprof[3] += clock64() - tp0; tp0 = clock64(); }
+
+    // ---- E: logits = F3 y2 + b3, MoL sample (replicated in every CTA) -----------------------------
+    wait_vec(3, target);
+    gather(img_y2);
+    tc_fence_before();
+    __syncthreads();
+    if (issuer) issue_chain(OFF_F3, SBO_H, OFF_A, SBO_H, H / 16, TC_F3, idesc_f3, bar_mma);
+    if (fold_warp) {
+      mbar_wait(bar_mma, n_mma & 1, p.abort_flag);
+      tc_fence_after();
+      float lg[32];
+#pragma unroll
+      for (int c = 0; c < 32; c += 4) tmem_ld4(tlane + TC_F3 + c, lg + c);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 30; ++i) lg[i] += b3[i];
+      x = mol_sample([&](int i) { return lg[i]; }, [&](int i) { return ur[i]; });
+      if (owns_fold && cta == 0) {
+        p.out[(size_t)fold * p.out_pitch + t] = x;
+        if (p.logits_out)
+          for (int i = 0; i < 30; ++i) p.logits_out[((size_t)t * B + fold) * 30 + i] = lg[i];
+      }
+    }
+    ++n_mma;
+    if (profiling) { tprof[4] += clock64() - tp0; }
+    if (ld_relaxed_s32(p.abort_flag) != 0) break;      // every wait above is bounded; leave promptly
+  }
+
+  if (profiling) for (int i = 0; i < 5; ++i) p.prof[i] = tprof[i];
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "n"(TMEM_COLS));
+}
+
+// --------------------------------------------------------------------------------------------
+// host side
+// --------------------------------------------------------------------------------------------
+// K-major no-swizzle operand image: element (r, k) at (r/8)*(K/8)*64 + (k/8)*64 + (r%8)*8 + k%8
+inline size_t img_index(int r, int k, int K) { return (size_t)(r / 8) * (K / 8) * 64 + (size_t)(k / 8) * 64 + (r % 8) * 8 + (k % 8); }
+
+class TcEngine : public Engine {
+ public:
+  ~TcEngine() override {
+    cudaSetDevice(device);
+    cudaFree(d_blob_); cudaFree(d_scratch_); cudaFree(d_sync_);
+  }
+  const char* name() const override { return cfg.precision == WRNN_PREC_BF16 ? "tcgen05-bf16" : "tcgen05-fp16"; }
+  int grid_ctas() const override { return P; }
+  const void* kernel() const { return cfg.precision == WRNN_PREC_BF16 ? (const void*)wrnn_tc_kernel<1> : (const void*)wrnn_tc_kernel<0>; }
+
+  int init(const HostWeights& w) {
+    Folded f; fold(w, f);
+    const bool bf = cfg.precision == WRNN_PREC_BF16;
+    auto cvt = [&](double v) -> uint16_t { return bf ? f2bf((float)v) : f2h((float)v); };
+    std::vector<unsigned char> blob((size_t)WEIGHT_BYTES * P, 0);
+    CtaSlice s;
+    for (int c = 0; c < P; ++c) {
+      slice_for_cta(w, f, c, U, s);
+      unsigned char* base = blob.data() + (size_t)c * WEIGHT_BYTES;
+      uint16_t* s1 = reinterpret_cast<uint16_t*>(base + (OFF_S1 - OFF_S1));
+      uint16_t* s2 = reinterpret_cast<uint16_t*>(base + (OFF_S2 - OFF_S1));
+      uint16_t* s3 = reinterpret_cast<uint16_t*>(base + (OFF_S3 - OFF_S1));
+      uint16_t* f3 = reinterpret_cast<uint16_t*>(base + (OFF_F3 - OFF_S1));
+      uint16_t* q = reinterpret_cast<uint16_t*>(base + (OFF_Q - OFF_S1));
+      float* fv = reinterpret_cast<float*>(base + (OFF_VEC - OFF_S1));
+      for (int k = 0; k < H; ++k) {
+        for (int r = 0; r < 7 * U; ++r) s1[img_index(r, k, H)] = cvt(s.S1[(size_t)r * H + k]);
+        for (int r = 0; r < 4 * U; ++r) s2[img_index(r, k, H)] = cvt(s.S2[(size_t)r * H + k]);
+        for (int r = 0; r < U; ++r) s3[img_index(r, k, H)] = cvt(s.S3[(size_t)r * H + k]);
+        for (int r = 0; r < cfg.n_classes; ++r) f3[img_index(r, k, H)] = cvt(w.f3w[(size_t)r * H + k]);
+      }
+      for (int k = 0; k < CDIM; ++k)
+        for (int r = 0; r < 8 * U; ++r) q[img_index(r, k, CDIM)] = cvt(s.Q[(size_t)r * CDIM + k]);
+      for (int r = 0; r < 8 * U; ++r) { fv[r] = s.qk[r]; fv[32 + r] = s.vq[r]; }
+      for (int r = 0; r < 3 * U; ++r) { fv[64 + r] = s.b1h[r]; fv[76 + r] = s.b2h[r]; }
+      for (int r = 0; r < cfg.n_classes; ++r) fv[88 + r] = w.f3b[r];
+    }
+    WRNN_CUDA_OK(cudaMalloc(&d_blob_, blob.size()));
+    WRNN_CUDA_OK(cudaMemcpy(d_blob_, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+    WRNN_CUDA_OK(cudaMalloc(&d_sync_, 256));
+    WRNN_CUDA_OK(cudaMemset(d_sync_, 0, 256));
+    scratch_bytes_ = (size_t)4 * 2 * 8 * SBO_H;          // 4 vectors x 2 parities x (up to 8 row groups)
+    WRNN_CUDA_OK(cudaMalloc(&d_scratch_, scratch_bytes_));
+    WRNN_CUDA_OK(cudaFuncSetAttribute(kernel(), cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    int n_sm = 0;
+    WRNN_CUDA_OK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device));
+    if (n_sm < P) { set_error("tcgen05 engine needs >= 128 SMs for its co-resident weight shards"); return WRNN_E_NO_DEVICE; }
+    return WRNN_OK;
+  }
+
+  static bool supports_cfg(const wrnn_cfg& c) { return c.mode == WRNN_MODE_MOL && c.n_classes == 30 && c.precision != WRNN_PREC_FP32; }
+  bool supports(const wrnn_job& job) const override { return job.n_seg <= MT; }
+
+  int generate(const wrnn_job& job, cudaStream_t stream) override {
+    if (job.n_seg > MT) {
+      set_error("tcgen05 engine (this build): n_seg must be <= 64");
+      return WRNN_E_INVALID;
+    }
+    WRNN_CUDA_OK(cudaSetDevice(device));
+    WRNN_CUDA_OK(cudaMemsetAsync(d_sync_, 0, 256, stream));
+    WRNN_CUDA_OK(cudaMemsetAsync(d_scratch_, 0, scratch_bytes_, stream));
+    TcParams p{};
+    p.blob = static_cast<const unsigned char*>(d_blob_);
+    p.mels_up = job.mels_up; p.aux = job.aux; p.L = job.L; p.seg_stride = job.seg_stride;
+    p.n_seg = job.n_seg; p.steps = job.steps > 0 ? job.steps : job.seg_len; p.out_pitch = p.steps;
+    p.seg_first = job.seg_first; p.fmt = cfg.precision == WRNN_PREC_BF16;
+    p.uniforms = job.uniforms; p.seed = job.philox_seed; p.offset = job.philox_offset;
+    p.out = job.out; p.x_force = job.x_force; p.logits_out = job.logits_out;
+    p.xch = static_cast<unsigned char*>(d_scratch_);
+    p.counters = static_cast<unsigned*>(d_sync_);
+    p.abort_flag = reinterpret_cast<int*>(static_cast<unsigned*>(d_sync_) + 8);
+    p.prof = reinterpret_cast<long long*>(static_cast<unsigned char*>(d_sync_) + 64);
+    void* args[] = {&p};
+    WRNN_CUDA_OK(cudaLaunchCooperativeKernel(kernel(), dim3(P), dim3(NT), args, SMEM_BYTES, stream));
+    ++launches;
+    return WRNN_OK;
+  }
+
+  int check() override {
+    unsigned char buf[256];
+    WRNN_CUDA_OK(cudaSetDevice(device));
+    WRNN_CUDA_OK(cudaMemcpy(buf, d_sync_, 256, cudaMemcpyDeviceToHost));
+    const int flag = reinterpret_cast<int*>(buf)[8];
+    std::memcpy(prof, buf + 64, sizeof(prof));
+    if (flag != 0) {
+      set_error(flag == 2 ? "persistent kernel aborted: an MMA-completion mbarrier wait timed out"
+                          : "persistent kernel aborted: an inter-SM exchange wait timed out");
+      return WRNN_E_WATCHDOG;
+    }
+    return WRNN_OK;
+  }
+  long long prof[6] = {0, 0, 0, 0, 0, 0};
+
+ private:
+  void *d_blob_ = nullptr, *d_scratch_ = nullptr, *d_sync_ = nullptr;
+  size_t scratch_bytes_ = 0;
+};
+
+}  // namespace
+
+int make_tc_engine(const wrnn_cfg& cfg, const HostWeights& w, int device, Engine** out) {
+  if (!TcEngine::supports_cfg(cfg)) {
+    set_error("tcgen05 engine (this build) serves the MoL head with fp16/bf16 operands");
+    return WRNN_E_INVALID;
+  }
+  TcEngine* e = new TcEngine();
+  e->cfg = cfg; e->device = device;
+  const int rc = e->init(w);
+  if (rc != WRNN_OK) { delete e; return rc; }
+  *out = e;
+  return WRNN_OK;
+}
+
 }  // namespace wrnn
