@@ -140,13 +140,25 @@ def time_cpu_port(sample_steps: int, repeats: int = 1, warmup: int = 0):
     mels_f, aux_f = cpu_conditioning(model, mel)
     sd = {k: v.detach() for k, v in model.state_dict().items()}
     B = mels_f.shape[0]
+    # The loop is 19-row GEMVs: on a many-core host torch's default (all cores) oversubscribes badly
+    # (128 threads: ~40x slower than 8).  Give the CPU arm its best thread count from a short sweep.
+    trials = {}
+    for n in sorted({min(cores, c) for c in (4, 8, 16, 32, cores)}):
+        torch.set_num_threads(n)
+        torch.manual_seed(1234)
+        _, dt = torch_port.generate_segments_torch(sd, mels_f, aux_f, steps=40)
+        trials[n] = dt
+    best = min(trials, key=trials.get)
+    torch.set_num_threads(best)
+    cores = best
     times = []
     for i in range(warmup + repeats):
         torch.manual_seed(1234)
         _, dt = torch_port.generate_segments_torch(sd, mels_f, aux_f, steps=sample_steps)
         if i >= warmup:
             times.append(dt)
-    return dict(B=B, steps=sample_steps, seconds=times, cores=cores, threads=torch.get_num_threads())
+    return dict(B=B, steps=sample_steps, seconds=times, cores=cores, threads=torch.get_num_threads(),
+                host_cores=os.cpu_count() or 1, sweep={str(k): round(40 * B / v, 1) for k, v in trials.items()})
 
 
 def run_reference_arm(args):
@@ -157,7 +169,7 @@ def run_reference_arm(args):
     r = time_cpu_port(sample_steps, repeats=args.steps, warmup=args.warmup)
     per_step = float(np.mean(r["seconds"]))
     value = r["B"] * sample_steps / per_step
-    sample = f"{r['B']} folds x {sample_steps} of 12100 steps per bench step (torch CPU operators, {r['threads']} threads)"
+    sample = f"{r['B']} folds x {sample_steps} of 12100 steps per bench step (torch CPU operators, best of thread sweep = {r['threads']} threads on {r['host_cores']} host cores; samples/s by threads: {r['sweep']})"
     line = {"impl": "reference", "metric": "audio samples/sec (22.05 kHz) batched MoL generate", "value": value,
             "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": per_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -278,7 +290,7 @@ def run_ours(args):
             r = time_cpu_port(args.cpu_sample_steps)
             v = r["B"] * r["steps"] / r["seconds"][0]
             cpu = {"value": v, "unit": "samples/s", "cores": r["cores"], "kind": "port",
-                   "sample": f"{r['B']} folds x first {r['steps']} of 12100 steps, torch CPU operators, {r['threads']} threads"}
+                   "sample": f"{r['B']} folds x first {r['steps']} of 12100 steps, torch CPU operators, best of thread sweep = {r['threads']} threads on {r['host_cores']} host cores; samples/s by threads: {r['sweep']}"}
         line = {
             "metric": "audio samples/sec (22.05 kHz) batched MoL generate", "value": value, "unit": "samples/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_dev / args.steps * 1e3,
