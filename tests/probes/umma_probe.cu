@@ -25,13 +25,19 @@ __device__ __forceinline__ void mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_
                "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
                :: "r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
 }
+// whole converged warp executes; elect.sync predicates the instruction onto one lane
+__device__ __forceinline__ void mma_f16_elect(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n\t.reg .pred p, e;\n\tsetp.ne.b32 p, %4, 0;\n\telect.sync _|e, 0xffffffff;\n\t"
+               "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+               :: "r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
                "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
                "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}\n" :: "r"(bar), "r"(parity) : "memory");
 }
 
-struct Params { const __half* A; const __half* B; float* D; long long* cycles; int M, N, K, a_rows_real; };
+struct Params { const __half* A; const __half* B; float* D; long long* cycles; int M, N, K, a_rows_real, mode; };
 
 // A image: canonical K-major no-swizzle, LBO = 128 B (adjacent k8 chunks contiguous), SBO = K/8*128 B
 __global__ void __launch_bounds__(128, 1) umma_probe(Params p) {
@@ -67,13 +73,21 @@ __global__ void __launch_bounds__(128, 1) umma_probe(Params p) {
   for (int rep = 0; rep < 3; ++rep) {
     __syncthreads();
     t0 = clock64();
-    if (tid == 0) {
-      for (int k = 0; k < K / 16; ++k) {
-        const uint64_t ad = make_desc(smem_u32(sA) + k * 256, 128, sbo);
-        const uint64_t bd = make_desc(smem_u32(sB) + k * 256, 128, sbo);
-        mma_f16(tmem, ad, bd, idesc, k > 0 ? 1u : 0u);
+    if (p.mode == 0) {
+      if (tid == 0) {
+        for (int k = 0; k < K / 16; ++k) {
+          const uint64_t ad = make_desc(smem_u32(sA) + k * 256, 128, sbo);
+          const uint64_t bd = make_desc(smem_u32(sB) + k * 256, 128, sbo);
+          mma_f16(tmem, ad, bd, idesc, k > 0 ? 1u : 0u);
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(&mbar)) : "memory");
       }
-      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(&mbar)) : "memory");
+    } else if (warp == 0) {
+      const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
+#pragma unroll 4
+      for (int k = 0; k < K / 16; ++k)
+        mma_f16_elect(tmem, make_desc(a0 + k * 256, 128, sbo), make_desc(b0 + k * 256, 128, sbo), idesc, k > 0 ? 1u : 0u);
+      asm volatile("{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}\n" :: "r"(smem_u32(&mbar)) : "memory");
     }
     t1 = clock64();
     mbar_wait(smem_u32(&mbar), rep & 1);
@@ -99,7 +113,7 @@ __global__ void __launch_bounds__(128, 1) umma_probe(Params p) {
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 64;" :: "r"(tmem));
 }
 
-static int run_case(int M, int N, int K, int a_rows_real) {
+static int run_case(int M, int N, int K, int a_rows_real, int mode) {
   std::vector<__half> A((size_t)a_rows_real * K), B((size_t)N * K);
   std::vector<float> Af((size_t)a_rows_real * K), Bf((size_t)N * K);
   srand(1234 + M + N);
@@ -110,7 +124,7 @@ static int run_case(int M, int N, int K, int a_rows_real) {
   CK(cudaMalloc(&dA, A.size() * 2)); CK(cudaMalloc(&dB, B.size() * 2)); CK(cudaMalloc(&dD, 128 * 32 * 4)); CK(cudaMalloc(&dC, 64));
   CK(cudaMemcpy(dA, A.data(), A.size() * 2, cudaMemcpyHostToDevice)); CK(cudaMemcpy(dB, B.data(), B.size() * 2, cudaMemcpyHostToDevice));
   CK(cudaMemset(dD, 0xff, 128 * 32 * 4));
-  Params p{dA, dB, dD, dC, M, N, K, a_rows_real};
+  Params p{dA, dB, dD, dC, M, N, K, a_rows_real, mode};
   const int smem = 65536 * 2 + N * K * 2 + 1024;
   CK(cudaFuncSetAttribute(umma_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   umma_probe<<<1, 128, smem>>>(p);
@@ -128,7 +142,7 @@ static int run_case(int M, int N, int K, int a_rows_real) {
       if (e > maxerr) maxerr = e;
     }
   }
-  printf("M=%3d N=%2d K=%3d real_rows=%3d : %s  maxerr=%.3g  issue=%lld cyc  issue->done=%lld cyc  ld=%lld cyc\n", M, N, K,
+  printf("%s M=%3d N=%2d K=%3d real_rows=%3d : %s  maxerr=%.3g  issue=%lld cyc  issue->done=%lld cyc  ld=%lld cyc\n", mode ? "[elect-warp]" : "[tid==0   ]", M, N, K,
          a_rows_real, bad ? "MISMATCH" : "ok", maxerr, cyc[0], cyc[1], cyc[2]);
   if (bad) {   // help decoding: where did row 0 / row 17 land?
     for (int lane = 0; lane < 128; lane += 1) { bool nz = false; for (int c = 0; c < N; ++c) nz |= (D[lane * 32 + c] == D[lane * 32 + c]) && D[lane * 32 + c] != 0.f; if (nz && lane % 8 == 0) printf("   lane %d has data: %f %f\n", lane, D[lane * 32], D[lane * 32 + 1]); }
@@ -141,7 +155,7 @@ int main() {
   int fails = 0;
   const int cases[][4] = {{128, 32, 512, 128}, {64, 32, 512, 64}, {64, 16, 512, 64}, {64, 8, 512, 64}, {128, 16, 512, 128},
                           {64, 32, 512, 24}, {128, 32, 512, 24}, {64, 32, 208, 24}, {64, 32, 512, 56}};
-  for (auto& c : cases) fails += run_case(c[0], c[1], c[2], c[3]);
+  for (int mode = 0; mode < 2; ++mode) for (auto& c : cases) fails += run_case(c[0], c[1], c[2], c[3], mode);
   printf(fails ? "UMMA PROBE: %d case(s) FAILED\n" : "UMMA PROBE: all cases ok\n", fails);
   return fails ? 1 : 0;
 }

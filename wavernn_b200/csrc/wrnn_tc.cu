@@ -28,6 +28,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 #include "wrnn_device.cuh"
@@ -90,13 +91,17 @@ __device__ __forceinline__ uint32_t umma_idesc(int M, int N, int fmt) {
   // c_format F32 [4,6)=1 | a_format [7,10) | b_format [10,13) | K-major A,B | N>>3 [17,23) | M>>4 [24,29)
   return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+// Both are executed by a WHOLE (converged) warp with warp-uniform operands; `elect.sync` predicates the
+// instruction onto one lane.  Issuing from a `tid == k` branch instead makes ptxas wrap every UTCHMMA in
+// an ELECT/BRA.U.ANY loop that costs ~70 cycles per instruction (measured: tests/probes/umma_probe.cu).
 __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-               "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+  asm volatile("{\n\t.reg .pred p, e;\n\tsetp.ne.b32 p, %4, 0;\n\telect.sync _|e, 0xffffffff;\n\t"
+               "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
                :: "r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t mbar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(mbar) : "memory");
+  asm volatile("{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
+               "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}\n" :: "r"(mbar) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -161,7 +166,7 @@ __global__ void __launch_bounds__(NT, 1) wrnn_tc_kernel(const TcParams p) {
   const int n_groups = (B + 7) / 8;                    // real 8-row groups of the A images
   const int img_bytes = n_groups * SBO_H;
   const int gather_chunks = img_bytes / 16;
-  const bool issuer = (tid == 4 * 32);                 // warp 4 lane 0 issues every tcgen05.mma
+  const bool issuer = (warp == 4);                    // warp 4 (converged, elect.sync inside) issues every tcgen05.mma
   // fold ownership: M=64 accumulators put fold f in TMEM lane 32*(f/16) + f%16
   const int fold = warp * 16 + lane;
   const bool fold_warp = warp < 4;
@@ -551,6 +556,7 @@ class TcEngine : public Engine {
     void* args[] = {&p};
     WRNN_CUDA_OK(cudaLaunchCooperativeKernel(kernel(), dim3(P), dim3(NT), args, SMEM_BYTES, stream));
     ++launches;
+    last_steps_ = p.steps;
     return WRNN_OK;
   }
 
@@ -560,6 +566,10 @@ class TcEngine : public Engine {
     WRNN_CUDA_OK(cudaMemcpy(buf, d_sync_, 256, cudaMemcpyDeviceToHost));
     const int flag = reinterpret_cast<int*>(buf)[8];
     std::memcpy(prof, buf + 64, sizeof(prof));
+    if (getenv("WRNN_TC_PROF") && last_steps_ > 0) {     // average cycles per phase seen by CTA 0 / thread 0
+      fprintf(stderr, "[wrnn_tc prof] steps=%d  A(gru1)=%lld  B(h1'->gru2)=%lld  C(h2'->y1)=%lld  D(y1->y2)=%lld  E(y2->sample)=%lld cycles/step\n",
+              last_steps_, prof[0] / last_steps_, prof[1] / last_steps_, prof[2] / last_steps_, prof[3] / last_steps_, prof[4] / last_steps_);
+    }
     if (flag != 0) {
       set_error(flag == 2 ? "persistent kernel aborted: an MMA-completion mbarrier wait timed out"
                           : "persistent kernel aborted: an inter-SM exchange wait timed out");
@@ -572,6 +582,7 @@ class TcEngine : public Engine {
  private:
   void *d_blob_ = nullptr, *d_scratch_ = nullptr, *d_sync_ = nullptr;
   size_t scratch_bytes_ = 0;
+  int last_steps_ = 0;
 };
 
 }  // namespace
