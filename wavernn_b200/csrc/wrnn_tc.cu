@@ -16,13 +16,21 @@
 // registers for the whole sequence.
 //
 // Per step only the four 512-wide activation vectors cross SMs.  They are exchanged through
-// L2-resident buffers that are byte images of the UMMA A-operand layout, so a consumer's
-// gather is a flat coalesced 16-byte copy into shared memory; completion is a release/acquire
-// counter per vector.  fc3 + sampling is replicated in every CTA (same inputs, same
-// arithmetic => bitwise identical samples), which removes the fifth exchange of the step.
+// L2-resident buffers that are byte images of the UMMA A-operand layout, so a consumer pulls a
+// whole vector with ONE TMA bulk copy (cp.async.bulk global -> shared, mbarrier completion)
+// straight into the operand buffer; arrival is a release/acquire counter per vector.
+// fc3 + sampling is replicated in every CTA (same inputs, same arithmetic => bitwise
+// identical samples), which removes the fifth exchange of the step.
 //
-// This first version serves n_seg <= 64 (one M tile) and the MoL head; other jobs are served
-// by the SIMT engine (ENGINE_AUTO falls through).
+// Warp roles (no CTA-wide barrier inside the step loop):
+//   warps 0-3  fold warps   : TMEM -> registers, gates / relu / sampler, publish, signal
+//   warp  4    driver       : polls arrival counters, launches the TMA gather, issues every
+//                             tcgen05.mma chain (warp-uniform, elect.sync-predicated)
+//   warps 5-7  cond stagers : stream cond_{t+1} HBM -> registers -> fp16 operand image, one
+//                             step ahead of the recurrence
+//
+// This version serves n_seg <= 64 (one M tile) and the MoL head; other jobs are served by the
+// SIMT engine (ENGINE_AUTO falls through per job).
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
@@ -39,25 +47,26 @@ namespace {
 
 constexpr int P = 128;             // CTAs == weight shards
 constexpr int U = H / P;           // 4 hidden units per CTA
-constexpr int NT = 256;            // 8 warps: 0-3 own folds (TMEM lane quarters), 4-7 stage operands / issue MMAs
+constexpr int NT = 256;            // 8 warps, roles above
 constexpr int MT = 64;             // folds per M tile
 constexpr int KC = H / 8;          // 64 16-byte chunks per activation row
 constexpr int SBO_H = KC * 128;    // 8192: byte stride between 8-row groups, K = 512 images
 constexpr int KQ = CDIM / 8;       // 26 chunks per conditioning row
 constexpr int SBO_Q = KQ * 128;    // 3328
+constexpr int N_STAGERS = 96;      // threads of warps 5-7
 
 constexpr int N_S1 = 32, N_S2 = 16, N_S3 = 8, N_F3 = 32, N_Q = 32;
-// shared memory map (bytes).  sA first: its don't-care row groups alias what follows.
-constexpr int OFF_A = 0;                                  // activation A image, up to 8 row groups
-constexpr int OFF_COND = OFF_A + 8 * SBO_H;               // 65536: conditioning A image (8 groups x 3328)
-constexpr int OFF_S1 = OFF_COND + 8 * SBO_Q;              // 92160
+// shared memory map (bytes)
+constexpr int OFF_A = 0;                                  // activation A image, 8 row groups
+constexpr int OFF_COND = OFF_A + 8 * SBO_H;               // conditioning A image (8 groups x 3328)
+constexpr int OFF_S1 = OFF_COND + 8 * SBO_Q;
 constexpr int OFF_S2 = OFF_S1 + (N_S1 / 8) * SBO_H;
 constexpr int OFF_S3 = OFF_S2 + (N_S2 / 8) * SBO_H;
 constexpr int OFF_F3 = OFF_S3 + (N_S3 / 8) * SBO_H;
 constexpr int OFF_Q = OFF_F3 + (N_F3 / 8) * SBO_H;
 constexpr int OFF_VEC = OFF_Q + (N_Q / 8) * SBO_Q;        // fp32: qk[32] vq[32] b1h[12] b2h[12] b3[32] pad -> 128 floats
 constexpr int NVEC = 128;
-constexpr int OFF_BAR = OFF_VEC + NVEC * 4;               // 2 mbarriers + tmem base + flags
+constexpr int OFF_BAR = OFF_VEC + NVEC * 4;               // 3 mbarriers + tmem base
 constexpr int SMEM_BYTES = OFF_BAR + 64;
 constexpr int WEIGHT_BYTES = OFF_VEC + NVEC * 4 - OFF_S1; // per-CTA blob == smem[OFF_S1, OFF_BAR)
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
@@ -68,13 +77,13 @@ constexpr int TC_S1 = 0, TC_S2 = 32, TC_S3 = 48, TC_F3 = 64, TC_Q0 = 96, TC_Q1 =
 struct TcParams {
   const unsigned char* blob;
   const float* mels_up; const float* aux; long long L; long long seg_stride;
-  int n_seg, steps, out_pitch, seg_first, fmt;          // fmt: 0 = fp16, 1 = bf16 operands
+  int n_seg, steps, out_pitch, seg_first;
   const float* uniforms; unsigned long long seed, offset;
   float* out; const float* x_force; float* logits_out;
   unsigned char* xch;        // [4 vectors][2 parities][n_groups * SBO_H] activation images
   unsigned* counters;        // [4] monotonically increasing arrival counters
   int* abort_flag;
-  long long* prof;           // optional per-phase cycle counters of CTA 0 (may be null)
+  long long* prof;           // cycle counters of CTA 0 (fold thread 0: [0..4], driver lane 0: [5..7])
 };
 
 // ------------------------------------------------------------------------------------------
@@ -91,9 +100,9 @@ __device__ __forceinline__ uint32_t umma_idesc(int M, int N, int fmt) {
   // c_format F32 [4,6)=1 | a_format [7,10) | b_format [10,13) | K-major A,B | N>>3 [17,23) | M>>4 [24,29)
   return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
-// Both are executed by a WHOLE (converged) warp with warp-uniform operands; `elect.sync` predicates the
-// instruction onto one lane.  Issuing from a `tid == k` branch instead makes ptxas wrap every UTCHMMA in
-// an ELECT/BRA.U.ANY loop that costs ~70 cycles per instruction (measured: tests/probes/umma_probe.cu).
+// Executed by a WHOLE converged warp with warp-uniform operands; elect.sync predicates the instruction
+// onto one lane.  (Issuing from a `tid == k` branch makes ptxas wrap every UTCHMMA in an ELECT/BRA.U.ANY
+// loop: ~70 cycles per instruction instead of ~38, measured with tests/probes/umma_probe.cu.)
 __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile("{\n\t.reg .pred p, e;\n\tsetp.ne.b32 p, %4, 0;\n\telect.sync _|e, 0xffffffff;\n\t"
                "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
@@ -103,9 +112,17 @@ __device__ __forceinline__ void umma_commit(uint32_t mbar) {
   asm volatile("{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
                "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}\n" :: "r"(mbar) : "memory");
 }
+// TMA 1-D bulk copy global -> shared, completion counted in bytes on an mbarrier (whole warp, one lane elected)
+__device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t mbar) {
+  asm volatile("{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
+               "@e mbarrier.arrive.expect_tx.shared::cta.b64 _, [%3], %2;\n\t"
+               "@e cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n\t}\n"
+               :: "r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void proxy_fence_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void proxy_fence_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld4(uint32_t taddr, float* v) {
   uint32_t a, b, c, d;
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(taddr));
@@ -124,8 +141,12 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volat
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* abort_flag) {
   if (mbar_try(bar, parity)) return;
   const long long t0 = clock64();
+  unsigned spins = 0;
   while (!mbar_try(bar, parity)) {
-    if (clock64() - t0 > kWatchdogCycles) { atomicExch(abort_flag, 2); return; }
+    if ((++spins & 1023u) == 0) {                       // rarely: has another wait already given up?
+      if (ld_relaxed_s32(abort_flag) != 0) return;
+      if (clock64() - t0 > kWatchdogCycles) { atomicExch(abort_flag, 2); return; }
+    }
   }
 }
 __device__ __forceinline__ void counter_wait(const unsigned* ctr, unsigned target, int* abort_flag) {
@@ -148,6 +169,33 @@ template <> __device__ __forceinline__ uint32_t pack2<1>(float a, float b) {    
   return *reinterpret_cast<const uint32_t*>(&v);
 }
 
+// Epilogue transcendentals on the SFU (ex2/rcp/lg2 approx, rel. error ~1e-6 -- two orders below the
+// fp16 operand rounding of the contractions).  The strict SIMT engine keeps the libm versions.
+__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float fast_tanh(float x) { return 1.0f - __fdividef(2.0f, __expf(2.0f * x) + 1.0f); }
+__device__ __forceinline__ float gru_unit_fast(float gi_r, float gi_z, float gi_n, float gh_r, float gh_z, float gh_n, float h) {
+  const float r = fast_sigmoid(gi_r + gh_r);
+  const float z = fast_sigmoid(gi_z + gh_z);
+  const float n = fast_tanh(gi_n + r * gh_n);
+  return (1.0f - z) * n + z * h;
+}
+// utils/distribution.py:99-121 on SFU logs/exp
+__device__ __forceinline__ float mol_sample_fast(const float* lg, const float* u) {
+  int best = 0;
+  float bestv = -INFINITY;
+#pragma unroll
+  for (int k = 0; k < 10; ++k) {
+    const float g = lg[k] - __logf(-__logf(u[k]));
+    if (g > bestv) { bestv = g; best = k; }
+  }
+  float mean = lg[10], ls = lg[20];
+#pragma unroll
+  for (int k = 1; k < 10; ++k) { if (best == k) { mean = lg[10 + k]; ls = lg[20 + k]; } }
+  ls = fmaxf(ls, -32.23619130191664f);
+  const float x = mean + __expf(ls) * (__logf(u[10]) - __logf(1.0f - u[10]));
+  return fminf(fmaxf(x, -1.0f), 1.0f);
+}
+
 // ------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------
@@ -158,22 +206,14 @@ __global__ void __launch_bounds__(NT, 1) wrnn_tc_kernel(const TcParams p) {
   const float* qk = fv; const float* vq = fv + 32; const float* b1h = fv + 64; const float* b2h = fv + 76;
   const float* b3 = fv + 88;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 16);
-  const uint32_t bar_mma = smem_u32(&bars[0]), bar_q = smem_u32(&bars[1]);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 32);
+  const uint32_t bar_mma = smem_u32(&bars[0]), bar_q = smem_u32(&bars[1]), bar_g = smem_u32(&bars[2]);
 
   const int cta = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int B = p.n_seg, S = p.steps, u0 = cta * U;
   const int n_groups = (B + 7) / 8;                    // real 8-row groups of the A images
-  const int img_bytes = n_groups * SBO_H;
-  const int gather_chunks = img_bytes / 16;
-  const bool issuer = (warp == 4);                    // warp 4 (converged, elect.sync inside) issues every tcgen05.mma
-  // fold ownership: M=64 accumulators put fold f in TMEM lane 32*(f/16) + f%16
-  const int fold = warp * 16 + lane;
-  const bool fold_warp = warp < 4;
-  const bool owns_fold = fold_warp && lane < 16 && fold < B;
-  const uint32_t idesc_s1 = umma_idesc(MT, N_S1, FMT), idesc_s2 = umma_idesc(MT, N_S2, FMT),
-                 idesc_s3 = umma_idesc(MT, N_S3, FMT), idesc_f3 = umma_idesc(MT, N_F3, FMT),
-                 idesc_q = umma_idesc(MT, N_Q, FMT);
+  const uint32_t img_bytes = (uint32_t)n_groups * SBO_H;
+  const size_t xch_stride = (size_t)2 * img_bytes;     // per vector: two parities
 
   // ---- one-time setup: weights -> smem images, barriers, TMEM --------------------------------
   {
@@ -186,6 +226,7 @@ __global__ void __launch_bounds__(NT, 1) wrnn_tc_kernel(const TcParams p) {
   if (tid == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar_mma));
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar_q));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar_g));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -197,279 +238,280 @@ __global__ void __launch_bounds__(NT, 1) wrnn_tc_kernel(const TcParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16);       // this warp's lane quarter
 
-  // conditioning rows for step `ts` -> registers of the staging warps (4-7), then -> smem image
-  // Fast path (n_seg <= 24): each staging thread keeps <= 5 chunk tasks in registers, fetched a full
-  // phase before they are converted and stored, so the HBM latency never sits on a barrier.
-  constexpr int COND_TASKS = 5;
-  const bool cond_deferred = (B * KQ <= COND_TASKS * 128);
-  float4 creg[COND_TASKS][2];
-  auto cond_fetch = [&](int ts) {
-    const int n_tasks = B * KQ;
-    if (!cond_deferred) return;
+  if (warp < 4) {
+    // =========================================================================================
+    // fold warps: M=64 accumulators put fold f in TMEM lane 32*(f/16) + f%16
+    // =========================================================================================
+    const int fold = warp * 16 + lane;
+    const bool owns_fold = lane < 16 && fold < B;
+    const uint32_t tlane = tmem + ((uint32_t)(warp * 32) << 16);
+    const size_t pub_off = (size_t)(fold >> 3) * SBO_H + (u0 >> 3) * 128 + (fold & 7) * 16 + (u0 & 7) * 2;
+    const bool profiling = (p.prof != nullptr) && cta == 0 && tid == 0;
+    long long tprof[5] = {0, 0, 0, 0, 0};
+    auto publish = [&](unsigned char* img, const float* v) {   // this fold's 4 values of this CTA's units
+      uint2 w;
+      w.x = pack2<FMT>(v[0], v[1]); w.y = pack2<FMT>(v[2], v[3]);
+      if (owns_fold) *reinterpret_cast<uint2*>(img + pub_off) = w;
+    };
+    auto signal = [&](int v) {                           // all fold warps have stored: one release increment per CTA
+      tc_fence_before();
+      named_bar_sync(1, 128);
+      if (tid == 0) red_release_add_u32(p.counters + v, 1u);
+    };
+    float h1[U] = {0.f, 0.f, 0.f, 0.f}, h2[U] = {0.f, 0.f, 0.f, 0.f};
+    float x = 0.f;
+    unsigned n_mma = 0;                                   // completed phases of bar_mma
+
+    for (int t = 0; t < S; ++t) {
+      const int par = t & 1;
+      const uint32_t tq = (par ? TC_Q1 : TC_Q0);
+      unsigned char* img_h1 = p.xch + 0 * xch_stride + (size_t)par * img_bytes;
+      unsigned char* img_h2 = p.xch + 1 * xch_stride + (size_t)par * img_bytes;
+      unsigned char* img_y1 = p.xch + 2 * xch_stride + (size_t)par * img_bytes;
+      unsigned char* img_y2 = p.xch + 3 * xch_stride + (size_t)par * img_bytes;
+      long long tp0 = 0;
+      if (profiling) tp0 = clock64();
+
+      // draws for this step, fetched early so their latency hides under the step
+      float ur[11];
 #pragma unroll
-    for (int j = 0; j < COND_TASKS; ++j) {
-      const int task = (tid - 128) + j * 128;
-      creg[j][0] = make_float4(0.f, 0.f, 0.f, 0.f); creg[j][1] = creg[j][0];
-      if (task < n_tasks) {
-        const int f = task / KQ, c8 = task % KQ;
-        const long long row = (long long)f * p.seg_stride + ts;
-        if (row < p.L) {
-          const float* src = (c8 < FEAT / 8) ? p.mels_up + row * FEAT + c8 * 8 : p.aux + row * (4 * AUXD) + (c8 - FEAT / 8) * 8;
-          creg[j][0] = __ldg(reinterpret_cast<const float4*>(src));
-          creg[j][1] = __ldg(reinterpret_cast<const float4*>(src) + 1);
+      for (int i = 0; i < 11; ++i) ur[i] = 0.5f;
+      if (owns_fold) {
+        if (p.uniforms) {
+          const float* u = p.uniforms + (size_t)t * 11 * B;
+#pragma unroll
+          for (int i = 0; i < 10; ++i) ur[i] = __ldg(u + fold * 10 + i);
+          ur[10] = __ldg(u + 10 * B + fold);
+        } else {
+          const unsigned g = (unsigned)(p.seg_first + fold), k0 = (unsigned)p.seed, k1 = (unsigned)(p.seed >> 32), o0 = (unsigned)p.offset;
+          const Philox4 r0 = philox4x32_10((unsigned)t, g, 0u, o0, k0, k1), r1 = philox4x32_10((unsigned)t, g, 1u, o0, k0, k1),
+                        r2 = philox4x32_10((unsigned)t, g, 2u, o0, k0, k1);
+          ur[0] = u_ref_range(r0.x); ur[1] = u_ref_range(r0.y); ur[2] = u_ref_range(r0.z); ur[3] = u_ref_range(r0.w);
+          ur[4] = u_ref_range(r1.x); ur[5] = u_ref_range(r1.y); ur[6] = u_ref_range(r1.z); ur[7] = u_ref_range(r1.w);
+          ur[8] = u_ref_range(r2.x); ur[9] = u_ref_range(r2.y); ur[10] = u_ref_range(r2.z);
         }
       }
-    }
-  };
-  auto cond_store = [&](int ts) {
-    const int n_tasks = B * KQ;
-    if (!cond_deferred) {                                // larger tiles: fetch + convert + store in place
-      for (int task = tid - 128; task < n_tasks; task += 128) {
-        const int f = task / KQ, c8 = task % KQ;
-        const long long row = (long long)f * p.seg_stride + ts;
-        float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
-        if (row < p.L) {
-          const float* src = (c8 < FEAT / 8) ? p.mels_up + row * FEAT + c8 * 8 : p.aux + row * (4 * AUXD) + (c8 - FEAT / 8) * 8;
-          a = __ldg(reinterpret_cast<const float4*>(src)); b = __ldg(reinterpret_cast<const float4*>(src) + 1);
-        }
-        uint4 v;
-        v.x = pack2<FMT>(a.x, a.y); v.y = pack2<FMT>(a.z, a.w); v.z = pack2<FMT>(b.x, b.y); v.w = pack2<FMT>(b.z, b.w);
-        *reinterpret_cast<uint4*>(smem + OFF_COND + (f >> 3) * SBO_Q + c8 * 128 + (f & 7) * 16) = v;
-      }
-      return;
-    }
-#pragma unroll
-    for (int j = 0; j < COND_TASKS; ++j) {
-      const int task = (tid - 128) + j * 128;
-      if (task < n_tasks) {
-        const int f = task / KQ, c8 = task % KQ;
-        uint4 v;
-        v.x = pack2<FMT>(creg[j][0].x, creg[j][0].y); v.y = pack2<FMT>(creg[j][0].z, creg[j][0].w);
-        v.z = pack2<FMT>(creg[j][1].x, creg[j][1].y); v.w = pack2<FMT>(creg[j][1].z, creg[j][1].w);
-        *reinterpret_cast<uint4*>(smem + OFF_COND + (f >> 3) * SBO_Q + c8 * 128 + (f & 7) * 16) = v;
-      }
-    }
-  };
-  auto issue_chain = [&](int off_b, int sbo_b, int off_a, int sbo_a, int ksteps, uint32_t d_col, uint32_t idesc, uint32_t bar) {
-    // D[64 folds, N] = A[64, K] * B[N, K]^T, K = 16 per instruction (two 8-element core-matrix columns = 256 B)
-    tc_fence_after();
-    const uint32_t a0 = smem_u32(smem + off_a), b0 = smem_u32(smem + off_b);
-    for (int k = 0; k < ksteps; ++k)
-      umma_f16(tmem + d_col, umma_desc(a0 + k * 256, 128, sbo_a), umma_desc(b0 + k * 256, 128, sbo_b), idesc, k > 0);
-    umma_commit(bar);
-  };
-  auto gather = [&](const unsigned char* img) {       // L2 image -> smem A image, flat 16-byte copy
-    const int4* src = reinterpret_cast<const int4*>(img);
-    int4* dst = reinterpret_cast<int4*>(smem + OFF_A);
-    for (int i = tid; i < gather_chunks; i += NT) dst[i] = __ldcg(src + i);
-    proxy_fence_smem();
-  };
-  auto publish = [&](unsigned char* img, const float* v) {   // this fold's 4 values of this CTA's units
-    uint2 w;
-    w.x = pack2<FMT>(v[0], v[1]); w.y = pack2<FMT>(v[2], v[3]);
-    *reinterpret_cast<uint2*>(img + (fold >> 3) * SBO_H + (u0 >> 3) * 128 + (fold & 7) * 16 + (u0 & 7) * 2) = w;
-  };
-  auto signal = [&](int v) {                           // fold warps have stored; one release increment per CTA
-    named_bar_sync(1, 128);
-    if (tid == 0) red_release_add_u32(p.counters + v, 1u);
-  };
-  auto wait_vec = [&](int v, unsigned target) {
-    if (tid == 0) counter_wait(p.counters + v, target, p.abort_flag);
-    tc_fence_before();
-    __syncthreads();
-  };
+      float xf = 0.f;
+      if (owns_fold && p.x_force && t > 0) xf = __ldg(p.x_force + (size_t)(t - 1) * B + fold);
 
-  // ---- prologue: pre_0 = Q cond_0 ------------------------------------------------------------
-  if (!fold_warp) { cond_fetch(0); cond_store(0); proxy_fence_smem(); }
-  tc_fence_before();
-  __syncthreads();
-  if (issuer) issue_chain(OFF_Q, SBO_Q, OFF_COND, SBO_Q, CDIM / 16, TC_Q0, idesc_q, bar_q);
-  if (!fold_warp && S > 1) cond_fetch(1);
-
-  float h1[U] = {0.f, 0.f, 0.f, 0.f}, h2[U] = {0.f, 0.f, 0.f, 0.f};
-  float x = 0.f;
-  unsigned n_mma = 0;                                   // completed uses of bar_mma (parity)
-  const size_t xch_stride = (size_t)2 * img_bytes;      // per vector: two parities
-  long long tprof[6] = {0, 0, 0, 0, 0, 0};
-  const bool profiling = (p.prof != nullptr) && cta == 0 && tid == 0;
-
-  for (int t = 0; t < S; ++t) {
-    const int par = t & 1;
-    const uint32_t tq = (par ? TC_Q1 : TC_Q0);
-    unsigned char* img_h1 = p.xch + 0 * xch_stride + (size_t)par * img_bytes;
-    unsigned char* img_h2 = p.xch + 1 * xch_stride + (size_t)par * img_bytes;
-    unsigned char* img_y1 = p.xch + 2 * xch_stride + (size_t)par * img_bytes;
-    unsigned char* img_y2 = p.xch + 3 * xch_stride + (size_t)par * img_bytes;
-    const unsigned target = (unsigned)P * (unsigned)(t + 1);
-    long long tp0 = 0;
-    if (profiling) tp0 = clock64();
-
-    // draws for this step, fetched early so their latency hides under the step
-    float ur[11];
+      // ---- A: GRU1.  gi1 = pre_t (conditioning chain, D_Q) + x * v1 ; gh1 = W1h h1 + b1h (D_S1 of step t-1)
+      float pre[32];                                      // this fold's 32 conditioning rows (+ qk + x*vq)
+      {
+        mbar_wait(bar_q, (uint32_t)(t & 1), p.abort_flag);           // pre_t landed in D_Q[par]
+        tc_fence_after();
+        if (p.x_force && t > 0) x = xf;
 #pragma unroll
-    for (int i = 0; i < 11; ++i) ur[i] = 0.5f;
-    if (owns_fold) {
-      if (p.uniforms) {
-        const float* u = p.uniforms + (size_t)t * 11 * B;
-#pragma unroll
-        for (int i = 0; i < 10; ++i) ur[i] = __ldg(u + fold * 10 + i);
-        ur[10] = __ldg(u + 10 * B + fold);
-      } else {
-        const unsigned g = (unsigned)(p.seg_first + fold), k0 = (unsigned)p.seed, k1 = (unsigned)(p.seed >> 32), o0 = (unsigned)p.offset;
-        const Philox4 r0 = philox4x32_10((unsigned)t, g, 0u, o0, k0, k1), r1 = philox4x32_10((unsigned)t, g, 1u, o0, k0, k1),
-                      r2 = philox4x32_10((unsigned)t, g, 2u, o0, k0, k1);
-        const unsigned rv[12] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, r2.y, r2.z, r2.w};
-#pragma unroll
-        for (int i = 0; i < 11; ++i) ur[i] = u_ref_range(rv[i]);
-      }
-    }
-    float xf = 0.f;
-    if (owns_fold && p.x_force && t > 0) xf = __ldg(p.x_force + (size_t)(t - 1) * B + fold);
-
-    // ---- A: GRU1.  gi1 = pre_t (conditioning, D_Q) + x * v1 ; gh1 = W1h h1 + b1h (D_S1 of step t-1)
-    float pre[32];                                      // this fold's 32 conditioning rows (+ qk + x*vq)
-    if (fold_warp) {
-      mbar_wait(bar_q, (uint32_t)(t & 1), p.abort_flag);           // pre_t landed in D_Q[par]
-      tc_fence_after();
-      if (p.x_force && t > 0) x = xf;
-#pragma unroll
-      for (int c = 0; c < 32; c += 4) tmem_ld4(tlane + tq + c, pre + c);
-      float gh[12];
-      if (t > 0) {
+        for (int c = 0; c < 32; c += 4) tmem_ld4(tlane + tq + c, pre + c);
+        float gh[12];
 #pragma unroll
         for (int c = 0; c < 12; c += 4) tmem_ld4(tlane + TC_S1 + 12 + c, gh + c);
-      }
-      tmem_ld_wait();
+        tmem_ld_wait();
 #pragma unroll
-      for (int q = 0; q < 32; ++q) pre[q] += qk[q] + x * vq[q];
-      float hv[U];
+        for (int q = 0; q < 32; ++q) pre[q] += qk[q] + x * vq[q];
+        float hv[U];
 #pragma unroll
-      for (int j = 0; j < U; ++j) {
-        const float ghr = (t > 0 ? gh[j] : 0.f) + b1h[j], ghz = (t > 0 ? gh[U + j] : 0.f) + b1h[U + j],
-                    ghn = (t > 0 ? gh[2 * U + j] : 0.f) + b1h[2 * U + j];
-        h1[j] = gru_unit(pre[j], pre[U + j], pre[2 * U + j], ghr, ghz, ghn, h1[j]);
-        hv[j] = h1[j];
+        for (int j = 0; j < U; ++j) {
+          const float ghr = (t > 0 ? gh[j] : 0.f) + b1h[j], ghz = (t > 0 ? gh[U + j] : 0.f) + b1h[U + j],
+                      ghn = (t > 0 ? gh[2 * U + j] : 0.f) + b1h[2 * U + j];
+          h1[j] = gru_unit_fast(pre[j], pre[U + j], pre[2 * U + j], ghr, ghz, ghn, h1[j]);
+          hv[j] = h1[j];
+        }
+        publish(img_h1, hv);
+        signal(0);
       }
-      if (owns_fold) publish(img_h1, hv);
-      signal(0);
-    }
-    if (profiling) { tprof[0] += clock64() - tp0; tp0 = clock64(); }
+      if (profiling) { const long long c = clock64(); tprof[0] += c - tp0; tp0 = c; }
 
-    // ---- B: [W2x ; W1h ; F1x] h1'  ->  GRU2, gh1 for step t+1, fc1 partial ---------------------
-    wait_vec(0, target);
-    gather(img_h1);
-    tc_fence_before();
-    __syncthreads();
-    if (issuer) issue_chain(OFF_S1, SBO_H, OFF_A, SBO_H, H / 16, TC_S1, idesc_s1, bar_mma);
-    if (fold_warp) {
-      mbar_wait(bar_mma, n_mma & 1, p.abort_flag);
-      tc_fence_after();
-      float gi[12], gh[12];
+      // ---- B: [W2x ; W1h ; F1x] h1'  ->  GRU2, gh1 for step t+1, fc1 partial ---------------------
+      {
+        mbar_wait(bar_mma, n_mma & 1, p.abort_flag); ++n_mma;
+        tc_fence_after();
+        float gi[12], gh[12];
 #pragma unroll
-      for (int c = 0; c < 12; c += 4) tmem_ld4(tlane + TC_S1 + c, gi + c);
-      if (t > 0) {
+        for (int c = 0; c < 12; c += 4) tmem_ld4(tlane + TC_S1 + c, gi + c);
 #pragma unroll
         for (int c = 0; c < 12; c += 4) tmem_ld4(tlane + TC_S2 + 4 + c, gh + c);
-      }
-      tmem_ld_wait();
-      float hv[U];
+        tmem_ld_wait();
+        float hv[U];
 #pragma unroll
-      for (int j = 0; j < U; ++j) {
-        const float ghr = (t > 0 ? gh[j] : 0.f) + b2h[j], ghz = (t > 0 ? gh[U + j] : 0.f) + b2h[U + j],
-                    ghn = (t > 0 ? gh[2 * U + j] : 0.f) + b2h[2 * U + j];
-        h2[j] = gru_unit(gi[j] + pre[3 * U + j], gi[U + j] + pre[4 * U + j], gi[2 * U + j] + pre[5 * U + j], ghr, ghz, ghn, h2[j]);
-        hv[j] = h2[j];
+        for (int j = 0; j < U; ++j) {
+          const float ghr = (t > 0 ? gh[j] : 0.f) + b2h[j], ghz = (t > 0 ? gh[U + j] : 0.f) + b2h[U + j],
+                      ghn = (t > 0 ? gh[2 * U + j] : 0.f) + b2h[2 * U + j];
+          h2[j] = gru_unit_fast(gi[j] + pre[3 * U + j], gi[U + j] + pre[4 * U + j], gi[2 * U + j] + pre[5 * U + j], ghr, ghz, ghn, h2[j]);
+          hv[j] = h2[j];
+        }
+        publish(img_h2, hv);
+        signal(1);
       }
-      if (owns_fold) publish(img_h2, hv);
-      signal(1);
-    }
-    ++n_mma;
-    if (profiling) { tprof[1] += clock64() - tp0; tp0 = clock64(); }
+      if (profiling) { const long long c = clock64(); tprof[1] += c - tp0; tp0 = c; }
 
-    // ---- C: [F1x ; W2h] h2'  ->  y1 = relu(fc1), gh2 for step t+1 ------------------------------
-    wait_vec(1, target);
-    gather(img_h2);
-    tc_fence_before();
-    __syncthreads();
-    if (issuer) issue_chain(OFF_S2, SBO_H, OFF_A, SBO_H, H / 16, TC_S2, idesc_s2, bar_mma);
-    if (!fold_warp) {
-      // staging warps: conditioning of step t+1 (fetched one phase ago) -> smem image -> Q chain
-      if (t + 1 < S) {
-        cond_store(t + 1);
-        proxy_fence_smem();
-        tc_fence_before();
+      // ---- C: [F1x ; W2h] h2'  ->  y1 = relu(fc1), gh2 for step t+1 ------------------------------
+      {
+        mbar_wait(bar_mma, n_mma & 1, p.abort_flag); ++n_mma;
+        tc_fence_after();
+        float a[4], b4[4];
+        tmem_ld4(tlane + TC_S2, a);                      // F1x h2'
+        tmem_ld4(tlane + TC_S1 + 24, b4);                // F1x h1' (phase B)
+        tmem_ld_wait();
+        float yv[U];
+#pragma unroll
+        for (int j = 0; j < U; ++j) yv[j] = fmaxf(a[j] + b4[j] + pre[6 * U + j], 0.f);
+        publish(img_y1, yv);
+        signal(2);
+      }
+      if (profiling) { const long long c = clock64(); tprof[2] += c - tp0; tp0 = c; }
+
+      // ---- D: F2x y1 -> y2 = relu(fc2) --------------------------------------------------------------
+      {
+        mbar_wait(bar_mma, n_mma & 1, p.abort_flag); ++n_mma;
+        tc_fence_after();
+        float a[4];
+        tmem_ld4(tlane + TC_S3, a);
+        tmem_ld_wait();
+        float yv[U];
+#pragma unroll
+        for (int j = 0; j < U; ++j) yv[j] = fmaxf(a[j] + pre[7 * U + j], 0.f);
+        publish(img_y2, yv);
+        signal(3);
+      }
+      if (profiling) { const long long c = clock64(); tprof[3] += c - tp0; tp0 = c; }
+
+      // ---- E: logits = F3 y2 + b3, MoL sample (replicated in every CTA) -----------------------------
+      {
+        mbar_wait(bar_mma, n_mma & 1, p.abort_flag); ++n_mma;
+        tc_fence_after();
+        float lg[32];
+#pragma unroll
+        for (int c = 0; c < 32; c += 4) tmem_ld4(tlane + TC_F3 + c, lg + c);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 30; ++i) lg[i] += b3[i];
+        x = mol_sample_fast(lg, ur);
+        if (owns_fold && cta == 0) {
+          p.out[(size_t)fold * p.out_pitch + t] = x;
+          if (p.logits_out) {
+#pragma unroll
+            for (int i = 0; i < 30; ++i) p.logits_out[((size_t)t * B + fold) * 30 + i] = lg[i];
+          }
+        }
+      }
+      if (profiling) { tprof[4] += clock64() - tp0; }
+      if (ld_relaxed_s32(p.abort_flag) != 0) break;      // every wait is bounded; leave promptly
+    }
+    if (profiling) for (int i = 0; i < 5; ++i) p.prof[i] = tprof[i];
+
+  } else if (warp == 4) {
+    // =========================================================================================
+    // driver warp: arrival counters -> TMA gather -> tcgen05.mma chains
+    // =========================================================================================
+    const uint32_t sA = smem_u32(smem + OFF_A);
+    const uint64_t dA = umma_desc(sA, 128, SBO_H), dC = umma_desc(smem_u32(smem + OFF_COND), 128, SBO_Q);
+    const uint64_t dS1 = umma_desc(smem_u32(smem + OFF_S1), 128, SBO_H), dS2 = umma_desc(smem_u32(smem + OFF_S2), 128, SBO_H),
+                   dS3 = umma_desc(smem_u32(smem + OFF_S3), 128, SBO_H), dF3 = umma_desc(smem_u32(smem + OFF_F3), 128, SBO_H),
+                   dQ = umma_desc(smem_u32(smem + OFF_Q), 128, SBO_Q);
+    const uint32_t idesc_s1 = umma_idesc(MT, N_S1, FMT), idesc_s2 = umma_idesc(MT, N_S2, FMT),
+                   idesc_s3 = umma_idesc(MT, N_S3, FMT), idesc_f3 = umma_idesc(MT, N_F3, FMT),
+                   idesc_q = umma_idesc(MT, N_Q, FMT);
+    const bool profiling = (p.prof != nullptr) && cta == 0 && lane == 0;
+    long long t_poll = 0, t_gather = 0, t_issue = 0;
+    unsigned n_g = 0;
+    // D[64 folds, N] (+)= A[64, 16] * B[N, 16]^T per instruction; K advances by two core-matrix columns
+    // (256 B => +16 in the descriptor's address field; no carry: every image ends below 256 KB)
+    auto chain = [&](uint64_t da, uint64_t db, int ksteps, uint32_t d_col, uint32_t idesc, uint32_t bar) {
+      tc_fence_after();
+#pragma unroll 8
+      for (int k = 0; k < ksteps; ++k) umma_f16(tmem + d_col, da + (uint64_t)(k * 16), db + (uint64_t)(k * 16), idesc, k > 0);
+      umma_commit(bar);
+    };
+    auto fetch_and_chain = [&](int v, unsigned target, const unsigned char* img, uint64_t db, uint32_t d_col, uint32_t idesc) {
+      long long c0 = 0, c1 = 0, c2 = 0;
+      if (profiling) c0 = clock64();
+      if (lane == 0) counter_wait(p.counters + v, target, p.abort_flag);   // acquire: all 128 producers have published
+      __syncwarp();
+      proxy_fence_global();                                                // generic-proxy writes -> async-proxy (TMA) read
+      if (profiling) c1 = clock64();
+      tma_bulk_g2s(sA, img, img_bytes, bar_g);
+      mbar_wait(bar_g, n_g & 1, p.abort_flag); ++n_g;
+      if (profiling) c2 = clock64();
+      chain(dA, db, H / 16, d_col, idesc, bar_mma);
+      if (profiling) { const long long c3 = clock64(); t_poll += c1 - c0; t_gather += c2 - c1; t_issue += c3 - c2; }
+    };
+
+    named_bar_sync(2, 128);                               // stagers have written cond_0
+    chain(dC, dQ, CDIM / 16, TC_Q0, idesc_q, bar_q);
+    for (int t = 0; t < S; ++t) {
+      const int par = t & 1;
+      const unsigned target = (unsigned)P * (unsigned)(t + 1);
+      const unsigned char* base = p.xch + (size_t)par * img_bytes;
+      fetch_and_chain(0, target, base + 0 * xch_stride, dS1, TC_S1, idesc_s1);
+      fetch_and_chain(1, target, base + 1 * xch_stride, dS2, TC_S2, idesc_s2);
+      if (t + 1 < S) {                                    // conditioning chain for step t+1, behind S2 in the tensor pipe
         named_bar_sync(2, 128);
-        if (issuer) issue_chain(OFF_Q, SBO_Q, OFF_COND, SBO_Q, CDIM / 16, par ? TC_Q0 : TC_Q1, idesc_q, bar_q);
+        chain(dC, dQ, CDIM / 16, par ? TC_Q0 : TC_Q1, idesc_q, bar_q);
       }
-    } else {
-      mbar_wait(bar_mma, n_mma & 1, p.abort_flag);
-      tc_fence_after();
-      float a[4], b4[4];
-      tmem_ld4(tlane + TC_S2, a);                      // F1x h2'
-      tmem_ld4(tlane + TC_S1 + 24, b4);                // F1x h1' (phase B)
-      tmem_ld_wait();
-      float yv[U];
-#pragma unroll
-      for (int j = 0; j < U; ++j) yv[j] = fmaxf(a[j] + b4[j] + pre[6 * U + j], 0.f);
-      if (owns_fold) publish(img_y1, yv);
-      signal(2);
-    }
-    ++n_mma;
-    if (profiling) { tprof[2] += clock64() - tp0; tp0 = clock64(); }
-
-    // ---- D: F2x y1 -> y2 = relu(fc2) --------------------------------------------------------------
-    wait_vec(2, target);
-    gather(img_y1);
-    tc_fence_before();
-    __syncthreads();
-    if (issuer) issue_chain(OFF_S3, SBO_H, OFF_A, SBO_H, H / 16, TC_S3, idesc_s3, bar_mma);
-    if (!fold_warp) {
-      if (t + 2 < S) cond_fetch(t + 2);                // lands in registers while phases D, E, A, B run
-    } else {
-      mbar_wait(bar_mma, n_mma & 1, p.abort_flag);
-      tc_fence_after();
-      float a[4];
-      tmem_ld4(tlane + TC_S3, a);
-      tmem_ld_wait();
-      float yv[U];
-#pragma unroll
-      for (int j = 0; j < U; ++j) yv[j] = fmaxf(a[j] + pre[7 * U + j], 0.f);
-      if (owns_fold) publish(img_y2, yv);
-      signal(3);
-    }
-    ++n_mma;
-    if (profiling) { tprof[3] += clock64() - tp0; tp0 = clock64(); }
-
-    // ---- E: logits = F3 y2 + b3, MoL sample (replicated in every CTA) -----------------------------
-    wait_vec(3, target);
-    gather(img_y2);
-    tc_fence_before();
-    __syncthreads();
-    if (issuer) issue_chain(OFF_F3, SBO_H, OFF_A, SBO_H, H / 16, TC_F3, idesc_f3, bar_mma);
-    if (fold_warp) {
-      mbar_wait(bar_mma, n_mma & 1, p.abort_flag);
-      tc_fence_after();
-      float lg[32];
-#pragma unroll
-      for (int c = 0; c < 32; c += 4) tmem_ld4(tlane + TC_F3 + c, lg + c);
-      tmem_ld_wait();
-#pragma unroll
-      for (int i = 0; i < 30; ++i) lg[i] += b3[i];
-      x = mol_sample([&](int i) { return lg[i]; }, [&](int i) { return ur[i]; });
-      if (owns_fold && cta == 0) {
-        p.out[(size_t)fold * p.out_pitch + t] = x;
-        if (p.logits_out)
-          for (int i = 0; i < 30; ++i) p.logits_out[((size_t)t * B + fold) * 30 + i] = lg[i];
+      fetch_and_chain(2, target, base + 2 * xch_stride, dS3, TC_S3, idesc_s3);
+      fetch_and_chain(3, target, base + 3 * xch_stride, dF3, TC_F3, idesc_f3);
+      if (ld_relaxed_s32(p.abort_flag) != 0) {            // keep the stagers' barrier protocol consistent, then leave
+        for (int r = t + 2; r < S; ++r) named_bar_sync(2, 128);
+        break;
       }
     }
-    ++n_mma;
-    if (profiling) { tprof[4] += clock64() - tp0; }
-    if (ld_relaxed_s32(p.abort_flag) != 0) break;      // every wait above is bounded; leave promptly
+    if (profiling) { p.prof[5] = t_poll; p.prof[6] = t_gather; p.prof[7] = t_issue; }
+
+  } else {
+    // =========================================================================================
+    // cond stagers (warps 5-7): cond_n rows -> fp16/bf16 A image, one step ahead
+    // =========================================================================================
+    const int st = tid - 160;
+    constexpr int COND_TASKS = 6;                          // (fold, 8-column chunk) tasks held in registers per thread
+    const int n_tasks = B * KQ;
+    const bool deferred = n_tasks <= COND_TASKS * N_STAGERS;   // n_seg <= 22: loads fly a whole step before use
+    float4 creg[COND_TASKS][2];
+    auto src_of = [&](int f, int c8, long long row) -> const float4* {
+      const float* s = (c8 < FEAT / 8) ? p.mels_up + row * FEAT + c8 * 8 : p.aux + row * (4 * AUXD) + (c8 - FEAT / 8) * 8;
+      return reinterpret_cast<const float4*>(s);
+    };
+    auto store_task = [&](int f, int c8, const float4& a, const float4& b) {
+      uint4 v;
+      v.x = pack2<FMT>(a.x, a.y); v.y = pack2<FMT>(a.z, a.w); v.z = pack2<FMT>(b.x, b.y); v.w = pack2<FMT>(b.z, b.w);
+      *reinterpret_cast<uint4*>(smem + OFF_COND + (f >> 3) * SBO_Q + c8 * 128 + (f & 7) * 16) = v;
+    };
+    auto fetch = [&](int n) {
+#pragma unroll
+      for (int j = 0; j < COND_TASKS; ++j) {
+        const int task = st + j * N_STAGERS;
+        creg[j][0] = make_float4(0.f, 0.f, 0.f, 0.f); creg[j][1] = creg[j][0];
+        if (task < n_tasks) {
+          const int f = task / KQ, c8 = task % KQ;
+          const long long row = (long long)f * p.seg_stride + n;
+          if (row < p.L) { const float4* s = src_of(f, c8, row); creg[j][0] = __ldg(s); creg[j][1] = __ldg(s + 1); }
+        }
+      }
+    };
+    if (deferred) fetch(0);
+    for (int n = 0; n < S; ++n) {
+      if (n > 0) mbar_wait(bar_q, (uint32_t)((n - 1) & 1), p.abort_flag);   // chain n-1 has consumed the image
+      if (deferred) {
+#pragma unroll
+        for (int j = 0; j < COND_TASKS; ++j) {
+          const int task = st + j * N_STAGERS;
+          if (task < n_tasks) store_task(task / KQ, task % KQ, creg[j][0], creg[j][1]);
+        }
+      } else {
+        for (int task = st; task < n_tasks; task += N_STAGERS) {
+          const int f = task / KQ, c8 = task % KQ;
+          const long long row = (long long)f * p.seg_stride + n;
+          float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+          if (row < p.L) { const float4* s = src_of(f, c8, row); a = __ldg(s); b = __ldg(s + 1); }
+          store_task(f, c8, a, b);
+        }
+      }
+      proxy_fence_smem();
+      named_bar_sync(2, 128);                              // hand the image to the driver warp
+      if (deferred && n + 1 < S) fetch(n + 1);
+    }
   }
 
-  if (profiling) for (int i = 0; i < 5; ++i) p.prof[i] = tprof[i];
   tc_fence_before();
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "n"(TMEM_COLS));
@@ -546,7 +588,7 @@ class TcEngine : public Engine {
     p.blob = static_cast<const unsigned char*>(d_blob_);
     p.mels_up = job.mels_up; p.aux = job.aux; p.L = job.L; p.seg_stride = job.seg_stride;
     p.n_seg = job.n_seg; p.steps = job.steps > 0 ? job.steps : job.seg_len; p.out_pitch = p.steps;
-    p.seg_first = job.seg_first; p.fmt = cfg.precision == WRNN_PREC_BF16;
+    p.seg_first = job.seg_first;
     p.uniforms = job.uniforms; p.seed = job.philox_seed; p.offset = job.philox_offset;
     p.out = job.out; p.x_force = job.x_force; p.logits_out = job.logits_out;
     p.xch = static_cast<unsigned char*>(d_scratch_);
@@ -566,18 +608,20 @@ class TcEngine : public Engine {
     WRNN_CUDA_OK(cudaMemcpy(buf, d_sync_, 256, cudaMemcpyDeviceToHost));
     const int flag = reinterpret_cast<int*>(buf)[8];
     std::memcpy(prof, buf + 64, sizeof(prof));
-    if (getenv("WRNN_TC_PROF") && last_steps_ > 0) {     // average cycles per phase seen by CTA 0 / thread 0
-      fprintf(stderr, "[wrnn_tc prof] steps=%d  A(gru1)=%lld  B(h1'->gru2)=%lld  C(h2'->y1)=%lld  D(y1->y2)=%lld  E(y2->sample)=%lld cycles/step\n",
-              last_steps_, prof[0] / last_steps_, prof[1] / last_steps_, prof[2] / last_steps_, prof[3] / last_steps_, prof[4] / last_steps_);
+    if (getenv("WRNN_TC_PROF") && last_steps_ > 0) {     // average cycles per step seen by CTA 0
+      const long long n = last_steps_;
+      fprintf(stderr, "[wrnn_tc prof] steps=%d | fold thread: A(gru1)=%lld B(h1'->gru2)=%lld C(h2'->y1)=%lld D(y1->y2)=%lld "
+              "E(y2->sample)=%lld | driver warp: poll=%lld gather=%lld issue=%lld  (cycles per step)\n",
+              last_steps_, prof[0] / n, prof[1] / n, prof[2] / n, prof[3] / n, prof[4] / n, prof[5] / n, prof[6] / n, prof[7] / n);
     }
     if (flag != 0) {
-      set_error(flag == 2 ? "persistent kernel aborted: an MMA-completion mbarrier wait timed out"
+      set_error(flag == 2 ? "persistent kernel aborted: an mbarrier wait (MMA / TMA completion) timed out"
                           : "persistent kernel aborted: an inter-SM exchange wait timed out");
       return WRNN_E_WATCHDOG;
     }
     return WRNN_OK;
   }
-  long long prof[6] = {0, 0, 0, 0, 0, 0};
+  long long prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 
  private:
   void *d_blob_ = nullptr, *d_scratch_ = nullptr, *d_sync_ = nullptr;
