@@ -29,6 +29,38 @@ __device__ __forceinline__ bool barrier(unsigned* ctr, unsigned target) {
   return true;
 }
 
+// variant: relaxed polling by 4 staggered lanes (one per warp 0..3), one acquire fence after success
+__device__ __forceinline__ void barrier_staggered(unsigned* ctr, unsigned target) {
+  __shared__ volatile int s_go;
+  if (threadIdx.x == 0) s_go = 0;
+  __syncthreads();
+  if (threadIdx.x == 0) red_rel(ctr);
+  if ((threadIdx.x & 31) == 0 && threadIdx.x < 128) {
+    const int k = threadIdx.x >> 5;
+    long long t0 = clock64();
+    while (clock64() - t0 < 170 * k) {}                      // stagger the poll phases by ~170 cycles
+    unsigned v;
+    do {
+      asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+    } while (v < target && s_go == 0 && clock64() - t0 < (1ll << 28));
+    asm volatile("fence.acq_rel.gpu;" ::: "memory");
+    s_go = 1;
+  }
+  __syncthreads();
+}
+
+// variant: no release/acquire at all (red.relaxed + ld.relaxed): the bare arrival cost
+__device__ __forceinline__ void barrier_relaxed(unsigned* ctr, unsigned target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
+    long long t0 = clock64();
+    unsigned v;
+    do { asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory"); } while (v < target && clock64() - t0 < (1ll << 28));
+  }
+  __syncthreads();
+}
+
 __global__ void __launch_bounds__(NT, 1) probe(unsigned* ctr, unsigned char* img, long long* result, int mode) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ uint64_t mbar;
@@ -38,10 +70,45 @@ __global__ void __launch_bounds__(NT, 1) probe(unsigned* ctr, unsigned char* img
   barrier(ctr, ++nb * P);
   const long long t0 = clock64();
   unsigned acc = 0;
+  int failed = 0;
+  __shared__ int dbg_once_s; int* dbg_once = &dbg_once_s; if (tid == 0) dbg_once_s = 0;
   for (int r = 0; r < ROUNDS; ++r) {
     unsigned char* buf = img + (size_t)(r & 1) * IMG * 2;
     if (mode == 0) {
       barrier(ctr, ++nb * P);
+    } else if (mode == 4) {
+      barrier_staggered(ctr, ++nb * P);
+    } else if (mode == 5) {
+      barrier_relaxed(ctr, ++nb * P);
+    } else if (mode == 6) {
+      // flag-in-data, polite polling: one 16 B chunk per producer CTA is polled with back-off by ONE warp,
+      // everything else is fetched once the probes are in
+      const unsigned tag = (unsigned)r + 1;
+      if (tid < 12) {
+        int4 v = make_int4(cta, tid, r, (int)tag);
+        asm volatile("st.global.cg.v4.s32 [%0], {%1,%2,%3,%4};" :: "l"(reinterpret_cast<int4*>(buf) + cta * 12 + tid), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+      }
+      if (tid < 128) {                       // thread k watches the LAST chunk of producer k
+        int4 v; long long tw = clock64();
+        for (;;) {
+          asm volatile("ld.global.cg.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(reinterpret_cast<const int4*>(buf) + tid * 12 + 11) : "memory");
+          if ((unsigned)v.w == tag || clock64() - tw > (1ll << 24)) break;
+          __nanosleep(40);
+        }
+        if ((unsigned)v.w != tag) failed = 1;
+      }
+      if (__syncthreads_or(failed)) { if (cta == 0 && tid == 0) result[24] = r + 1; break; }
+      for (int i = tid; i < IMG / 16; i += NT) {
+        int4 v;
+        long long tw = clock64();
+        do {
+          asm volatile("ld.global.cg.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(reinterpret_cast<const int4*>(buf) + i) : "memory");
+        } while ((unsigned)v.w != tag && clock64() - tw < (1ll << 24));
+        if ((unsigned)v.w != tag) failed = 1;
+        reinterpret_cast<int4*>(smem)[i] = v;
+      }
+      if (__syncthreads_or(failed)) { if (cta == 0 && tid == 0) result[24] = r + 1; break; }
+      acc += reinterpret_cast<unsigned*>(smem)[(tid * 4) % (IMG / 4)];
     } else if (mode == 1 || mode == 2) {
       // publish: 19 folds x 8 bytes (4 halfs of this CTA's units)
       if (tid < 19) *reinterpret_cast<uint2*>(buf + (tid / 8) * 8192 + (cta / 2) * 128 + (tid % 8) * 16 + (cta % 2) * 8) = make_uint2(r, cta);
@@ -77,10 +144,14 @@ __global__ void __launch_bounds__(NT, 1) probe(unsigned* ctr, unsigned char* img
         long long tw = clock64();
         do {
           asm volatile("ld.global.cg.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(reinterpret_cast<const int4*>(buf) + i) : "memory");
-        } while ((unsigned)v.w != tag && clock64() - tw < (1ll << 26));
+        } while ((unsigned)v.w != tag && clock64() - tw < (1ll << 24));
+        if ((unsigned)v.w != tag && cta == 0 && atomicAdd(dbg_once, 1) == 0) {
+          result[16] = i; result[17] = v.w; result[18] = tag; result[19] = r; result[20] = v.x; result[21] = v.y; result[22] = v.z;
+        }
+        if ((unsigned)v.w != tag) { failed = 1; }
         reinterpret_cast<int4*>(smem)[i] = v;
       }
-      __syncthreads();
+      if (__syncthreads_or(failed)) break;
       acc += reinterpret_cast<unsigned*>(smem)[(tid * 4) % (IMG / 4)];
     }
   }
@@ -94,13 +165,16 @@ int main() {
   CK(cudaMemset(res, 0, 256));
   CK(cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, IMG + 1024));
   const char* names[] = {"A counter barrier only", "B publish + barrier + LDG gather 24KB", "C publish + barrier + TMA bulk gather 24KB",
-                         "D flag-in-data gather 24KB (no barrier)"};
-  for (int mode = 0; mode < 4; ++mode) {
+                         "D flag-in-data gather 24KB (no barrier)", "E counter barrier, 4 staggered relaxed pollers",
+                         "F counter barrier, red.relaxed + ld.relaxed (no fences)", "G flag-in-data, polite probe + LDG gather 24KB"};
+  for (int mode = 0; mode < 7; ++mode) {
     CK(cudaMemset(ctr, 0, 64)); CK(cudaMemset(img, 0, IMG * 4));
     void* args[] = {&ctr, &img, &res, &mode};
     CK(cudaLaunchCooperativeKernel((const void*)probe, dim3(P), dim3(NT), args, IMG + 1024, 0));
     CK(cudaDeviceSynchronize());
-    long long h[16]; CK(cudaMemcpy(h, res, 128, cudaMemcpyDeviceToHost));
+    long long h[32]; CK(cudaMemcpy(h, res, 256, cudaMemcpyDeviceToHost));
+    if (mode == 6 && h[24]) printf("   mode G FAILED at round %lld\n", h[24] - 1);
+    if (mode == 3 && h[18]) printf("   mode D first timeout: chunk %lld saw tag %lld (x=%lld y=%lld z=%lld) wanted %lld at round %lld\n", h[16], h[17], h[20], h[21], h[22], h[18], h[19]);
     printf("%-45s : %6lld cycles/round%s\n", names[mode], h[mode], (mode == 2 && h[4]) ? "  (TMA wait TIMED OUT)" : "");
     fflush(stdout);
   }

@@ -23,7 +23,7 @@
 // identical samples), which removes the fifth exchange of the step.
 //
 // Warp roles (no CTA-wide barrier inside the step loop):
-//   warps 0-3  fold warps   : TMEM -> registers, gates / relu / sampler, publish, signal
+//   warps 0-3  fold warps   : TMEM -> registers (sum of the K-quarter partials), gates / relu / sampler, publish, signal
 //   warp  4    driver       : polls arrival counters, launches the TMA gather, issues every
 //                             tcgen05.mma chain (warp-uniform, elect.sync-predicated)
 //   warps 5-7  cond stagers : stream cond_{t+1} HBM -> registers -> fp16 operand image, one
@@ -72,7 +72,12 @@ constexpr int WEIGHT_BYTES = OFF_VEC + NVEC * 4 - OFF_S1; // per-CTA blob == sme
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 
 // TMEM columns (fp32 accumulators; M=64 => lanes 0-15 of each lane quarter)
-constexpr int TC_S1 = 0, TC_S2 = 32, TC_S3 = 48, TC_F3 = 64, TC_Q0 = 96, TC_Q1 = 128, TMEM_COLS = 256;
+// Every K=512 chain is split over KW issuing warps (K quarters), each accumulating into its own columns;
+// the fold threads add the KW partials when they read them (fixed order => identical in every CTA).
+constexpr int KW = 4;
+constexpr int TC_S1 = 0, TC_S2 = TC_S1 + KW * N_S1, TC_S3 = TC_S2 + KW * N_S2, TC_F3 = TC_S3 + KW * N_S3,
+              TC_Q0 = TC_F3 + KW * N_F3, TC_Q1 = TC_Q0 + N_Q, TMEM_COLS = 512;
+static_assert(TC_Q1 + N_Q <= TMEM_COLS, "TMEM budget");
 
 struct TcParams {
   const unsigned char* blob;
@@ -129,6 +134,24 @@ __device__ __forceinline__ void tmem_ld4(uint32_t taddr, float* v) {
   v[0] = __uint_as_float(a); v[1] = __uint_as_float(b); v[2] = __uint_as_float(c); v[3] = __uint_as_float(d);
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// out[0 .. 4*NG) = sum over the KW partial accumulators (column stride `wstride`) of 4*NG columns at taddr
+template <int NG, int NW>
+__device__ __forceinline__ void tmem_ld_sum(uint32_t taddr, int wstride, float* out) {
+  float part[NW > 1 ? NW - 1 : 1][4 * NG];
+#pragma unroll
+  for (int g = 0; g < NG; ++g) tmem_ld4(taddr + 4 * g, out + 4 * g);
+#pragma unroll
+  for (int w = 1; w < NW; ++w) {
+#pragma unroll
+    for (int g = 0; g < NG; ++g) tmem_ld4(taddr + w * wstride + 4 * g, part[w - 1] + 4 * g);
+  }
+  tmem_ld_wait();
+#pragma unroll
+  for (int w = 1; w < NW; ++w) {
+#pragma unroll
+    for (int i = 0; i < 4 * NG; ++i) out[i] += part[w - 1][i];
+  }
+}
 __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
@@ -224,7 +247,7 @@ __global__ void __launch_bounds__(NT, 1) wrnn_tc_kernel(const TcParams p) {
     for (int i = tid; i < OFF_S1 / 16; i += NT) z[i] = make_int4(0, 0, 0, 0);   // A images start as zeros
   }
   if (tid == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar_mma));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar_mma), "n"(KW));   // one commit per issuing warp
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar_q));
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar_g));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -304,9 +327,7 @@ __global__ void __launch_bounds__(NT, 1) wrnn_tc_kernel(const TcParams p) {
 #pragma unroll
         for (int c = 0; c < 32; c += 4) tmem_ld4(tlane + tq + c, pre + c);
         float gh[12];
-#pragma unroll
-        for (int c = 0; c < 12; c += 4) tmem_ld4(tlane + TC_S1 + 12 + c, gh + c);
-        tmem_ld_wait();
+        tmem_ld_sum<3, KW>(tlane + TC_S1 + 12, N_S1, gh);           // W1h h1 (step t-1, phase B); also completes `pre`
 #pragma unroll
         for (int q = 0; q < 32; ++q) pre[q] += qk[q] + x * vq[q];
         float hv[U];
@@ -327,11 +348,8 @@ __global__ void __launch_bounds__(NT, 1) wrnn_tc_kernel(const TcParams p) {
         mbar_wait(bar_mma, n_mma & 1, p.abort_flag); ++n_mma;
         tc_fence_after();
         float gi[12], gh[12];
-#pragma unroll
-        for (int c = 0; c < 12; c += 4) tmem_ld4(tlane + TC_S1 + c, gi + c);
-#pragma unroll
-        for (int c = 0; c < 12; c += 4) tmem_ld4(tlane + TC_S2 + 4 + c, gh + c);
-        tmem_ld_wait();
+        tmem_ld_sum<3, KW>(tlane + TC_S1, N_S1, gi);                // W2x h1'
+        tmem_ld_sum<3, KW>(tlane + TC_S2 + 4, N_S2, gh);            // W2h h2 (step t-1, phase C)
         float hv[U];
 #pragma unroll
         for (int j = 0; j < U; ++j) {
@@ -350,9 +368,8 @@ __global__ void __launch_bounds__(NT, 1) wrnn_tc_kernel(const TcParams p) {
         mbar_wait(bar_mma, n_mma & 1, p.abort_flag); ++n_mma;
         tc_fence_after();
         float a[4], b4[4];
-        tmem_ld4(tlane + TC_S2, a);                      // F1x h2'
-        tmem_ld4(tlane + TC_S1 + 24, b4);                // F1x h1' (phase B)
-        tmem_ld_wait();
+        tmem_ld_sum<1, KW>(tlane + TC_S2, N_S2, a);                 // F1x h2'
+        tmem_ld_sum<1, KW>(tlane + TC_S1 + 24, N_S1, b4);           // F1x h1' (phase B)
         float yv[U];
 #pragma unroll
         for (int j = 0; j < U; ++j) yv[j] = fmaxf(a[j] + b4[j] + pre[6 * U + j], 0.f);
@@ -366,8 +383,7 @@ __global__ void __launch_bounds__(NT, 1) wrnn_tc_kernel(const TcParams p) {
         mbar_wait(bar_mma, n_mma & 1, p.abort_flag); ++n_mma;
         tc_fence_after();
         float a[4];
-        tmem_ld4(tlane + TC_S3, a);
-        tmem_ld_wait();
+        tmem_ld_sum<1, KW>(tlane + TC_S3, N_S3, a);
         float yv[U];
 #pragma unroll
         for (int j = 0; j < U; ++j) yv[j] = fmaxf(a[j] + pre[7 * U + j], 0.f);
@@ -381,9 +397,8 @@ __global__ void __launch_bounds__(NT, 1) wrnn_tc_kernel(const TcParams p) {
         mbar_wait(bar_mma, n_mma & 1, p.abort_flag); ++n_mma;
         tc_fence_after();
         float lg[32];
-#pragma unroll
-        for (int c = 0; c < 32; c += 4) tmem_ld4(tlane + TC_F3 + c, lg + c);
-        tmem_ld_wait();
+        tmem_ld_sum<4, KW>(tlane + TC_F3, N_F3, lg);                // two halves keep the register peak down
+        tmem_ld_sum<4, KW>(tlane + TC_F3 + 16, N_F3, lg + 16);
 #pragma unroll
         for (int i = 0; i < 30; ++i) lg[i] += b3[i];
         x = mol_sample_fast(lg, ur);
@@ -396,78 +411,68 @@ __global__ void __launch_bounds__(NT, 1) wrnn_tc_kernel(const TcParams p) {
         }
       }
       if (profiling) { tprof[4] += clock64() - tp0; }
-      if (ld_relaxed_s32(p.abort_flag) != 0) break;      // every wait is bounded; leave promptly
+      // no early exit on abort: every wait is bounded and fails fast once the abort flag is up, and the
+      // named barriers must be executed the same number of times by all participating warps
     }
     if (profiling) for (int i = 0; i < 5; ++i) p.prof[i] = tprof[i];
 
-  } else if (warp == 4) {
+  } else {
     // =========================================================================================
-    // driver warp: arrival counters -> TMA gather -> tcgen05.mma chains
+    // issuer warps 4-7.  Warp q = warp-4 owns the K quarter [128q, 128q+128) of every K=512 chain and
+    // accumulates into its own TMEM columns.  Warp 4 ("leader") also watches the arrival counters and
+    // launches the TMA gather; warp 5 issues the conditioning chain; all four stage cond_{t+1}.
     // =========================================================================================
+    const int q = warp - 4;
+    const bool leader = (q == 0);
     const uint32_t sA = smem_u32(smem + OFF_A);
-    const uint64_t dA = umma_desc(sA, 128, SBO_H), dC = umma_desc(smem_u32(smem + OFF_COND), 128, SBO_Q);
-    const uint64_t dS1 = umma_desc(smem_u32(smem + OFF_S1), 128, SBO_H), dS2 = umma_desc(smem_u32(smem + OFF_S2), 128, SBO_H),
-                   dS3 = umma_desc(smem_u32(smem + OFF_S3), 128, SBO_H), dF3 = umma_desc(smem_u32(smem + OFF_F3), 128, SBO_H),
+    const uint64_t koff = (uint64_t)(q * (H / 16 / KW) * 16);             // descriptor address-field offset of this K quarter
+    const uint64_t dA = umma_desc(sA, 128, SBO_H) + koff, dC = umma_desc(smem_u32(smem + OFF_COND), 128, SBO_Q);
+    const uint64_t dS1 = umma_desc(smem_u32(smem + OFF_S1), 128, SBO_H) + koff, dS2 = umma_desc(smem_u32(smem + OFF_S2), 128, SBO_H) + koff,
+                   dS3 = umma_desc(smem_u32(smem + OFF_S3), 128, SBO_H) + koff, dF3 = umma_desc(smem_u32(smem + OFF_F3), 128, SBO_H) + koff,
                    dQ = umma_desc(smem_u32(smem + OFF_Q), 128, SBO_Q);
     const uint32_t idesc_s1 = umma_idesc(MT, N_S1, FMT), idesc_s2 = umma_idesc(MT, N_S2, FMT),
                    idesc_s3 = umma_idesc(MT, N_S3, FMT), idesc_f3 = umma_idesc(MT, N_F3, FMT),
                    idesc_q = umma_idesc(MT, N_Q, FMT);
-    const bool profiling = (p.prof != nullptr) && cta == 0 && lane == 0;
+    const bool profiling = (p.prof != nullptr) && cta == 0 && tid == 128;
     long long t_poll = 0, t_gather = 0, t_issue = 0;
     unsigned n_g = 0;
+
     // D[64 folds, N] (+)= A[64, 16] * B[N, 16]^T per instruction; K advances by two core-matrix columns
     // (256 B => +16 in the descriptor's address field; no carry: every image ends below 256 KB)
-    auto chain = [&](uint64_t da, uint64_t db, int ksteps, uint32_t d_col, uint32_t idesc, uint32_t bar) {
-      tc_fence_after();
-#pragma unroll 8
-      for (int k = 0; k < ksteps; ++k) umma_f16(tmem + d_col, da + (uint64_t)(k * 16), db + (uint64_t)(k * 16), idesc, k > 0);
-      umma_commit(bar);
-    };
-    auto fetch_and_chain = [&](int v, unsigned target, const unsigned char* img, uint64_t db, uint32_t d_col, uint32_t idesc) {
-      long long c0 = 0, c1 = 0, c2 = 0;
+    auto launch = [&](int v, unsigned target, const unsigned char* img) {      // leader only
+      long long c0 = 0;
       if (profiling) c0 = clock64();
-      if (lane == 0) counter_wait(p.counters + v, target, p.abort_flag);   // acquire: all 128 producers have published
+      if (lane == 0) counter_wait(p.counters + v, target, p.abort_flag);        // acquire: all 128 producers have published
       __syncwarp();
-      proxy_fence_global();                                                // generic-proxy writes -> async-proxy (TMA) read
-      if (profiling) c1 = clock64();
+      proxy_fence_global();                                                     // generic-proxy writes -> async-proxy (TMA) read
+      if (profiling) t_poll += clock64() - c0;
       tma_bulk_g2s(sA, img, img_bytes, bar_g);
-      mbar_wait(bar_g, n_g & 1, p.abort_flag); ++n_g;
-      if (profiling) c2 = clock64();
-      chain(dA, db, H / 16, d_col, idesc, bar_mma);
-      if (profiling) { const long long c3 = clock64(); t_poll += c1 - c0; t_gather += c2 - c1; t_issue += c3 - c2; }
+    };
+    auto quarter = [&](uint64_t db, uint32_t d_col, uint32_t idesc) {
+      long long c0 = 0, c1 = 0;
+      if (profiling) c0 = clock64();
+      mbar_wait(bar_g, n_g & 1, p.abort_flag); ++n_g;                           // the gathered vector is in smem
+      tc_fence_after();
+      if (profiling) c1 = clock64();
+#pragma unroll
+      for (int k = 0; k < H / 16 / KW; ++k) umma_f16(tmem + d_col, dA + (uint64_t)(k * 16), db + (uint64_t)(k * 16), idesc, k > 0);
+      umma_commit(bar_mma);
+      if (profiling) { const long long c2 = clock64(); t_gather += c1 - c0; t_issue += c2 - c1; }
+    };
+    auto cond_chain = [&](uint32_t d_col) {                                     // warp 5: pre_{n} = Q cond_n (K = 208)
+      tc_fence_after();
+#pragma unroll
+      for (int k = 0; k < CDIM / 16; ++k) umma_f16(tmem + d_col, dC + (uint64_t)(k * 16), dQ + (uint64_t)(k * 16), idesc_q, k > 0);
+      umma_commit(bar_q);
     };
 
-    named_bar_sync(2, 128);                               // stagers have written cond_0
-    chain(dC, dQ, CDIM / 16, TC_Q0, idesc_q, bar_q);
-    for (int t = 0; t < S; ++t) {
-      const int par = t & 1;
-      const unsigned target = (unsigned)P * (unsigned)(t + 1);
-      const unsigned char* base = p.xch + (size_t)par * img_bytes;
-      fetch_and_chain(0, target, base + 0 * xch_stride, dS1, TC_S1, idesc_s1);
-      fetch_and_chain(1, target, base + 1 * xch_stride, dS2, TC_S2, idesc_s2);
-      if (t + 1 < S) {                                    // conditioning chain for step t+1, behind S2 in the tensor pipe
-        named_bar_sync(2, 128);
-        chain(dC, dQ, CDIM / 16, par ? TC_Q0 : TC_Q1, idesc_q, bar_q);
-      }
-      fetch_and_chain(2, target, base + 2 * xch_stride, dS3, TC_S3, idesc_s3);
-      fetch_and_chain(3, target, base + 3 * xch_stride, dF3, TC_F3, idesc_f3);
-      if (ld_relaxed_s32(p.abort_flag) != 0) {            // keep the stagers' barrier protocol consistent, then leave
-        for (int r = t + 2; r < S; ++r) named_bar_sync(2, 128);
-        break;
-      }
-    }
-    if (profiling) { p.prof[5] = t_poll; p.prof[6] = t_gather; p.prof[7] = t_issue; }
-
-  } else {
-    // =========================================================================================
-    // cond stagers (warps 5-7): cond_n rows -> fp16/bf16 A image, one step ahead
-    // =========================================================================================
-    const int st = tid - 160;
-    constexpr int COND_TASKS = 6;                          // (fold, 8-column chunk) tasks held in registers per thread
+    // ---- conditioning staging (all 128 issuer threads): cond_n rows -> fp16/bf16 A image, one step ahead
+    const int st = tid - 128;
+    constexpr int COND_TASKS = 5;                          // (fold, 8-column chunk) tasks held in registers per thread
     const int n_tasks = B * KQ;
-    const bool deferred = n_tasks <= COND_TASKS * N_STAGERS;   // n_seg <= 22: loads fly a whole step before use
+    const bool deferred = n_tasks <= COND_TASKS * 128;     // n_seg <= 24: loads fly a whole step before use
     float4 creg[COND_TASKS][2];
-    auto src_of = [&](int f, int c8, long long row) -> const float4* {
+    auto src_of = [&](int c8, long long row) -> const float4* {
       const float* s = (c8 < FEAT / 8) ? p.mels_up + row * FEAT + c8 * 8 : p.aux + row * (4 * AUXD) + (c8 - FEAT / 8) * 8;
       return reinterpret_cast<const float4*>(s);
     };
@@ -476,40 +481,65 @@ __global__ void __launch_bounds__(NT, 1) wrnn_tc_kernel(const TcParams p) {
       v.x = pack2<FMT>(a.x, a.y); v.y = pack2<FMT>(a.z, a.w); v.z = pack2<FMT>(b.x, b.y); v.w = pack2<FMT>(b.z, b.w);
       *reinterpret_cast<uint4*>(smem + OFF_COND + (f >> 3) * SBO_Q + c8 * 128 + (f & 7) * 16) = v;
     };
-    auto fetch = [&](int n) {
+    auto cond_fetch = [&](int n) {
+      if (!deferred) return;
 #pragma unroll
       for (int j = 0; j < COND_TASKS; ++j) {
-        const int task = st + j * N_STAGERS;
+        const int task = st + j * 128;
         creg[j][0] = make_float4(0.f, 0.f, 0.f, 0.f); creg[j][1] = creg[j][0];
         if (task < n_tasks) {
           const int f = task / KQ, c8 = task % KQ;
           const long long row = (long long)f * p.seg_stride + n;
-          if (row < p.L) { const float4* s = src_of(f, c8, row); creg[j][0] = __ldg(s); creg[j][1] = __ldg(s + 1); }
+          if (row < p.L) { const float4* s = src_of(c8, row); creg[j][0] = __ldg(s); creg[j][1] = __ldg(s + 1); }
         }
       }
     };
-    if (deferred) fetch(0);
-    for (int n = 0; n < S; ++n) {
-      if (n > 0) mbar_wait(bar_q, (uint32_t)((n - 1) & 1), p.abort_flag);   // chain n-1 has consumed the image
+    auto cond_store = [&](int n) {
       if (deferred) {
 #pragma unroll
         for (int j = 0; j < COND_TASKS; ++j) {
-          const int task = st + j * N_STAGERS;
+          const int task = st + j * 128;
           if (task < n_tasks) store_task(task / KQ, task % KQ, creg[j][0], creg[j][1]);
         }
       } else {
-        for (int task = st; task < n_tasks; task += N_STAGERS) {
+        for (int task = st; task < n_tasks; task += 128) {
           const int f = task / KQ, c8 = task % KQ;
           const long long row = (long long)f * p.seg_stride + n;
           float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
-          if (row < p.L) { const float4* s = src_of(f, c8, row); a = __ldg(s); b = __ldg(s + 1); }
+          if (row < p.L) { const float4* s = src_of(c8, row); a = __ldg(s); b = __ldg(s + 1); }
           store_task(f, c8, a, b);
         }
       }
       proxy_fence_smem();
-      named_bar_sync(2, 128);                              // hand the image to the driver warp
-      if (deferred && n + 1 < S) fetch(n + 1);
+    };
+
+    cond_fetch(0);
+    cond_store(0);
+    named_bar_sync(2, 128);
+    if (q == 1) cond_chain(TC_Q0);
+    if (S > 1) cond_fetch(1);
+
+    for (int t = 0; t < S; ++t) {
+      const int par = t & 1;
+      const unsigned target = (unsigned)P * (unsigned)(t + 1);
+      const unsigned char* base = p.xch + (size_t)par * img_bytes;
+      if (leader) launch(0, target, base + 0 * xch_stride);
+      quarter(dS1, TC_S1 + q * N_S1, idesc_s1);
+      if (leader) launch(1, target, base + 1 * xch_stride);
+      quarter(dS2, TC_S2 + q * N_S2, idesc_s2);
+      if (t + 1 < S) {                                    // conditioning of step t+1, behind S2 in the tensor pipe
+        mbar_wait(bar_q, (uint32_t)(t & 1), p.abort_flag);           // chain t has consumed the cond image
+        cond_store(t + 1);
+        named_bar_sync(2, 128);
+        if (q == 1) cond_chain(par ? TC_Q0 : TC_Q1);
+        if (t + 2 < S) cond_fetch(t + 2);
+      }
+      if (leader) launch(2, target, base + 2 * xch_stride);
+      quarter(dS3, TC_S3 + q * N_S3, idesc_s3);
+      if (leader) launch(3, target, base + 3 * xch_stride);
+      quarter(dF3, TC_F3 + q * N_F3, idesc_f3);
     }
+    if (profiling) { p.prof[5] = t_poll; p.prof[6] = t_gather; p.prof[7] = t_issue; }
   }
 
   tc_fence_before();
