@@ -196,6 +196,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")       # keep NCCL's version banner off stdout (one JSON line only)
         dist.init_process_group("nccl", device_id=device)
 
     model = build_model(device)
