@@ -202,13 +202,22 @@ def test_tcgen05_fold_counts_and_zero_padded_tail(n_seg):
     assert np.abs(out - emu).max() <= 1e-3
 
 
-def test_auto_engine_picks_tcgen05_for_small_jobs_and_falls_back_for_large(mol):
+def test_auto_engine_tiles_large_jobs_on_tcgen05_and_serves_raw_on_simt(mol):
     out, name = run_engine(mol["model"], mol["m_up"], mol["aux"], uniforms=mol["U"], steps=50, **mol["kw"])
     assert name.startswith("tcgen05")
+    # 150 folds = 3 tiles of <= 64 folds (64 + 64 + 22), the last one ragged, stream shorter than the last folds
     rs = np.random.RandomState(0)
-    n_seg, seg_len, stride = 70, 40, 30
-    L = 69 * stride + 40
+    n_seg, seg_len, stride = 150, 48, 30
+    L = 149 * stride + 20
     m_up, aux = rs.rand(L, 80).astype(np.float32), rs.randn(L, 128).astype(np.float32)
     U = helpers.replay_uniforms(5, seg_len, n_seg)
-    out, name = run_engine(mol["model"], m_up, aux, n_seg=n_seg, seg_len=seg_len, seg_stride=stride, uniforms=U)
+    kw = dict(n_seg=n_seg, seg_len=seg_len, seg_stride=stride, uniforms=U)
+    out, lg, name = run_engine(mol["model"], m_up, aux, want_logits=True, **kw)
+    assert name.startswith("tcgen05")
+    emu, lemu = C.generate_segments(mol["w"], m_up, aux, precision="fp16", want_logits=True, **kw)
+    print(f"{name} 150 folds in 3 tiles: vs emulation {np.abs(out - emu).max():.3e} logits {np.abs(lg - lemu).max():.3e}")
+    assert np.abs(out - emu).max() <= 1e-3 and np.abs(lg - lemu).max() <= 1e-3
+    raw_model = helpers.make_model(0, "RAW", "cuda")
+    expo = np.ones((4, 2, 512), np.float32)
+    _, name = run_engine(raw_model, m_up[:200], aux[:200], n_seg=2, seg_len=4, seg_stride=4, expo=expo)
     assert name.startswith("simt")

@@ -29,8 +29,8 @@
 //   warps 5-7  cond stagers : stream cond_{t+1} HBM -> registers -> fp16 operand image, one
 //                             step ahead of the recurrence
 //
-// This version serves n_seg <= 64 (one M tile) and the MoL head; other jobs are served by the
-// SIMT engine (ENGINE_AUTO falls through per job).
+// One launch serves a tile of <= 64 folds (one M tile); larger jobs run tile after tile.  MoL head only:
+// the RAW 9-bit head and the fp32 strict mode are served by the SIMT engine (ENGINE_AUTO falls through).
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
@@ -82,7 +82,8 @@ static_assert(TC_Q1 + N_Q <= TMEM_COLS, "TMEM budget");
 struct TcParams {
   const unsigned char* blob;
   const float* mels_up; const float* aux; long long L; long long seg_stride;
-  int n_seg, steps, out_pitch, seg_first;
+  int n_seg, steps, out_pitch, seg_first;   // n_seg = folds of THIS launch's tile (<= 64)
+  int f0, n_total;                         // first fold of the tile / folds of the whole job (indexing of the job-wide arrays)
   const float* uniforms; unsigned long long seed, offset;
   float* out; const float* x_force; float* logits_out;
   unsigned char* xch;        // [4 vectors][3 ring slots][n_groups * SBO_H] activation images, sentinel-filled
@@ -230,7 +231,7 @@ __global__ void __launch_bounds__(NT, 1) wrnn_tc_kernel(const TcParams p) {
   const float* b3 = fv + 88;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 32);
-  const uint32_t bar_mma = smem_u32(&bars[0]), bar_q = smem_u32(&bars[1]), bar_pub = smem_u32(&bars[2]), bar_w = smem_u32(&bars[3]);
+  const uint32_t bar_mma = smem_u32(&bars[0]), bar_q = smem_u32(&bars[1]), bar_pub = smem_u32(&bars[2]), bar_g = smem_u32(&bars[3]);
 
   const int cta = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int B = p.n_seg, S = p.steps, u0 = cta * U;
@@ -250,7 +251,7 @@ __global__ void __launch_bounds__(NT, 1) wrnn_tc_kernel(const TcParams p) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar_mma), "n"(KW));   // one commit per issuing warp
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar_q));
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 128;" :: "r"(bar_pub));            // every fold-warp thread arrives once per vector
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar_w));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar_g));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -306,12 +307,12 @@ __global__ void __launch_bounds__(NT, 1) wrnn_tc_kernel(const TcParams p) {
       for (int i = 0; i < 11; ++i) ur[i] = 0.5f;
       if (owns_fold) {
         if (p.uniforms) {
-          const float* u = p.uniforms + (size_t)t * 11 * B;
+          const float* u = p.uniforms + (size_t)t * 11 * p.n_total;
 #pragma unroll
-          for (int i = 0; i < 10; ++i) ur[i] = __ldg(u + fold * 10 + i);
-          ur[10] = __ldg(u + 10 * B + fold);
+          for (int i = 0; i < 10; ++i) ur[i] = __ldg(u + (p.f0 + fold) * 10 + i);
+          ur[10] = __ldg(u + 10 * p.n_total + p.f0 + fold);
         } else {
-          const unsigned g = (unsigned)(p.seg_first + fold), k0 = (unsigned)p.seed, k1 = (unsigned)(p.seed >> 32), o0 = (unsigned)p.offset;
+          const unsigned g = (unsigned)(p.seg_first + p.f0 + fold), k0 = (unsigned)p.seed, k1 = (unsigned)(p.seed >> 32), o0 = (unsigned)p.offset;
           const Philox4 r0 = philox4x32_10((unsigned)t, g, 0u, o0, k0, k1), r1 = philox4x32_10((unsigned)t, g, 1u, o0, k0, k1),
                         r2 = philox4x32_10((unsigned)t, g, 2u, o0, k0, k1);
           ur[0] = u_ref_range(r0.x); ur[1] = u_ref_range(r0.y); ur[2] = u_ref_range(r0.z); ur[3] = u_ref_range(r0.w);
@@ -320,7 +321,7 @@ __global__ void __launch_bounds__(NT, 1) wrnn_tc_kernel(const TcParams p) {
         }
       }
       float xf = 0.f;
-      if (owns_fold && p.x_force && t > 0) xf = __ldg(p.x_force + (size_t)(t - 1) * B + fold);
+      if (owns_fold && p.x_force && t > 0) xf = __ldg(p.x_force + (size_t)(t - 1) * p.n_total + p.f0 + fold);
 
       // ---- A: GRU1.  gi1 = pre_t (conditioning chain, D_Q) + x * v1 ; gh1 = W1h h1 + b1h (D_S1 of step t-1)
       float pre[32];                                      // this fold's 32 conditioning rows (+ qk + x*vq)
@@ -403,10 +404,10 @@ __global__ void __launch_bounds__(NT, 1) wrnn_tc_kernel(const TcParams p) {
         for (int i = 0; i < 30; ++i) lg[i] += b3[i];
         x = mol_sample_fast(lg, ur);
         if (owns_fold && cta == 0) {
-          p.out[(size_t)fold * p.out_pitch + t] = x;
+          p.out[(size_t)(p.f0 + fold) * p.out_pitch + t] = x;
           if (p.logits_out) {
 #pragma unroll
-            for (int i = 0; i < 30; ++i) p.logits_out[((size_t)t * B + fold) * 30 + i] = lg[i];
+            for (int i = 0; i < 30; ++i) p.logits_out[((size_t)t * p.n_total + p.f0 + fold) * 30 + i] = lg[i];
           }
         }
       }
@@ -436,55 +437,60 @@ __global__ void __launch_bounds__(NT, 1) wrnn_tc_kernel(const TcParams p) {
                    idesc_q = umma_idesc(MT, N_Q, FMT);
     const bool profiling = (p.prof != nullptr) && cta == 0 && tid == 128;
     long long t_pub = 0, t_gather = 0, t_issue = 0, n_retry = 0;
-    unsigned n_pub = 0;
+    unsigned n_pub = 0, n_g = 0;
 
-    // Pull this warp's K quarter of one exchanged vector (image `img`) into the A image.
-    // Lane l, slot j handles 16-byte chunk (group g = gb + j/4, local chunk c = (j%4)*32 + l): row g*8 + c%8, k8 = 16q + c/8.
+    // Bring one exchanged vector (L2 image `img`) into the A image and make this warp's K quarter usable.
+    //  1. wait until this CTA's own fold warps have published (=> they are done with the accumulators the next
+    //     chain overwrites, and -- all CTAs running in lock-step -- the peers' stores are in flight as well);
+    //  2. warp 4 pulls the WHOLE image with one TMA bulk copy, speculatively, after a short delay;
+    //  3. every issuer warp checks ITS quarter in shared memory against the sentinel; chunks that were still
+    //     in flight (rare) are re-read from L2 with polite 16-byte polling and patched in.
+    // Lane l, slot j handles chunk (group g = gb + j/4, c = (j%4)*32 + l): row g*8 + c%8, k8 = 16q + c/8.
     auto gather_quarter = [&](const unsigned char* img) {
       long long c0 = 0, c1 = 0;
       if (profiling) c0 = clock64();
-      // own fold warps have finished reading the accumulators this chain overwrites and have issued their own
-      // stores for this vector; every CTA runs in lock-step, so the peers' stores are in flight too
       mbar_wait(bar_pub, n_pub & 1, p.abort_flag); ++n_pub;
       if (profiling) c1 = clock64();
-      { const long long d0 = clock64(); while (clock64() - d0 < p.spec_delay) {} }   // ~ the store's way to L2
+      if (q == 0) {
+        { const long long d0 = clock64(); while (clock64() - d0 < p.spec_delay) {} }   // ~ the stores' way to L2
+        tma_bulk_g2s(sA, img, img_bytes, bar_g);
+      }
+      mbar_wait(bar_g, n_g & 1, p.abort_flag); ++n_g;
+      bool patched = false;
       for (int gb = 0; gb < n_groups; gb += 3) {
-        uint4 v[12];
         unsigned pending = 0;
 #pragma unroll
         for (int j = 0; j < 12; ++j) {
           const int g = gb + (j >> 2), c = (j & 3) * 32 + lane;
-          if (g < n_groups && g * 8 + (c & 7) < B) pending |= 1u << j;
+          if (g < n_groups && g * 8 + (c & 7) < B) {
+            const uint4 v = *reinterpret_cast<const uint4*>(smem + OFF_A + g * SBO_H + q * 2048 + c * 16);
+            if (v.x == 0xffffffffu || v.z == 0xffffffffu) pending |= 1u << j;
+          }
         }
-        const unsigned wanted = pending;
+        if (!__any_sync(0xffffffffu, pending != 0)) continue;
+        patched = true;
         const long long w0 = clock64();
-        for (;;) {
+        for (;;) {                                            // slow path: some producer's store had not landed yet
+          if (profiling) ++n_retry;
 #pragma unroll
           for (int j = 0; j < 12; ++j) {
             if (pending & (1u << j)) {
               const int g = gb + (j >> 2), c = (j & 3) * 32 + lane;
               const unsigned char* src = img + (size_t)g * SBO_H + q * 2048 + c * 16;
-              asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v[j].x), "=r"(v[j].y), "=r"(v[j].z), "=r"(v[j].w) : "l"(src) : "memory");
+              uint4 v;
+              asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(src) : "memory");
+              if (v.x != 0xffffffffu && v.z != 0xffffffffu) {
+                *reinterpret_cast<uint4*>(smem + OFF_A + g * SBO_H + q * 2048 + c * 16) = v;
+                pending &= ~(1u << j);
+              }
             }
           }
-#pragma unroll
-          for (int j = 0; j < 12; ++j) {
-            if ((pending & (1u << j)) && v[j].x != 0xffffffffu && v[j].z != 0xffffffffu) pending &= ~(1u << j);
-          }
           if (!__any_sync(0xffffffffu, pending != 0)) break;
-          if (profiling) ++n_retry;
           if (clock64() - w0 > kWatchdogCycles || ld_relaxed_s32(p.abort_flag) != 0) { atomicExch(p.abort_flag, 1); break; }
           __nanosleep(32);                                  // polite re-poll: leave the L2 slices room for the stores
         }
-#pragma unroll
-        for (int j = 0; j < 12; ++j) {
-          if (wanted & (1u << j)) {
-            const int g = gb + (j >> 2), c = (j & 3) * 32 + lane;
-            *reinterpret_cast<uint4*>(smem + OFF_A + g * SBO_H + q * 2048 + c * 16) = v[j];
-          }
-        }
       }
-      proxy_fence_smem();
+      if (patched) proxy_fence_smem();
       __syncwarp();
       if (profiling) { const long long c2 = clock64(); t_pub += c1 - c0; t_gather += c2 - c1; }
     };
@@ -529,7 +535,7 @@ __global__ void __launch_bounds__(NT, 1) wrnn_tc_kernel(const TcParams p) {
         creg[j][0] = make_float4(0.f, 0.f, 0.f, 0.f); creg[j][1] = creg[j][0];
         if (task < n_tasks) {
           const int f = task / KQ, c8 = task % KQ;
-          const long long row = (long long)f * p.seg_stride + n;
+          const long long row = (long long)(p.f0 + f) * p.seg_stride + n;
           if (row < p.L) { const float4* s = src_of(c8, row); creg[j][0] = __ldg(s); creg[j][1] = __ldg(s + 1); }
         }
       }
@@ -544,7 +550,7 @@ __global__ void __launch_bounds__(NT, 1) wrnn_tc_kernel(const TcParams p) {
       } else {
         for (int task = st; task < n_tasks; task += 128) {
           const int f = task / KQ, c8 = task % KQ;
-          const long long row = (long long)f * p.seg_stride + n;
+          const long long row = (long long)(p.f0 + f) * p.seg_stride + n;
           float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
           if (row < p.L) { const float4* s = src_of(c8, row); a = __ldg(s); b = __ldg(s + 1); }
           store_task(f, c8, a, b);
@@ -566,17 +572,19 @@ __global__ void __launch_bounds__(NT, 1) wrnn_tc_kernel(const TcParams p) {
       quarter(dS1, TC_S1 + q * N_S1, idesc_s1);
       gather_quarter(base + 1 * xch_stride);
       quarter(dS2, TC_S2 + q * N_S2, idesc_s2);
-      if (t + 1 < S) {                                    // conditioning of step t+1, behind S2 in the tensor pipe
+      gather_quarter(base + 2 * xch_stride);
+      quarter(dS3, TC_S3 + q * N_S3, idesc_s3);
+      gather_quarter(base + 3 * xch_stride);
+      quarter(dF3, TC_F3 + q * N_F3, idesc_f3);
+      if (t + 1 < S) {
+        // Conditioning of step t+1, in the slack while the fold warps sample and run GRU1: the chain queues
+        // behind F3 in the tensor pipe and lands before phase A of step t+1 asks for it.
         mbar_wait(bar_q, (uint32_t)(t & 1), p.abort_flag);           // chain t has consumed the cond image
         cond_store(t + 1);
         named_bar_sync(2, 128);
         if (q == 1) cond_chain(par ? TC_Q0 : TC_Q1);
         if (t + 2 < S) cond_fetch(t + 2);
       }
-      gather_quarter(base + 2 * xch_stride);
-      quarter(dS3, TC_S3 + q * N_S3, idesc_s3);
-      gather_quarter(base + 3 * xch_stride);
-      quarter(dF3, TC_F3 + q * N_F3, idesc_f3);
     }
     if (profiling) { p.prof[5] = t_pub; p.prof[6] = t_gather; p.prof[7] = t_issue; p.prof[8] = n_retry; }
   }
@@ -643,16 +651,11 @@ class TcEngine : public Engine {
   }
 
   static bool supports_cfg(const wrnn_cfg& c) { return c.mode == WRNN_MODE_MOL && c.n_classes == 30 && c.precision != WRNN_PREC_FP32; }
-  bool supports(const wrnn_job& job) const override { return job.n_seg <= MT; }
+  bool supports(const wrnn_job&) const override { return true; }   // any fold count: tiles of 64 folds, one launch each
 
   int generate(const wrnn_job& job, cudaStream_t stream) override {
-    if (job.n_seg > MT) {
-      set_error("tcgen05 engine (this build): n_seg must be <= 64");
-      return WRNN_E_INVALID;
-    }
     WRNN_CUDA_OK(cudaSetDevice(device));
     WRNN_CUDA_OK(cudaMemsetAsync(d_sync_, 0, 256, stream));
-    WRNN_CUDA_OK(cudaMemsetAsync(d_scratch_, 0xff, scratch_bytes_, stream));      // sentinel everywhere
     TcParams p{};
     p.blob = static_cast<const unsigned char*>(d_blob_);
     p.mels_up = job.mels_up; p.aux = job.aux; p.L = job.L; p.seg_stride = job.seg_stride;
@@ -661,12 +664,20 @@ class TcEngine : public Engine {
     p.uniforms = job.uniforms; p.seed = job.philox_seed; p.offset = job.philox_offset;
     p.out = job.out; p.x_force = job.x_force; p.logits_out = job.logits_out;
     p.xch = static_cast<unsigned char*>(d_scratch_);
-    { const char* e = getenv("WRNN_TC_DELAY"); p.spec_delay = e ? atoi(e) : 300; }
+    { const char* e = getenv("WRNN_TC_DELAY"); p.spec_delay = e ? atoi(e) : 100; }
     p.abort_flag = reinterpret_cast<int*>(static_cast<unsigned*>(d_sync_) + 8);
     p.prof = reinterpret_cast<long long*>(static_cast<unsigned char*>(d_sync_) + 64);
-    void* args[] = {&p};
-    WRNN_CUDA_OK(cudaLaunchCooperativeKernel(kernel(), dim3(P), dim3(NT), args, SMEM_BYTES, stream));
-    ++launches;
+    p.n_total = job.n_seg;
+    // In this latency-bound regime a step costs the same for 1 or 64 folds, so larger jobs run as consecutive
+    // tiles of 64 folds (one persistent launch each) at the full per-tile rate.
+    for (int f0 = 0; f0 < job.n_seg; f0 += MT) {
+      p.f0 = f0;
+      p.n_seg = job.n_seg - f0 < MT ? job.n_seg - f0 : MT;
+      WRNN_CUDA_OK(cudaMemsetAsync(d_scratch_, 0xff, scratch_bytes_, stream));    // sentinel everywhere
+      void* args[] = {&p};
+      WRNN_CUDA_OK(cudaLaunchCooperativeKernel(kernel(), dim3(P), dim3(NT), args, SMEM_BYTES, stream));
+      ++launches;
+    }
     last_steps_ = p.steps;
     return WRNN_OK;
   }
