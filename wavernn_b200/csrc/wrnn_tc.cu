@@ -86,10 +86,10 @@ struct TcParams {
   int f0, n_total;                         // first fold of the tile / folds of the whole job (indexing of the job-wide arrays)
   const float* uniforms; unsigned long long seed, offset;
   float* out; const float* x_force; float* logits_out;
-  unsigned char* xch;        // [4 vectors][3 ring slots][n_groups * SBO_H] activation images, sentinel-filled
-  int spec_delay;            // cycles an issuer warp waits after its own CTA published before its first gather
+  unsigned char* xch;        // [4 vectors][2 parities][n_groups * SBO_H] activation images
+  unsigned* counters;        // [4] monotonically increasing arrival counters
   int* abort_flag;
-  long long* prof;           // cycle counters of CTA 0 (fold thread 0: [0..4], issuer warp 4 lane 0: [5..8])
+  long long* prof;           // cycle counters of CTA 0 (fold thread 0: [0..4], driver lane 0: [5..7])
 };
 
 // ------------------------------------------------------------------------------------------
@@ -231,13 +231,13 @@ __global__ void __launch_bounds__(NT, 1) wrnn_tc_kernel(const TcParams p) {
   const float* b3 = fv + 88;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 32);
-  const uint32_t bar_mma = smem_u32(&bars[0]), bar_q = smem_u32(&bars[1]), bar_pub = smem_u32(&bars[2]), bar_g = smem_u32(&bars[3]);
+  const uint32_t bar_mma = smem_u32(&bars[0]), bar_q = smem_u32(&bars[1]), bar_g = smem_u32(&bars[2]);
 
   const int cta = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int B = p.n_seg, S = p.steps, u0 = cta * U;
   const int n_groups = (B + 7) / 8;                    // real 8-row groups of the A images
   const uint32_t img_bytes = (uint32_t)n_groups * SBO_H;
-  const size_t xch_stride = (size_t)3 * img_bytes;     // per vector: ring of three step slots
+  const size_t xch_stride = (size_t)2 * img_bytes;     // per vector: two parities
 
   // ---- one-time setup: weights -> smem images, barriers, TMEM --------------------------------
   {
@@ -250,7 +250,6 @@ __global__ void __launch_bounds__(NT, 1) wrnn_tc_kernel(const TcParams p) {
   if (tid == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar_mma), "n"(KW));   // one commit per issuing warp
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar_q));
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 128;" :: "r"(bar_pub));            // every fold-warp thread arrives once per vector
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar_g));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -274,21 +273,15 @@ __global__ void __launch_bounds__(NT, 1) wrnn_tc_kernel(const TcParams p) {
     const size_t pub_off = (size_t)(fold >> 3) * SBO_H + (u0 >> 3) * 128 + (fold & 7) * 16 + (u0 & 7) * 2;
     const bool profiling = (p.prof != nullptr) && cta == 0 && tid == 0;
     long long tprof[5] = {0, 0, 0, 0, 0};
-    // Publish this fold's 4 values of this CTA's units into ring slot `cur` of vector v, and put the sentinel
-    // back into slot `prev` (step t-1): every CTA has consumed v(t-1) by the time anyone can publish v(t).
-    // No fence, no counter: a consumer recognises valid data by the absence of the sentinel (0xFFFF pairs are
-    // fp16/bf16 NaNs that the saturating conversions never produce).
-    auto publish = [&](int v, int cur, int prev, const float* val) {
+    auto publish = [&](unsigned char* img, const float* v) {   // this fold's 4 values of this CTA's units
       uint2 w;
-      w.x = pack2<FMT>(val[0], val[1]); w.y = pack2<FMT>(val[2], val[3]);
-      unsigned char* base = p.xch + (size_t)v * xch_stride + pub_off;
-      if (owns_fold) {
-        asm volatile("st.global.cg.v2.u32 [%0], {%1, %2};" :: "l"(base + (size_t)cur * img_bytes), "r"(w.x), "r"(w.y) : "memory");
-        asm volatile("st.global.cg.v2.u32 [%0], {%1, %2};" :: "l"(base + (size_t)prev * img_bytes), "r"(0xffffffffu), "r"(0xffffffffu) : "memory");
-      }
-      // tell the issuer warps: accumulators read, own stores issued
+      w.x = pack2<FMT>(v[0], v[1]); w.y = pack2<FMT>(v[2], v[3]);
+      if (owns_fold) *reinterpret_cast<uint2*>(img + pub_off) = w;
+    };
+    auto signal = [&](int v) {                           // all fold warps have stored: one release increment per CTA
       tc_fence_before();
-      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar_pub) : "memory");
+      named_bar_sync(1, 128);
+      if (tid == 0) red_release_add_u32(p.counters + v, 1u);
     };
     float h1[U] = {0.f, 0.f, 0.f, 0.f}, h2[U] = {0.f, 0.f, 0.f, 0.f};
     float x = 0.f;
@@ -297,7 +290,10 @@ __global__ void __launch_bounds__(NT, 1) wrnn_tc_kernel(const TcParams p) {
     for (int t = 0; t < S; ++t) {
       const int par = t & 1;
       const uint32_t tq = (par ? TC_Q1 : TC_Q0);
-      const int cur = t % 3, prev = (t + 2) % 3;          // ring slots of step t and step t-1
+      unsigned char* img_h1 = p.xch + 0 * xch_stride + (size_t)par * img_bytes;
+      unsigned char* img_h2 = p.xch + 1 * xch_stride + (size_t)par * img_bytes;
+      unsigned char* img_y1 = p.xch + 2 * xch_stride + (size_t)par * img_bytes;
+      unsigned char* img_y2 = p.xch + 3 * xch_stride + (size_t)par * img_bytes;
       long long tp0 = 0;
       if (profiling) tp0 = clock64();
 
@@ -343,7 +339,8 @@ __global__ void __launch_bounds__(NT, 1) wrnn_tc_kernel(const TcParams p) {
           h1[j] = gru_unit_fast(pre[j], pre[U + j], pre[2 * U + j], ghr, ghz, ghn, h1[j]);
           hv[j] = h1[j];
         }
-        publish(0, cur, prev, hv);
+        publish(img_h1, hv);
+        signal(0);
       }
       if (profiling) { const long long c = clock64(); tprof[0] += c - tp0; tp0 = c; }
 
@@ -362,7 +359,8 @@ __global__ void __launch_bounds__(NT, 1) wrnn_tc_kernel(const TcParams p) {
           h2[j] = gru_unit_fast(gi[j] + pre[3 * U + j], gi[U + j] + pre[4 * U + j], gi[2 * U + j] + pre[5 * U + j], ghr, ghz, ghn, h2[j]);
           hv[j] = h2[j];
         }
-        publish(1, cur, prev, hv);
+        publish(img_h2, hv);
+        signal(1);
       }
       if (profiling) { const long long c = clock64(); tprof[1] += c - tp0; tp0 = c; }
 
@@ -376,7 +374,8 @@ __global__ void __launch_bounds__(NT, 1) wrnn_tc_kernel(const TcParams p) {
         float yv[U];
 #pragma unroll
         for (int j = 0; j < U; ++j) yv[j] = fmaxf(a[j] + b4[j] + pre[6 * U + j], 0.f);
-        publish(2, cur, prev, yv);
+        publish(img_y1, yv);
+        signal(2);
       }
       if (profiling) { const long long c = clock64(); tprof[2] += c - tp0; tp0 = c; }
 
@@ -389,7 +388,8 @@ __global__ void __launch_bounds__(NT, 1) wrnn_tc_kernel(const TcParams p) {
         float yv[U];
 #pragma unroll
         for (int j = 0; j < U; ++j) yv[j] = fmaxf(a[j] + pre[7 * U + j], 0.f);
-        publish(3, cur, prev, yv);
+        publish(img_y2, yv);
+        signal(3);
       }
       if (profiling) { const long long c = clock64(); tprof[3] += c - tp0; tp0 = c; }
 
@@ -419,13 +419,12 @@ __global__ void __launch_bounds__(NT, 1) wrnn_tc_kernel(const TcParams p) {
 
   } else {
     // =========================================================================================
-    // issuer warps 4-7.  Warp q = warp-4 owns the K quarter [128q, 128q+128) of every K=512 chain: it pulls
-    // that quarter of the exchanged vector out of L2 itself (16-byte loads, batched so that the whole
-    // quarter is ONE L2 round trip), validates it against the sentinel, writes it into the A image and
-    // issues its 8 tcgen05.mma into its own TMEM columns.  Warp 5 also issues the conditioning chain;
-    // all four stage cond_{t+1}.
+    // issuer warps 4-7.  Warp q = warp-4 owns the K quarter [128q, 128q+128) of every K=512 chain and
+    // accumulates into its own TMEM columns.  Warp 4 ("leader") also watches the arrival counters and
+    // launches the TMA gather; warp 5 issues the conditioning chain; all four stage cond_{t+1}.
     // =========================================================================================
     const int q = warp - 4;
+    const bool leader = (q == 0);
     const uint32_t sA = smem_u32(smem + OFF_A);
     const uint64_t koff = (uint64_t)(q * (H / 16 / KW) * 16);             // descriptor address-field offset of this K quarter
     const uint64_t dA = umma_desc(sA, 128, SBO_H) + koff, dC = umma_desc(smem_u32(smem + OFF_COND), 128, SBO_Q);
@@ -436,74 +435,30 @@ __global__ void __launch_bounds__(NT, 1) wrnn_tc_kernel(const TcParams p) {
                    idesc_s3 = umma_idesc(MT, N_S3, FMT), idesc_f3 = umma_idesc(MT, N_F3, FMT),
                    idesc_q = umma_idesc(MT, N_Q, FMT);
     const bool profiling = (p.prof != nullptr) && cta == 0 && tid == 128;
-    long long t_pub = 0, t_gather = 0, t_issue = 0, n_retry = 0;
-    unsigned n_pub = 0, n_g = 0;
+    long long t_poll = 0, t_gather = 0, t_issue = 0;
+    unsigned n_g = 0;
 
-    // Bring one exchanged vector (L2 image `img`) into the A image and make this warp's K quarter usable.
-    //  1. wait until this CTA's own fold warps have published (=> they are done with the accumulators the next
-    //     chain overwrites, and -- all CTAs running in lock-step -- the peers' stores are in flight as well);
-    //  2. warp 4 pulls the WHOLE image with one TMA bulk copy, speculatively, after a short delay;
-    //  3. every issuer warp checks ITS quarter in shared memory against the sentinel; chunks that were still
-    //     in flight (rare) are re-read from L2 with polite 16-byte polling and patched in.
-    // Lane l, slot j handles chunk (group g = gb + j/4, c = (j%4)*32 + l): row g*8 + c%8, k8 = 16q + c/8.
-    auto gather_quarter = [&](const unsigned char* img) {
-      long long c0 = 0, c1 = 0;
-      if (profiling) c0 = clock64();
-      mbar_wait(bar_pub, n_pub & 1, p.abort_flag); ++n_pub;
-      if (profiling) c1 = clock64();
-      if (q == 0) {
-        { const long long d0 = clock64(); while (clock64() - d0 < p.spec_delay) {} }   // ~ the stores' way to L2
-        tma_bulk_g2s(sA, img, img_bytes, bar_g);
-      }
-      mbar_wait(bar_g, n_g & 1, p.abort_flag); ++n_g;
-      bool patched = false;
-      for (int gb = 0; gb < n_groups; gb += 3) {
-        unsigned pending = 0;
-#pragma unroll
-        for (int j = 0; j < 12; ++j) {
-          const int g = gb + (j >> 2), c = (j & 3) * 32 + lane;
-          if (g < n_groups && g * 8 + (c & 7) < B) {
-            const uint4 v = *reinterpret_cast<const uint4*>(smem + OFF_A + g * SBO_H + q * 2048 + c * 16);
-            if (v.x == 0xffffffffu || v.z == 0xffffffffu) pending |= 1u << j;
-          }
-        }
-        if (!__any_sync(0xffffffffu, pending != 0)) continue;
-        patched = true;
-        const long long w0 = clock64();
-        for (;;) {                                            // slow path: some producer's store had not landed yet
-          if (profiling) ++n_retry;
-#pragma unroll
-          for (int j = 0; j < 12; ++j) {
-            if (pending & (1u << j)) {
-              const int g = gb + (j >> 2), c = (j & 3) * 32 + lane;
-              const unsigned char* src = img + (size_t)g * SBO_H + q * 2048 + c * 16;
-              uint4 v;
-              asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(src) : "memory");
-              if (v.x != 0xffffffffu && v.z != 0xffffffffu) {
-                *reinterpret_cast<uint4*>(smem + OFF_A + g * SBO_H + q * 2048 + c * 16) = v;
-                pending &= ~(1u << j);
-              }
-            }
-          }
-          if (!__any_sync(0xffffffffu, pending != 0)) break;
-          if (clock64() - w0 > kWatchdogCycles || ld_relaxed_s32(p.abort_flag) != 0) { atomicExch(p.abort_flag, 1); break; }
-          __nanosleep(32);                                  // polite re-poll: leave the L2 slices room for the stores
-        }
-      }
-      if (patched) proxy_fence_smem();
-      __syncwarp();
-      if (profiling) { const long long c2 = clock64(); t_pub += c1 - c0; t_gather += c2 - c1; }
-    };
     // D[64 folds, N] (+)= A[64, 16] * B[N, 16]^T per instruction; K advances by two core-matrix columns
     // (256 B => +16 in the descriptor's address field; no carry: every image ends below 256 KB)
-    auto quarter = [&](uint64_t db, uint32_t d_col, uint32_t idesc) {
+    auto launch = [&](int v, unsigned target, const unsigned char* img) {      // leader only
       long long c0 = 0;
       if (profiling) c0 = clock64();
+      if (lane == 0) counter_wait(p.counters + v, target, p.abort_flag);        // acquire: all 128 producers have published
+      __syncwarp();
+      proxy_fence_global();                                                     // generic-proxy writes -> async-proxy (TMA) read
+      if (profiling) t_poll += clock64() - c0;
+      tma_bulk_g2s(sA, img, img_bytes, bar_g);
+    };
+    auto quarter = [&](uint64_t db, uint32_t d_col, uint32_t idesc) {
+      long long c0 = 0, c1 = 0;
+      if (profiling) c0 = clock64();
+      mbar_wait(bar_g, n_g & 1, p.abort_flag); ++n_g;                           // the gathered vector is in smem
       tc_fence_after();
+      if (profiling) c1 = clock64();
 #pragma unroll
       for (int k = 0; k < H / 16 / KW; ++k) umma_f16(tmem + d_col, dA + (uint64_t)(k * 16), db + (uint64_t)(k * 16), idesc, k > 0);
       umma_commit(bar_mma);
-      if (profiling) t_issue += clock64() - c0;
+      if (profiling) { const long long c2 = clock64(); t_gather += c1 - c0; t_issue += c2 - c1; }
     };
     auto cond_chain = [&](uint32_t d_col) {                                     // warp 5: pre_{n} = Q cond_n (K = 208)
       tc_fence_after();
@@ -567,14 +522,15 @@ __global__ void __launch_bounds__(NT, 1) wrnn_tc_kernel(const TcParams p) {
 
     for (int t = 0; t < S; ++t) {
       const int par = t & 1;
-      const unsigned char* base = p.xch + (size_t)(t % 3) * img_bytes;
-      gather_quarter(base + 0 * xch_stride);
+      const unsigned target = (unsigned)P * (unsigned)(t + 1);
+      const unsigned char* base = p.xch + (size_t)par * img_bytes;
+      if (leader) launch(0, target, base + 0 * xch_stride);
       quarter(dS1, TC_S1 + q * N_S1, idesc_s1);
-      gather_quarter(base + 1 * xch_stride);
+      if (leader) launch(1, target, base + 1 * xch_stride);
       quarter(dS2, TC_S2 + q * N_S2, idesc_s2);
-      gather_quarter(base + 2 * xch_stride);
+      if (leader) launch(2, target, base + 2 * xch_stride);
       quarter(dS3, TC_S3 + q * N_S3, idesc_s3);
-      gather_quarter(base + 3 * xch_stride);
+      if (leader) launch(3, target, base + 3 * xch_stride);
       quarter(dF3, TC_F3 + q * N_F3, idesc_f3);
       if (t + 1 < S) {
         // Conditioning of step t+1, in the slack while the fold warps sample and run GRU1: the chain queues
@@ -586,7 +542,7 @@ __global__ void __launch_bounds__(NT, 1) wrnn_tc_kernel(const TcParams p) {
         if (t + 2 < S) cond_fetch(t + 2);
       }
     }
-    if (profiling) { p.prof[5] = t_pub; p.prof[6] = t_gather; p.prof[7] = t_issue; p.prof[8] = n_retry; }
+    if (profiling) { p.prof[5] = t_poll; p.prof[6] = t_gather; p.prof[7] = t_issue; }
   }
 
   tc_fence_before();
@@ -641,7 +597,7 @@ class TcEngine : public Engine {
     WRNN_CUDA_OK(cudaMemcpy(d_blob_, blob.data(), blob.size(), cudaMemcpyHostToDevice));
     WRNN_CUDA_OK(cudaMalloc(&d_sync_, 256));
     WRNN_CUDA_OK(cudaMemset(d_sync_, 0, 256));
-    scratch_bytes_ = (size_t)4 * 3 * 8 * SBO_H;          // 4 vectors x 3 ring slots x (up to 8 row groups)
+    scratch_bytes_ = (size_t)4 * 2 * 8 * SBO_H;          // 4 vectors x 2 parities x (up to 8 row groups)
     WRNN_CUDA_OK(cudaMalloc(&d_scratch_, scratch_bytes_));
     WRNN_CUDA_OK(cudaFuncSetAttribute(kernel(), cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     int n_sm = 0;
@@ -655,7 +611,6 @@ class TcEngine : public Engine {
 
   int generate(const wrnn_job& job, cudaStream_t stream) override {
     WRNN_CUDA_OK(cudaSetDevice(device));
-    WRNN_CUDA_OK(cudaMemsetAsync(d_sync_, 0, 256, stream));
     TcParams p{};
     p.blob = static_cast<const unsigned char*>(d_blob_);
     p.mels_up = job.mels_up; p.aux = job.aux; p.L = job.L; p.seg_stride = job.seg_stride;
@@ -664,16 +619,17 @@ class TcEngine : public Engine {
     p.uniforms = job.uniforms; p.seed = job.philox_seed; p.offset = job.philox_offset;
     p.out = job.out; p.x_force = job.x_force; p.logits_out = job.logits_out;
     p.xch = static_cast<unsigned char*>(d_scratch_);
-    { const char* e = getenv("WRNN_TC_DELAY"); p.spec_delay = e ? atoi(e) : 100; }
+    p.counters = static_cast<unsigned*>(d_sync_);
     p.abort_flag = reinterpret_cast<int*>(static_cast<unsigned*>(d_sync_) + 8);
     p.prof = reinterpret_cast<long long*>(static_cast<unsigned char*>(d_sync_) + 64);
+    WRNN_CUDA_OK(cudaMemsetAsync(d_sync_, 0, 256, stream));
     p.n_total = job.n_seg;
     // In this latency-bound regime a step costs the same for 1 or 64 folds, so larger jobs run as consecutive
     // tiles of 64 folds (one persistent launch each) at the full per-tile rate.
     for (int f0 = 0; f0 < job.n_seg; f0 += MT) {
       p.f0 = f0;
       p.n_seg = job.n_seg - f0 < MT ? job.n_seg - f0 : MT;
-      WRNN_CUDA_OK(cudaMemsetAsync(d_scratch_, 0xff, scratch_bytes_, stream));    // sentinel everywhere
+      WRNN_CUDA_OK(cudaMemsetAsync(d_sync_, 0, 32, stream));                       // arrival counters (the abort flag is sticky)
       void* args[] = {&p};
       WRNN_CUDA_OK(cudaLaunchCooperativeKernel(kernel(), dim3(P), dim3(NT), args, SMEM_BYTES, stream));
       ++launches;
@@ -691,9 +647,8 @@ class TcEngine : public Engine {
     if (getenv("WRNN_TC_PROF") && last_steps_ > 0) {     // average cycles per step seen by CTA 0
       const long long n = last_steps_;
       fprintf(stderr, "[wrnn_tc prof] steps=%d | fold thread: A(gru1)=%lld B(h1'->gru2)=%lld C(h2'->y1)=%lld D(y1->y2)=%lld "
-              "E(y2->sample)=%lld | issuer warp: wait-own-publish=%lld gather=%lld issue=%lld (cycles per step) gather retries per step=%.3f\n",
-              last_steps_, prof[0] / n, prof[1] / n, prof[2] / n, prof[3] / n, prof[4] / n, prof[5] / n, prof[6] / n, prof[7] / n,
-              (double)prof[8] / (double)n);
+              "E(y2->sample)=%lld | driver warp: poll=%lld gather=%lld issue=%lld  (cycles per step)\n",
+              last_steps_, prof[0] / n, prof[1] / n, prof[2] / n, prof[3] / n, prof[4] / n, prof[5] / n, prof[6] / n, prof[7] / n);
     }
     if (flag != 0) {
       set_error(flag == 2 ? "persistent kernel aborted: an mbarrier wait (MMA / TMA completion) timed out"
@@ -702,7 +657,7 @@ class TcEngine : public Engine {
     }
     return WRNN_OK;
   }
-  long long prof[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  long long prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 
  private:
   void *d_blob_ = nullptr, *d_scratch_ = nullptr, *d_sync_ = nullptr;
