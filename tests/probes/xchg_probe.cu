@@ -12,8 +12,9 @@
 #include <cstdlib>
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__); exit(2); } } while (0)
 
-constexpr int P = 128, NT = 256, ROUNDS = 2000, IMG = 24576;   // 3 row groups x 8 KB
+constexpr int NT = 256, ROUNDS = 2000, IMG = 24576;   // 3 row groups x 8 KB
 
+__device__ int P = 128;
 __device__ __forceinline__ unsigned ld_acq(const unsigned* p) { unsigned v; asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
 __device__ __forceinline__ void red_rel(unsigned* p) { asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p) : "memory"); }
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -159,7 +160,10 @@ __global__ void __launch_bounds__(NT, 1) probe(unsigned* ctr, unsigned char* img
   if (cta == 0 && tid == 0) { result[mode] = (t1 - t0) / ROUNDS; result[8 + mode] = acc; }
 }
 
-int main() {
+int main(int argc, char** argv) {
+  int hostP = argc > 1 ? atoi(argv[1]) : 128;
+  CK(cudaMemcpyToSymbol(P, &hostP, sizeof(int)));
+  printf("== %d CTAs ==\n", hostP);
   unsigned* ctr; unsigned char* img; long long* res;
   CK(cudaMalloc(&ctr, 64)); CK(cudaMalloc(&img, IMG * 4)); CK(cudaMalloc(&res, 256));
   CK(cudaMemset(res, 0, 256));
@@ -168,9 +172,10 @@ int main() {
                          "D flag-in-data gather 24KB (no barrier)", "E counter barrier, 4 staggered relaxed pollers",
                          "F counter barrier, red.relaxed + ld.relaxed (no fences)", "G flag-in-data, polite probe + LDG gather 24KB"};
   for (int mode = 0; mode < 7; ++mode) {
+    if (hostP != 128 && (mode == 3 || mode == 6)) continue;
     CK(cudaMemset(ctr, 0, 64)); CK(cudaMemset(img, 0, IMG * 4));
     void* args[] = {&ctr, &img, &res, &mode};
-    CK(cudaLaunchCooperativeKernel((const void*)probe, dim3(P), dim3(NT), args, IMG + 1024, 0));
+    CK(cudaLaunchCooperativeKernel((const void*)probe, dim3(hostP), dim3(NT), args, IMG + 1024, 0));
     CK(cudaDeviceSynchronize());
     long long h[32]; CK(cudaMemcpy(h, res, 256, cudaMemcpyDeviceToHost));
     if (mode == 6 && h[24]) printf("   mode G FAILED at round %lld\n", h[24] - 1);

@@ -528,19 +528,19 @@ __global__ void __launch_bounds__(NT, 1) wrnn_tc_kernel(const TcParams p) {
       quarter(dS1, TC_S1 + q * N_S1, idesc_s1);
       if (leader) launch(1, target, base + 1 * xch_stride);
       quarter(dS2, TC_S2 + q * N_S2, idesc_s2);
-      if (leader) launch(2, target, base + 2 * xch_stride);
-      quarter(dS3, TC_S3 + q * N_S3, idesc_s3);
-      if (leader) launch(3, target, base + 3 * xch_stride);
-      quarter(dF3, TC_F3 + q * N_F3, idesc_f3);
       if (t + 1 < S) {
-        // Conditioning of step t+1, in the slack while the fold warps sample and run GRU1: the chain queues
-        // behind F3 in the tensor pipe and lands before phase A of step t+1 asks for it.
+        // Conditioning of step t+1: queued behind S2 in the tensor pipe.  (Measured: placing this block after
+        // the F3 chain instead costs ~0.5 us per step -- it then delays phase A of the next step.)
         mbar_wait(bar_q, (uint32_t)(t & 1), p.abort_flag);           // chain t has consumed the cond image
         cond_store(t + 1);
         named_bar_sync(2, 128);
         if (q == 1) cond_chain(par ? TC_Q0 : TC_Q1);
         if (t + 2 < S) cond_fetch(t + 2);
       }
+      if (leader) launch(2, target, base + 2 * xch_stride);
+      quarter(dS3, TC_S3 + q * N_S3, idesc_s3);
+      if (leader) launch(3, target, base + 3 * xch_stride);
+      quarter(dF3, TC_F3 + q * N_F3, idesc_f3);
     }
     if (profiling) { p.prof[5] = t_poll; p.prof[6] = t_gather; p.prof[7] = t_issue; }
   }
