@@ -134,23 +134,50 @@ __device__ __forceinline__ void tmem_ld4(uint32_t taddr, float* v) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(taddr));
   v[0] = __uint_as_float(a); v[1] = __uint_as_float(b); v[2] = __uint_as_float(c); v[3] = __uint_as_float(d);
 }
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr));
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]) : "r"(taddr));
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t r[32];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]) : "r"(taddr));
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-// out[0 .. 4*NG) = sum over the KW partial accumulators (column stride `wstride`) of 4*NG columns at taddr
-template <int NG, int NW>
+template <int N> __device__ __forceinline__ void tmem_ldN(uint32_t taddr, float* v) {
+  if constexpr (N == 4) tmem_ld4(taddr, v);
+  else if constexpr (N == 8) tmem_ld8(taddr, v);
+  else if constexpr (N == 16) tmem_ld16(taddr, v);
+  else tmem_ld32(taddr, v);
+}
+// out[0 .. NC) = sum over the NW partial accumulators (column stride `wstride`) of NC columns at taddr.
+// One wide tcgen05.ld per partial (NL = NC rounded up to 4/8/16/32 columns; the surplus columns are ignored):
+// every tcgen05.ld instruction costs tens of cycles of issue on the critical path, so fewer and wider wins.
+template <int NC, int NW>
 __device__ __forceinline__ void tmem_ld_sum(uint32_t taddr, int wstride, float* out) {
-  float part[NW > 1 ? NW - 1 : 1][4 * NG];
+  constexpr int NL = NC <= 4 ? 4 : NC <= 8 ? 8 : NC <= 16 ? 16 : 32;
+  float part[NW][NL];
 #pragma unroll
-  for (int g = 0; g < NG; ++g) tmem_ld4(taddr + 4 * g, out + 4 * g);
-#pragma unroll
-  for (int w = 1; w < NW; ++w) {
-#pragma unroll
-    for (int g = 0; g < NG; ++g) tmem_ld4(taddr + w * wstride + 4 * g, part[w - 1] + 4 * g);
-  }
+  for (int w = 0; w < NW; ++w) tmem_ldN<NL>(taddr + w * wstride, part[w]);
   tmem_ld_wait();
 #pragma unroll
-  for (int w = 1; w < NW; ++w) {
+  for (int i = 0; i < NC; ++i) {
+    float acc = part[0][i];
 #pragma unroll
-    for (int i = 0; i < 4 * NG; ++i) out[i] += part[w - 1][i];
+    for (int w = 1; w < NW; ++w) acc += part[w][i];
+    out[i] = acc;
   }
 }
 __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
@@ -174,11 +201,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* ab
   }
 }
 __device__ __forceinline__ void counter_wait(const unsigned* ctr, unsigned target, int* abort_flag) {
-  // relaxed loads: the counter is only a hint (see publish()); the data is validated against the sentinel
-  auto ld = [](const unsigned* p) { unsigned v; asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; };
-  if (ld(ctr) >= target) return;
+  if (ld_acquire_u32(ctr) >= target) return;
   const long long t0 = clock64();
-  while (ld(ctr) < target) {
+  while (ld_acquire_u32(ctr) < target) {
     if (clock64() - t0 > kWatchdogCycles || ld_relaxed_s32(abort_flag) != 0) { atomicExch(abort_flag, 1); return; }
   }
 }
@@ -239,7 +264,7 @@ __global__ void __launch_bounds__(NT, 1) wrnn_tc_kernel(const TcParams p) {
   const int B = p.n_seg, S = p.steps, u0 = cta * U;
   const int n_groups = (B + 7) / 8;                    // real 8-row groups of the A images
   const uint32_t img_bytes = (uint32_t)n_groups * SBO_H;
-  const size_t xch_stride = (size_t)3 * img_bytes;     // per vector: ring of three step slots
+  const size_t xch_stride = (size_t)2 * img_bytes;     // per vector: two parities
 
   // ---- one-time setup: weights -> smem images, barriers, TMEM --------------------------------
   {
@@ -275,22 +300,15 @@ __global__ void __launch_bounds__(NT, 1) wrnn_tc_kernel(const TcParams p) {
     const size_t pub_off = (size_t)(fold >> 3) * SBO_H + (u0 >> 3) * 128 + (fold & 7) * 16 + (u0 & 7) * 2;
     const bool profiling = (p.prof != nullptr) && cta == 0 && tid == 0;
     long long tprof[5] = {0, 0, 0, 0, 0};
-    // Publish this fold's 4 values of this CTA's units into ring slot `cur` of vector v and put the sentinel back
-    // into slot `prev` (step t-1: every CTA has consumed v(t-1) by the time anyone can publish v(t)).  Arrival is
-    // ONE RELAXED increment per CTA: no release fence (measured ~1100 cycles per exchange).  Consumers therefore
-    // treat the counter as a hint and validate the data itself: 0xFFFF pairs are fp16/bf16 NaNs that the
-    // saturating conversions never produce, so "no sentinel left" == "every producer's store has landed".
-    auto publish = [&](int v, int cur, int prev, const float* val) {
+    auto publish = [&](unsigned char* img, const float* v) {   // this fold's 4 values of this CTA's units
       uint2 w;
-      w.x = pack2<FMT>(val[0], val[1]); w.y = pack2<FMT>(val[2], val[3]);
-      unsigned char* base = p.xch + (size_t)v * xch_stride + pub_off;
-      if (owns_fold) {
-        asm volatile("st.global.cg.v2.u32 [%0], {%1, %2};" :: "l"(base + (size_t)cur * img_bytes), "r"(w.x), "r"(w.y) : "memory");
-        asm volatile("st.global.cg.v2.u32 [%0], {%1, %2};" :: "l"(base + (size_t)prev * img_bytes), "r"(0xffffffffu), "r"(0xffffffffu) : "memory");
-      }
+      w.x = pack2<FMT>(v[0], v[1]); w.y = pack2<FMT>(v[2], v[3]);
+      if (owns_fold) *reinterpret_cast<uint2*>(img + pub_off) = w;
+    };
+    auto signal = [&](int v) {                           // all fold warps have stored: one release increment per CTA
       tc_fence_before();
-      named_bar_sync(1, 128);                              // all fold warps: accumulators read, stores issued
-      if (tid == 0) asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" :: "l"(p.counters + v) : "memory");
+      named_bar_sync(1, 128);
+      if (tid == 0) red_release_add_u32(p.counters + v, 1u);
     };
     float h1[U] = {0.f, 0.f, 0.f, 0.f}, h2[U] = {0.f, 0.f, 0.f, 0.f};
     float x = 0.f;
@@ -299,7 +317,10 @@ __global__ void __launch_bounds__(NT, 1) wrnn_tc_kernel(const TcParams p) {
     for (int t = 0; t < S; ++t) {
       const int par = t & 1;
       const uint32_t tq = (par ? TC_Q1 : TC_Q0);
-      const int cur = t % 3, prev = (t + 2) % 3;          // ring slots of step t and step t-1
+      unsigned char* img_h1 = p.xch + 0 * xch_stride + (size_t)par * img_bytes;
+      unsigned char* img_h2 = p.xch + 1 * xch_stride + (size_t)par * img_bytes;
+      unsigned char* img_y1 = p.xch + 2 * xch_stride + (size_t)par * img_bytes;
+      unsigned char* img_y2 = p.xch + 3 * xch_stride + (size_t)par * img_bytes;
       long long tp0 = 0;
       if (profiling) tp0 = clock64();
 
@@ -331,10 +352,9 @@ __global__ void __launch_bounds__(NT, 1) wrnn_tc_kernel(const TcParams p) {
         mbar_wait(bar_q, (uint32_t)(t & 1), p.abort_flag);           // pre_t landed in D_Q[par]
         tc_fence_after();
         if (p.x_force && t > 0) x = xf;
-#pragma unroll
-        for (int c = 0; c < 32; c += 4) tmem_ld4(tlane + tq + c, pre + c);
+        tmem_ld32(tlane + tq, pre);
         float gh[12];
-        tmem_ld_sum<3, KW>(tlane + TC_S1 + 12, N_S1, gh);           // W1h h1 (step t-1, phase B); also completes `pre`
+        tmem_ld_sum<12, KW>(tlane + TC_S1 + 12, N_S1, gh);           // W1h h1 (step t-1, phase B); also completes `pre`
 #pragma unroll
         for (int q = 0; q < 32; ++q) pre[q] += qk[q] + x * vq[q];
         float hv[U];
@@ -345,7 +365,8 @@ __global__ void __launch_bounds__(NT, 1) wrnn_tc_kernel(const TcParams p) {
           h1[j] = gru_unit_fast(pre[j], pre[U + j], pre[2 * U + j], ghr, ghz, ghn, h1[j]);
           hv[j] = h1[j];
         }
-        publish(0, cur, prev, hv);
+        publish(img_h1, hv);
+        signal(0);
       }
       if (profiling) { const long long c = clock64(); tprof[0] += c - tp0; tp0 = c; }
 
@@ -354,8 +375,8 @@ __global__ void __launch_bounds__(NT, 1) wrnn_tc_kernel(const TcParams p) {
         mbar_wait(bar_mma, n_mma & 1, p.abort_flag); ++n_mma;
         tc_fence_after();
         float gi[12], gh[12];
-        tmem_ld_sum<3, KW>(tlane + TC_S1, N_S1, gi);                // W2x h1'
-        tmem_ld_sum<3, KW>(tlane + TC_S2 + 4, N_S2, gh);            // W2h h2 (step t-1, phase C)
+        tmem_ld_sum<12, KW>(tlane + TC_S1, N_S1, gi);                // W2x h1'
+        tmem_ld_sum<12, KW>(tlane + TC_S2 + 4, N_S2, gh);            // W2h h2 (step t-1, phase C)
         float hv[U];
 #pragma unroll
         for (int j = 0; j < U; ++j) {
@@ -364,7 +385,8 @@ __global__ void __launch_bounds__(NT, 1) wrnn_tc_kernel(const TcParams p) {
           h2[j] = gru_unit_fast(gi[j] + pre[3 * U + j], gi[U + j] + pre[4 * U + j], gi[2 * U + j] + pre[5 * U + j], ghr, ghz, ghn, h2[j]);
           hv[j] = h2[j];
         }
-        publish(1, cur, prev, hv);
+        publish(img_h2, hv);
+        signal(1);
       }
       if (profiling) { const long long c = clock64(); tprof[1] += c - tp0; tp0 = c; }
 
@@ -373,12 +395,13 @@ __global__ void __launch_bounds__(NT, 1) wrnn_tc_kernel(const TcParams p) {
         mbar_wait(bar_mma, n_mma & 1, p.abort_flag); ++n_mma;
         tc_fence_after();
         float a[4], b4[4];
-        tmem_ld_sum<1, KW>(tlane + TC_S2, N_S2, a);                 // F1x h2'
-        tmem_ld_sum<1, KW>(tlane + TC_S1 + 24, N_S1, b4);           // F1x h1' (phase B)
+        tmem_ld_sum<4, KW>(tlane + TC_S2, N_S2, a);                 // F1x h2'
+        tmem_ld_sum<4, KW>(tlane + TC_S1 + 24, N_S1, b4);           // F1x h1' (phase B)
         float yv[U];
 #pragma unroll
         for (int j = 0; j < U; ++j) yv[j] = fmaxf(a[j] + b4[j] + pre[6 * U + j], 0.f);
-        publish(2, cur, prev, yv);
+        publish(img_y1, yv);
+        signal(2);
       }
       if (profiling) { const long long c = clock64(); tprof[2] += c - tp0; tp0 = c; }
 
@@ -387,11 +410,12 @@ __global__ void __launch_bounds__(NT, 1) wrnn_tc_kernel(const TcParams p) {
         mbar_wait(bar_mma, n_mma & 1, p.abort_flag); ++n_mma;
         tc_fence_after();
         float a[4];
-        tmem_ld_sum<1, KW>(tlane + TC_S3, N_S3, a);
+        tmem_ld_sum<4, KW>(tlane + TC_S3, N_S3, a);
         float yv[U];
 #pragma unroll
         for (int j = 0; j < U; ++j) yv[j] = fmaxf(a[j] + pre[7 * U + j], 0.f);
-        publish(3, cur, prev, yv);
+        publish(img_y2, yv);
+        signal(3);
       }
       if (profiling) { const long long c = clock64(); tprof[3] += c - tp0; tp0 = c; }
 
@@ -400,8 +424,8 @@ __global__ void __launch_bounds__(NT, 1) wrnn_tc_kernel(const TcParams p) {
         mbar_wait(bar_mma, n_mma & 1, p.abort_flag); ++n_mma;
         tc_fence_after();
         float lg[32];
-        tmem_ld_sum<4, KW>(tlane + TC_F3, N_F3, lg);                // two halves keep the register peak down
-        tmem_ld_sum<4, KW>(tlane + TC_F3 + 16, N_F3, lg + 16);
+        tmem_ld_sum<16, KW>(tlane + TC_F3, N_F3, lg);               // two halves keep the register peak down
+        tmem_ld_sum<16, KW>(tlane + TC_F3 + 16, N_F3, lg + 16);
 #pragma unroll
         for (int i = 0; i < 30; ++i) lg[i] += b3[i];
         x = mol_sample_fast(lg, ur);
@@ -437,7 +461,7 @@ __global__ void __launch_bounds__(NT, 1) wrnn_tc_kernel(const TcParams p) {
                    idesc_s3 = umma_idesc(MT, N_S3, FMT), idesc_f3 = umma_idesc(MT, N_F3, FMT),
                    idesc_q = umma_idesc(MT, N_Q, FMT);
     const bool profiling = (p.prof != nullptr) && cta == 0 && tid == 128;
-    long long t_poll = 0, t_gather = 0, t_issue = 0, n_retry = 0;
+    long long t_poll = 0, t_gather = 0, t_issue = 0;
     unsigned n_g = 0;
 
     // D[64 folds, N] (+)= A[64, 16] * B[N, 16]^T per instruction; K advances by two core-matrix columns
@@ -445,58 +469,16 @@ __global__ void __launch_bounds__(NT, 1) wrnn_tc_kernel(const TcParams p) {
     auto launch = [&](int v, unsigned target, const unsigned char* img) {      // leader only
       long long c0 = 0;
       if (profiling) c0 = clock64();
-      if (lane == 0) counter_wait(p.counters + v, target, p.abort_flag);        // hint: all 128 producers have issued their stores
+      if (lane == 0) counter_wait(p.counters + v, target, p.abort_flag);        // acquire: all 128 producers have published
       __syncwarp();
+      proxy_fence_global();                                                     // generic-proxy writes -> async-proxy (TMA) read
       if (profiling) t_poll += clock64() - c0;
       tma_bulk_g2s(sA, img, img_bytes, bar_g);
-    };
-    // Sentinel check of this warp's K quarter of the freshly gathered image (lane l, slot j: group gb + j/4, chunk
-    // c = (j%4)*32 + l -> row g*8 + c%8, k8 = 16q + c/8).  Chunks whose store had not landed when the TMA read
-    // them (the relaxed counter allows that, rarely) are re-read from L2 with polite polling and patched in.
-    const unsigned char* cur_img = nullptr;
-    auto validate_quarter = [&]() {
-      bool patched = false;
-      for (int gb = 0; gb < n_groups; gb += 3) {
-        unsigned pending = 0;
-#pragma unroll
-        for (int j = 0; j < 12; ++j) {
-          const int g = gb + (j >> 2), c = (j & 3) * 32 + lane;
-          if (g < n_groups && g * 8 + (c & 7) < B) {
-            const uint4 v = *reinterpret_cast<const uint4*>(smem + OFF_A + g * SBO_H + q * 2048 + c * 16);
-            if (v.x == 0xffffffffu || v.z == 0xffffffffu) pending |= 1u << j;
-          }
-        }
-        if (!__any_sync(0xffffffffu, pending != 0)) continue;
-        patched = true;
-        const long long w0 = clock64();
-        for (;;) {
-          if (profiling) ++n_retry;
-#pragma unroll
-          for (int j = 0; j < 12; ++j) {
-            if (pending & (1u << j)) {
-              const int g = gb + (j >> 2), c = (j & 3) * 32 + lane;
-              const unsigned char* src = cur_img + (size_t)g * SBO_H + q * 2048 + c * 16;
-              uint4 v;
-              asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(src) : "memory");
-              if (v.x != 0xffffffffu && v.z != 0xffffffffu) {
-                *reinterpret_cast<uint4*>(smem + OFF_A + g * SBO_H + q * 2048 + c * 16) = v;
-                pending &= ~(1u << j);
-              }
-            }
-          }
-          if (!__any_sync(0xffffffffu, pending != 0)) break;
-          if (clock64() - w0 > kWatchdogCycles || ld_relaxed_s32(p.abort_flag) != 0) { atomicExch(p.abort_flag, 1); break; }
-          __nanosleep(32);
-        }
-      }
-      if (patched) proxy_fence_smem();
-      __syncwarp();
     };
     auto quarter = [&](uint64_t db, uint32_t d_col, uint32_t idesc) {
       long long c0 = 0, c1 = 0;
       if (profiling) c0 = clock64();
       mbar_wait(bar_g, n_g & 1, p.abort_flag); ++n_g;                           // the gathered vector is in smem
-      validate_quarter();
       tc_fence_after();
       if (profiling) c1 = clock64();
 #pragma unroll
@@ -567,12 +549,10 @@ __global__ void __launch_bounds__(NT, 1) wrnn_tc_kernel(const TcParams p) {
     for (int t = 0; t < S; ++t) {
       const int par = t & 1;
       const unsigned target = (unsigned)P * (unsigned)(t + 1);
-      const unsigned char* base = p.xch + (size_t)(t % 3) * img_bytes;
-      cur_img = base + 0 * xch_stride;
-      if (leader) launch(0, target, cur_img);
+      const unsigned char* base = p.xch + (size_t)par * img_bytes;
+      if (leader) launch(0, target, base + 0 * xch_stride);
       quarter(dS1, TC_S1 + q * N_S1, idesc_s1);
-      cur_img = base + 1 * xch_stride;
-      if (leader) launch(1, target, cur_img);
+      if (leader) launch(1, target, base + 1 * xch_stride);
       quarter(dS2, TC_S2 + q * N_S2, idesc_s2);
       if (t + 1 < S) {
         // Conditioning of step t+1: queued behind S2 in the tensor pipe.  (Measured: placing this block after
@@ -583,14 +563,12 @@ __global__ void __launch_bounds__(NT, 1) wrnn_tc_kernel(const TcParams p) {
         if (q == 1) cond_chain(par ? TC_Q0 : TC_Q1);
         if (t + 2 < S) cond_fetch(t + 2);
       }
-      cur_img = base + 2 * xch_stride;
-      if (leader) launch(2, target, cur_img);
+      if (leader) launch(2, target, base + 2 * xch_stride);
       quarter(dS3, TC_S3 + q * N_S3, idesc_s3);
-      cur_img = base + 3 * xch_stride;
-      if (leader) launch(3, target, cur_img);
+      if (leader) launch(3, target, base + 3 * xch_stride);
       quarter(dF3, TC_F3 + q * N_F3, idesc_f3);
     }
-    if (profiling) { p.prof[5] = t_poll; p.prof[6] = t_gather; p.prof[7] = t_issue; p.prof[8] = n_retry; }
+    if (profiling) { p.prof[5] = t_poll; p.prof[6] = t_gather; p.prof[7] = t_issue; }
   }
 
   tc_fence_before();
@@ -645,7 +623,7 @@ class TcEngine : public Engine {
     WRNN_CUDA_OK(cudaMemcpy(d_blob_, blob.data(), blob.size(), cudaMemcpyHostToDevice));
     WRNN_CUDA_OK(cudaMalloc(&d_sync_, 256));
     WRNN_CUDA_OK(cudaMemset(d_sync_, 0, 256));
-    scratch_bytes_ = (size_t)4 * 3 * 8 * SBO_H;          // 4 vectors x 3 ring slots x (up to 8 row groups)
+    scratch_bytes_ = (size_t)4 * 2 * 8 * SBO_H;          // 4 vectors x 2 parities x (up to 8 row groups)
     WRNN_CUDA_OK(cudaMalloc(&d_scratch_, scratch_bytes_));
     WRNN_CUDA_OK(cudaFuncSetAttribute(kernel(), cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     int n_sm = 0;
@@ -678,7 +656,6 @@ class TcEngine : public Engine {
       p.f0 = f0;
       p.n_seg = job.n_seg - f0 < MT ? job.n_seg - f0 : MT;
       WRNN_CUDA_OK(cudaMemsetAsync(d_sync_, 0, 32, stream));                       // arrival counters (the abort flag is sticky)
-      WRNN_CUDA_OK(cudaMemsetAsync(d_scratch_, 0xff, scratch_bytes_, stream));    // sentinel in every exchange slot
       void* args[] = {&p};
       WRNN_CUDA_OK(cudaLaunchCooperativeKernel(kernel(), dim3(P), dim3(NT), args, SMEM_BYTES, stream));
       ++launches;
@@ -696,9 +673,8 @@ class TcEngine : public Engine {
     if (getenv("WRNN_TC_PROF") && last_steps_ > 0) {     // average cycles per step seen by CTA 0
       const long long n = last_steps_;
       fprintf(stderr, "[wrnn_tc prof] steps=%d | fold thread: A(gru1)=%lld B(h1'->gru2)=%lld C(h2'->y1)=%lld D(y1->y2)=%lld "
-              "E(y2->sample)=%lld | driver warp: poll=%lld gather+validate=%lld issue=%lld (cycles per step) patch rounds per step=%.4f\n",
-              last_steps_, prof[0] / n, prof[1] / n, prof[2] / n, prof[3] / n, prof[4] / n, prof[5] / n, prof[6] / n, prof[7] / n,
-              (double)prof[8] / (double)n);
+              "E(y2->sample)=%lld | driver warp: poll=%lld gather=%lld issue=%lld  (cycles per step)\n",
+              last_steps_, prof[0] / n, prof[1] / n, prof[2] / n, prof[3] / n, prof[4] / n, prof[5] / n, prof[6] / n, prof[7] / n);
     }
     if (flag != 0) {
       set_error(flag == 2 ? "persistent kernel aborted: an mbarrier wait (MMA / TMA completion) timed out"
@@ -707,7 +683,7 @@ class TcEngine : public Engine {
     }
     return WRNN_OK;
   }
-  long long prof[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  long long prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 
  private:
   void *d_blob_ = nullptr, *d_scratch_ = nullptr, *d_sync_ = nullptr;
