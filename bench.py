@@ -60,6 +60,16 @@ def build_model(device):
     return m.to(device)
 
 
+def measured_traffic(args, model):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel on this workload, taken from
+    the committed ncu --set full capture (profiles/r01_tc_traffic.json); None when no capture matches."""
+    p = ROOT / "profiles" / "r01_tc_traffic.json"
+    if not p.is_file() or args.workload != "cfg2" or args.seg_steps:
+        return None
+    d = json.loads(p.read_text())
+    return d.get("dram_bytes_per_launch") if d.get("engine") == model.gen_stats.get("engine") else None
+
+
 def measured_peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.is_file():
@@ -201,7 +211,12 @@ def run_ours(args):
 
     model = build_model(device)
     model.gen_precision, model.gen_engine = args.precision, args.engine
-    T = frames_for(world)
+    cfg5 = args.workload == "cfg5"
+    if cfg5:
+        # BASELINE configs[4] (SURVEY 8d choice A): T=172,034 frames = 35.8 min -> exactly 4096 folds with the
+        # reference's own target/overlap; the 4096 folds are sharded over the ranks (strong scaling); in-kernel RNG
+        model.gen_rng = "philox"
+    T = 172_034 if cfg5 else frames_for(world)
     torch.manual_seed(0)
     mel_host = torch.rand(1, 80, T).pin_memory()
     geo = fold_geometry(T * HOP, TARGET, OVERLAP)
@@ -216,17 +231,21 @@ def run_ours(args):
         off = shard.row_lo - shard.frame_lo * HOP
         m_up = m_up[off:off + shard.row_hi - shard.row_lo].contiguous()
         aux = aux[off:off + shard.row_hi - shard.row_lo].contiguous()
-    torch.manual_seed(1234)
-    u_all, _ = model._reference_draws(geo, S)
     f0, n = shard.seg_first, shard.n_seg
-    uni = torch.cat([u_all[:, 10 * f0:10 * (f0 + n)], u_all[:, 10 * B_total + f0:10 * B_total + f0 + n]], 1).contiguous().to(device)
+    if cfg5:
+        u_all, uni_ptr, h2d_rng = None, 0, 0
+    else:
+        torch.manual_seed(1234)
+        u_all, _ = model._reference_draws(geo, S)
+        uni = torch.cat([u_all[:, 10 * f0:10 * (f0 + n)], u_all[:, 10 * B_total + f0:10 * B_total + f0 + n]], 1).contiguous().to(device)
+        uni_ptr, h2d_rng = uni.data_ptr(), u_all.numel() * 4
     out = torch.empty((n, S), dtype=torch.float32, device=device)
     engine = model._get_engine(device)
     stream = torch.cuda.current_stream(device)
 
     def device_step():
         engine.generate(mels_up=m_up.data_ptr(), aux=aux.data_ptr(), L=m_up.shape[0], n_seg=n, seg_len=S,
-                        seg_stride=geo.seg_stride, out=out.data_ptr(), seg_first=f0, uniforms=uni.data_ptr(),
+                        seg_stride=geo.seg_stride, out=out.data_ptr(), seg_first=f0, uniforms=uni_ptr,
                         steps=args.seg_steps, stream=stream.cuda_stream)
         if world > 1:
             return gather_segments(out, shard, geo)
@@ -295,20 +314,21 @@ def run_ours(args):
         line = {
             "metric": "audio samples/sec (22.05 kHz) batched MoL generate", "value": value, "unit": "samples/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_dev / args.steps * 1e3,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "higher_is_better": True, "scaling": "strong" if cfg5 else "weak", "vs_baseline": None,
             "dtype": {"fp16": "f16", "bf16": "bf16", "fp32": "f32"}[args.precision], "data": "synthetic",
-            "config": {"workload": f"cfg2 x{world}: mel T={T} frames -> {B_total} folds x {S} steps "
-                                   f"({FOLDS_PER_GPU} folds per GPU), target={TARGET} overlap={OVERLAP}, MoL head, "
-                                   "rnn_dims=512, random-init weights, torch.rand mel",
+            "config": {"workload": (f"cfg5: mel T={T} frames (35.8 min) -> {B_total} folds x {S} steps sharded over {world} GPU(s), "
+                                    if cfg5 else
+                                    f"cfg2 x{world}: mel T={T} frames -> {B_total} folds x {S} steps ({FOLDS_PER_GPU} folds per GPU), ")
+                                   + f"target={TARGET} overlap={OVERLAP}, MoL head, rnn_dims=512, random-init weights, torch.rand mel",
                        "engine": model.gen_stats.get("engine", engine.name), "grid_ctas": engine.grid_ctas,
                        "parallelism": f"folds sharded x{world}" if world > 1 else "single GPU",
                        "l2_policy": "no flush: the per-step conditioning stream (183 MB per 19 folds) exceeds the 126 MB L2",
-                       "rng": "reference-compatible torch CPU draws, resident in HBM for `value`"},
+                       "rng": "in-kernel Philox4x32-10" if cfg5 else "reference-compatible torch CPU draws, resident in HBM for `value`"},
             "clocks": clocks, "gpu_launches": int(gpu_launches),
-            "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(mel_host.numel() * 4 + u_all.numel() * 4),
+            "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(mel_host.numel() * 4 + h2d_rng),
                     "d2h_bytes_per_step": int(B_total * S * 4), "ms_per_step": t_e2e / args.steps * 1e3},
             "roofline": {"bound": "tensor", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                         "frac": ach_tf / peak_tf, "traffic": None, "peak_source": peaks["src"],
+                         "frac": ach_tf / peak_tf, "traffic": measured_traffic(args, model), "peak_source": peaks["src"],
                          "note": "latency/sync-bound at 19 folds per GPU (SURVEY 8d): fraction of the dense-fp16 "
                                  "tensor roofline is reported for completeness",
                          "hbm_achieved_gbs": value / world * BYTES_PER_SAMPLE / 1e9, "hbm_peak_gbs": peaks["hbm_gbs"]},
@@ -334,6 +354,9 @@ def main():
     ap.add_argument("--engine", default="auto", choices=["auto", "simt", "tcgen05"])
     ap.add_argument("--cpu-sample-steps", type=int, default=3000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg5"],
+                    help="cfg2 (default, the headline config: 19 folds per GPU) or cfg5 (4096 folds of a 35.8-min mel, "
+                         "sharded over the ranks, in-kernel Philox draws)")
     ap.add_argument("--seg-steps", type=int, default=0,
                     help="PROFILING ONLY: generate just the first N steps of every fold in the device-timed region "
                          "(keeps ncu captures short); the printed line is then marked partial and is not a bench value")
