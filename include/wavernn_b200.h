@@ -50,7 +50,7 @@ enum { WRNN_MODE_MOL = 0, WRNN_MODE_RAW = 1 };   /* fatchord_version.py:98-104 *
 enum { WRNN_PREC_F16 = 0, WRNN_PREC_FP32 = 1, WRNN_PREC_BF16 = 2 };
 
 /* Which kernel family executes the job.  AUTO picks the fastest that supports it. */
-enum { WRNN_ENGINE_AUTO = 0, WRNN_ENGINE_SIMT = 1, WRNN_ENGINE_TCGEN05 = 2, WRNN_ENGINE_TCGEN05_CLUSTER = 3 };
+enum { WRNN_ENGINE_AUTO = 0, WRNN_ENGINE_SIMT = 1, WRNN_ENGINE_TCGEN05 = 2 };
 
 typedef struct wrnn_handle wrnn_t;
 

@@ -221,47 +221,3 @@ def test_auto_engine_tiles_large_jobs_on_tcgen05_and_serves_raw_on_simt(mol):
     expo = np.ones((4, 2, 512), np.float32)
     _, name = run_engine(raw_model, m_up[:200], aux[:200], n_seg=2, seg_len=4, seg_stride=4, expo=expo)
     assert name.startswith("simt")
-
-
-# ---------------------------------------------------------------------------------------------
-# tcgen05 cluster-tail engine (fc1/fc2/fc3 per 16-CTA cluster, y1/y2 over DSMEM; n_seg <= 24)
-# ---------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("precision", ["fp16", "bf16"])
-def test_cluster_tail_engine_matches_emulation_and_reference(mol, precision):
-    out, lg, name = run_engine(mol["model"], mol["m_up"], mol["aux"], uniforms=mol["U"], want_logits=True,
-                               precision=precision, engine="tcgen05c", **mol["kw"])
-    assert name == f"tcgen05c-{precision}"
-    emu, lemu = C.generate_segments(mol["w"], mol["m_up"], mol["aux"], uniforms=mol["U"], precision=precision,
-                                    want_logits=True, **mol["kw"])
-    d_emu, d_ref = np.abs(out - emu), np.abs(out - mol["g"]["raw"])
-    print(f"{name}: vs emulation max {d_emu.max():.3e} (logits {np.abs(lg - lemu).max():.3e}); vs reference max {d_ref.max():.3e}")
-    tol_emu, tol_ref = (1e-3, 2e-2) if precision == "fp16" else (2e-2, 5e-2)
-    assert np.isfinite(out).all()
-    assert d_emu.max() <= tol_emu and d_ref.max() <= tol_ref
-
-
-def test_cluster_tail_teacher_forced_logits(mol):
-    g = mol["g"]
-    kw = dict(uniforms=mol["U"], x_force=g["raw"].T.copy(), want_logits=True, steps=600, **mol["kw"])
-    out_c, lg_c, name = run_engine(mol["model"], mol["m_up"], mol["aux"], engine="tcgen05c", **kw)
-    out_t, lg_t, _ = run_engine(mol["model"], mol["m_up"], mol["aux"], engine="tcgen05", **kw)
-    print(f"{name} teacher-forced logits: vs reference {np.abs(lg_c - g['logits']).max():.3e}, vs tcgen05 {np.abs(lg_c - lg_t).max():.3e}")
-    assert np.abs(lg_c - g["logits"]).max() <= 5e-3
-    assert np.abs(lg_c - lg_t).max() <= 1e-3
-
-
-@pytest.mark.parametrize("n_seg", [1, 8, 19, 24])
-def test_cluster_tail_fold_counts_and_zero_padded_tail(n_seg):
-    model = helpers.make_model(3, "MOL", "cuda")
-    w = O.hot_weights(helpers.state_numpy(model))
-    rs = np.random.RandomState(100 + n_seg)
-    seg_len, stride = 160, 100
-    L = (n_seg - 1) * stride + 90
-    m_up = rs.rand(L, 80).astype(np.float32)
-    aux = rs.randn(L, 128).astype(np.float32)
-    U = helpers.replay_uniforms(5, seg_len, n_seg)
-    kw = dict(n_seg=n_seg, seg_len=seg_len, seg_stride=stride, uniforms=U)
-    out, name = run_engine(model, m_up, aux, engine="tcgen05c", **kw)
-    emu = C.generate_segments(w, m_up, aux, precision="fp16", **kw)
-    print(f"{name} n_seg={n_seg}: vs emulation {np.abs(out - emu).max():.3e}")
-    assert np.abs(out - emu).max() <= 1e-3

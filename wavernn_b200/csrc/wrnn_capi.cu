@@ -75,9 +75,7 @@ int wrnn_create(wrnn_t** out, const wrnn_cfg* cfg, const wrnn_weights* w, int de
     engine = WRNN_ENGINE_SIMT;
   }
   if (engine == WRNN_ENGINE_AUTO) engine = WRNN_ENGINE_TCGEN05;
-  if (engine == WRNN_ENGINE_TCGEN05_CLUSTER) {
-    rc = make_tcc_engine(*cfg, hw, device, &eng);
-  } else if (engine == WRNN_ENGINE_TCGEN05) {
+  if (engine == WRNN_ENGINE_TCGEN05) {
     rc = make_tc_engine(*cfg, hw, device, &eng);
     if (rc != WRNN_OK && cfg->engine == WRNN_ENGINE_AUTO && rc == WRNN_E_INVALID) {
       // configuration outside the tensor-core engine's envelope: AUTO may pick the SIMT engine
@@ -99,16 +97,6 @@ int wrnn_create(wrnn_t** out, const wrnn_cfg* cfg, const wrnn_weights* w, int de
 
 // ENGINE_AUTO: jobs outside the tensor-core engine's envelope go to the SIMT engine (same arithmetic contract).
 static int pick_engine(wrnn_t* h, const wrnn_job* job, Engine** out) {
-  // ENGINE_AUTO: small jobs (<= 24 folds) go to the cluster-tail engine when the device can host it
-  if (h->auto_engine && h->host_weights && job->n_seg <= 24 && h->engine->cfg.mode == WRNN_MODE_MOL &&
-      h->engine->cfg.precision != WRNN_PREC_FP32) {
-    if (!h->small_tried) {
-      h->small_tried = true;
-      const char* off = getenv("WRNN_NO_CLUSTER_TAIL");
-      if (!(off && off[0] == '1') && make_tcc_engine(h->engine->cfg, *h->host_weights, h->engine->device, &h->small) != WRNN_OK) h->small = nullptr;
-    }
-    if (h->small && h->small->supports(*job)) { *out = h->small; return WRNN_OK; }
-  }
   if (h->engine->supports(*job)) { *out = h->engine; return WRNN_OK; }
   if (!h->auto_engine || !h->host_weights) {
     set_error(std::string("job is outside the envelope of engine '") + h->engine->name() + "'");
@@ -127,7 +115,6 @@ void wrnn_destroy(wrnn_t* h) {
   if (h->d_stage) cudaFree(h->d_stage);
   delete h->engine;
   delete h->fallback;
-  delete h->small;
   delete h->host_weights;
   delete h;
 }
@@ -199,7 +186,7 @@ int wrnn_generate_host(wrnn_t* h, const wrnn_job* job) {
 const char* wrnn_engine_name(const wrnn_t* h) { return (h && h->last) ? h->last->name() : ""; }
 int wrnn_grid_ctas(const wrnn_t* h) { return (h && h->last) ? h->last->grid_ctas() : 0; }
 int64_t wrnn_launch_count(const wrnn_t* h) {
-  return (h && h->engine) ? h->engine->launches + (h->fallback ? h->fallback->launches : 0) + (h->small ? h->small->launches : 0) : 0;
+  return (h && h->engine) ? h->engine->launches + (h->fallback ? h->fallback->launches : 0) : 0;
 }
 
 }  // extern "C"

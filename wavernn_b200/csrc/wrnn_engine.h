@@ -37,16 +37,12 @@ class Engine {
 int make_simt_engine(const wrnn_cfg& cfg, const HostWeights& w, int device, Engine** out);
 // tcgen05 engine: 5th-gen tensor-core contractions with TMEM accumulators (bf16 operands).
 int make_tc_engine(const wrnn_cfg& cfg, const HostWeights& w, int device, Engine** out);
-// tcgen05 cluster-tail engine: fc1/fc2/fc3 replicated per 16-CTA cluster, y1/y2 exchanged over DSMEM (n_seg <= 24).
-int make_tcc_engine(const wrnn_cfg& cfg, const HostWeights& w, int device, Engine** out);
 
 }  // namespace wrnn
 
 struct wrnn_handle {
   wrnn::Engine* engine = nullptr;          // engine chosen at create time
   wrnn::Engine* fallback = nullptr;        // ENGINE_AUTO only: SIMT engine, created on first job outside `engine`'s envelope
-  wrnn::Engine* small = nullptr;           // ENGINE_AUTO only: cluster-tail engine for jobs of <= 24 folds (null if unavailable)
-  bool small_tried = false;
   wrnn::Engine* last = nullptr;            // engine that served the most recent job
   wrnn::HostWeights* host_weights = nullptr;
   bool auto_engine = false;
