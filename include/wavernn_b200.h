@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define WRNN_ABI_VERSION 1
+#define WRNN_ABI_VERSION 2
 
 enum {
   WRNN_OK = 0,
@@ -113,6 +113,12 @@ typedef struct {
   const float *x_force;   /* [seg_len, n_seg] teacher forcing: step t consumes
                              x_force[t-1] instead of its own previous sample        */
   float *logits_out;      /* [seg_len, n_seg, n_classes] fc3 outputs per step        */
+  /* Optional fold tables (device, [n_seg] int64 each; NULL = the strided windows above).
+   * fold b, step t reads conditioning row  fold_row0[b] + t ; rows >= fold_row_end[b] read as zeros.
+   * Lets one job carry the folds of SEVERAL utterances laid end to end in mels_up / aux
+   * (WaveRNN.generate_many; the reference vocodes sentences one at a time, gen_tacotron.py:139-163). */
+  const int64_t *fold_row0;
+  const int64_t *fold_row_end;
 } wrnn_job;
 
 int wrnn_abi_version(void);

@@ -221,3 +221,21 @@ def test_auto_engine_tiles_large_jobs_on_tcgen05_and_serves_raw_on_simt(mol):
     expo = np.ones((4, 2, 512), np.float32)
     _, name = run_engine(raw_model, m_up[:200], aux[:200], n_seg=2, seg_len=4, seg_stride=4, expo=expo)
     assert name.startswith("simt")
+
+
+def test_generate_many_equals_sequential_generate_calls(mol, tmp_path):
+    """the folds of several utterances in one job (per-fold conditioning windows, ABI v2) give exactly
+    the waveforms of one generate() call per utterance under the same torch seed."""
+    model = mol["model"]
+    mels = [helpers.make_mel(T, seed) for T, seed in ((30, 0), (26, 3), (41, 5), (22, 7))]
+    torch.manual_seed(99)
+    seq = [model.generate(m, None, True, 2750, 275, False) for m in mels]
+    torch.manual_seed(99)
+    many = model.generate_many(mels, [tmp_path / f"{i}.wav" for i in range(len(mels))], 2750, 275, False)
+    assert model.gen_stats["utterances"] == 4 and model.gen_stats["engine"].startswith("tcgen05")
+    for a, b in zip(seq, many):
+        assert a.shape == b.shape
+        np.testing.assert_allclose(b, a, rtol=0, atol=1e-6)
+    assert (tmp_path / "3.wav").exists()
+    # first utterance is the committed reference fixture's mel, but under seed 99 -> only sanity here
+    assert all(np.isfinite(w).all() and np.abs(w).max() <= 1.0 for w in many)

@@ -16,7 +16,7 @@ WRNN_OK, WRNN_E_INVALID, WRNN_E_CUDA, WRNN_E_NO_DEVICE, WRNN_E_WATCHDOG, WRNN_E_
 MODE_MOL, MODE_RAW = 0, 1
 PREC_F16, PREC_FP32, PREC_BF16 = 0, 1, 2
 ENGINE_AUTO, ENGINE_SIMT, ENGINE_TCGEN05 = 0, 1, 2
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 EXPORTS = ("wrnn_abi_version", "wrnn_last_error", "wrnn_create", "wrnn_destroy", "wrnn_generate",
            "wrnn_check", "wrnn_generate_host", "wrnn_engine_name", "wrnn_grid_ctas", "wrnn_launch_count")
@@ -49,7 +49,8 @@ class WrnnJob(C.Structure):
                 ("n_seg", C.c_int32), ("seg_len", C.c_int32), ("seg_first", C.c_int32), ("steps", C.c_int32),
                 ("uniforms", C.c_void_p), ("expo", C.c_void_p),
                 ("philox_seed", C.c_uint64), ("philox_offset", C.c_uint64),
-                ("out", C.c_void_p), ("x_force", C.c_void_p), ("logits_out", C.c_void_p)]
+                ("out", C.c_void_p), ("x_force", C.c_void_p), ("logits_out", C.c_void_p),
+                ("fold_row0", C.c_void_p), ("fold_row_end", C.c_void_p)]
 
 
 _lib = None
@@ -147,10 +148,12 @@ class Engine:
 
     def generate(self, *, mels_up: int, aux: int, L: int, n_seg: int, seg_len: int, seg_stride: int, out: int,
                  seg_first: int = 0, steps: int = 0, uniforms: int = 0, expo: int = 0, philox_seed: int = 0,
-                 philox_offset: int = 0, x_force: int = 0, logits_out: int = 0, stream: int = 0):
+                 philox_offset: int = 0, x_force: int = 0, logits_out: int = 0, fold_row0: int = 0, fold_row_end: int = 0,
+                 stream: int = 0):
         """All buffer arguments are raw device addresses (ints).  Asynchronous."""
         job = WrnnJob(mels_up, aux, L, seg_stride, n_seg, seg_len, seg_first, steps, uniforms or None,
-                      expo or None, philox_seed, philox_offset, out, x_force or None, logits_out or None)
+                      expo or None, philox_seed, philox_offset, out, x_force or None, logits_out or None,
+                      fold_row0 or None, fold_row_end or None)
         _check(self.lib, self.lib.wrnn_generate(self._h, C.byref(job), C.c_void_p(stream or None)))
 
     def check(self):

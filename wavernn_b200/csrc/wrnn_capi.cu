@@ -126,6 +126,7 @@ static int validate(const wrnn_t* h, const wrnn_job* job, bool host) {
     set_error("n_seg, seg_len, L and seg_stride must be positive"); return WRNN_E_INVALID;
   }
   if (job->steps < 0 || job->steps > job->seg_len) { set_error("steps must be in [0, seg_len]"); return WRNN_E_INVALID; }
+  if ((job->fold_row0 == nullptr) != (job->fold_row_end == nullptr)) { set_error("fold_row0 and fold_row_end go together"); return WRNN_E_INVALID; }
   (void)host;
   return WRNN_OK;
 }
@@ -156,7 +157,8 @@ int wrnn_generate_host(wrnn_t* h, const wrnn_job* job) {
   const size_t n_mel = (size_t)job->L * FEAT, n_aux = (size_t)job->L * 4 * AUXD;
   const size_t n_uni = job->uniforms ? S * 11 * B : 0, n_exp = job->expo ? S * B * NC : 0;
   const size_t n_xf = job->x_force ? S * B : 0, n_out = B * S, n_log = job->logits_out ? S * B * NC : 0;
-  const size_t total = (n_mel + n_aux + n_uni + n_exp + n_xf + n_out + n_log) * sizeof(float);
+  const size_t n_tab = job->fold_row0 ? 4 * B : 0;   // two int64 tables, counted in floats
+  const size_t total = (n_mel + n_aux + n_uni + n_exp + n_xf + n_out + n_log + n_tab + 2) * sizeof(float);
   if (total > h->stage_bytes) {
     if (h->d_stage) cudaFree(h->d_stage);
     h->d_stage = nullptr; h->stage_bytes = 0;
@@ -174,7 +176,14 @@ int wrnn_generate_host(wrnn_t* h, const wrnn_job* job) {
   dj.mels_up = up(job->mels_up, n_mel); dj.aux = up(job->aux, n_aux);
   dj.uniforms = up(job->uniforms, n_uni); dj.expo = up(job->expo, n_exp); dj.x_force = up(job->x_force, n_xf);
   dj.out = d; d += n_out;
-  dj.logits_out = n_log ? d : nullptr;
+  dj.logits_out = n_log ? d : nullptr; d += n_log;
+  if (n_tab) {
+    d = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(d) + 7) & ~uintptr_t(7));
+    int64_t* t0 = reinterpret_cast<int64_t*>(d);
+    cudaMemcpyAsync(t0, job->fold_row0, B * 8, cudaMemcpyHostToDevice, 0);
+    cudaMemcpyAsync(t0 + B, job->fold_row_end, B * 8, cudaMemcpyHostToDevice, 0);
+    dj.fold_row0 = t0; dj.fold_row_end = t0 + B;
+  }
   rc = e->generate(dj, 0);
   if (rc != WRNN_OK) return rc;
   WRNN_CUDA_OK(cudaMemcpyAsync(job->out, dj.out, n_out * sizeof(float), cudaMemcpyDeviceToHost, 0));

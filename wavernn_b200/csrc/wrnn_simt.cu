@@ -52,6 +52,7 @@ struct SimtParams {
   int n_seg, seg_len, seg_first, steps, Bp, out_pitch, n_classes, mode;
   const float* uniforms; const float* expo; unsigned long long seed, offset;
   float* out; const float* x_force; float* logits_out;
+  const long long* fold_row0; const long long* fold_row_end;
   float* xch;      // 4 x [H][Bp]: h1', h2', y1, y2
   float* xs;       // [Bp] previous sample per fold
   float* state;    // [P][NSTATE][Bp]
@@ -166,9 +167,10 @@ __global__ void __launch_bounds__(NT, 1) wrnn_simt_kernel(const SimtParams p) {
       const int b0 = tile * FT;
       for (int idx = tid; idx < CDIM * FT; idx += NT) {
         const int c = idx % CDIM, f = idx / CDIM, b = b0 + f;
-        const long long row = (long long)b * p.seg_stride + t;
+        long long row = (long long)b * p.seg_stride + t, row_end = p.L;
+        if (p.fold_row0 && b < B) { row = __ldg(p.fold_row0 + b) + t; row_end = __ldg(p.fold_row_end + b); }
         float v = 0.f;
-        if (b < B && row < p.L) v = (c < FEAT) ? __ldg(p.mels_up + row * FEAT + c) : __ldg(p.aux + row * (4 * AUXD) + (c - FEAT));
+        if (b < B && row < row_end) v = (c < FEAT) ? __ldg(p.mels_up + row * FEAT + c) : __ldg(p.aux + row * (4 * AUXD) + (c - FEAT));
         act[c * AP + f] = rnd(v);
       }
       __syncthreads();
@@ -458,6 +460,7 @@ class SimtEngine : public Engine {
     p.n_classes = cfg.n_classes; p.mode = cfg.mode;
     p.uniforms = job.uniforms; p.expo = job.expo; p.seed = job.philox_seed; p.offset = job.philox_offset;
     p.out = job.out; p.x_force = job.x_force; p.logits_out = job.logits_out;
+    p.fold_row0 = reinterpret_cast<const long long*>(job.fold_row0); p.fold_row_end = reinterpret_cast<const long long*>(job.fold_row_end);
     float* s = static_cast<float*>(d_scratch_);
     p.xch = s; s += (size_t)4 * H * Bp;
     p.xs = s; s += Bp;

@@ -88,6 +88,7 @@ struct TcParams {
   int f0, n_total;                         // first fold of the tile / folds of the whole job (indexing of the job-wide arrays)
   const float* uniforms; unsigned long long seed, offset;
   float* out; const float* x_force; float* logits_out;
+  const long long* fold_row0; const long long* fold_row_end;   // optional per-fold conditioning windows (job-wide, [n_total])
   unsigned char* xch;        // [4 vectors][2 parities][n_groups * SBO_H] activation images
   unsigned* counters;        // [4] monotonically increasing arrival counters
   int* abort_flag;
@@ -346,6 +347,9 @@ __global__ void __launch_bounds__(NT, 1) wrnn_tc_kernel(const TcParams p) {
     const int n_tasks = B * KQ;
     const bool deferred = n_tasks <= COND_TASKS * 128;     // n_seg <= 24: loads fly a whole step before use
     float4 creg[COND_TASKS][2];
+    // conditioning window of fold f of this tile: the strided fold, or the caller's tables (several utterances in one job)
+    auto row0_of = [&](int f) -> long long { return p.fold_row0 ? __ldg(p.fold_row0 + p.f0 + f) : (long long)(p.f0 + f) * p.seg_stride; };
+    auto end_of = [&](int f) -> long long { return p.fold_row_end ? __ldg(p.fold_row_end + p.f0 + f) : p.L; };
     auto src_of = [&](int c8, long long row) -> const float4* {
       const float* s = (c8 < FEAT / 8) ? p.mels_up + row * FEAT + c8 * 8 : p.aux + row * (4 * AUXD) + (c8 - FEAT / 8) * 8;
       return reinterpret_cast<const float4*>(s);
@@ -363,8 +367,8 @@ __global__ void __launch_bounds__(NT, 1) wrnn_tc_kernel(const TcParams p) {
         creg[j][0] = make_float4(0.f, 0.f, 0.f, 0.f); creg[j][1] = creg[j][0];
         if (task < n_tasks) {
           const int f = task / KQ, c8 = task % KQ;
-          const long long row = (long long)(p.f0 + f) * p.seg_stride + n;
-          if (row < p.L) { const float4* s = src_of(c8, row); creg[j][0] = __ldg(s); creg[j][1] = __ldg(s + 1); }
+          const long long row = row0_of(f) + n;
+          if (row < end_of(f)) { const float4* s = src_of(c8, row); creg[j][0] = __ldg(s); creg[j][1] = __ldg(s + 1); }
         }
       }
     };
@@ -378,9 +382,9 @@ __global__ void __launch_bounds__(NT, 1) wrnn_tc_kernel(const TcParams p) {
       } else {
         for (int task = st; task < n_tasks; task += 128) {
           const int f = task / KQ, c8 = task % KQ;
-          const long long row = (long long)(p.f0 + f) * p.seg_stride + n;
+          const long long row = row0_of(f) + n;
           float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
-          if (row < p.L) { const float4* s = src_of(c8, row); a = __ldg(s); b = __ldg(s + 1); }
+          if (row < end_of(f)) { const float4* s = src_of(c8, row); a = __ldg(s); b = __ldg(s + 1); }
           store_task(f, c8, a, b);
         }
       }
@@ -489,6 +493,7 @@ class TcEngine : public Engine {
     p.seg_first = job.seg_first;
     p.uniforms = job.uniforms; p.seed = job.philox_seed; p.offset = job.philox_offset;
     p.out = job.out; p.x_force = job.x_force; p.logits_out = job.logits_out;
+    p.fold_row0 = reinterpret_cast<const long long*>(job.fold_row0); p.fold_row_end = reinterpret_cast<const long long*>(job.fold_row_end);
     p.xch = static_cast<unsigned char*>(d_scratch_);
     p.counters = static_cast<unsigned*>(d_sync_);
     p.abort_flag = reinterpret_cast<int*>(static_cast<unsigned*>(d_sync_) + 8);

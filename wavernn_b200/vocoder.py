@@ -353,9 +353,69 @@ class WaveRNN(nn.Module):
         return output
 
     def generate_many(self, mels_list: Sequence, save_paths: Sequence, target, overlap, mu_law):
-        """Extension: vocode several utterances; each keeps the exact
-        per-utterance result of generate(..., batched=True, ...)."""
-        return [self.generate(m, p, True, target, overlap, mu_law) for m, p in zip(mels_list, save_paths)]
+        """Extension: vocode several utterances in ONE job.  The reference vocodes sentences one
+        at a time (gen_tacotron.py:139-163); here the folds of all utterances share the persistent kernel's
+        tiles -- a step costs the same for 1 or 64 folds, so k short utterances cost about one.
+        Returns the list of waveforms; each is exactly what `generate(m, path, True, target, overlap, mu_law)`
+        returns when the calls are made one after the other under the same torch seed (the per-utterance RNG
+        draws are made in that order)."""
+        device = self._require_cuda()
+        dist_on = torch.distributed.is_available() and torch.distributed.is_initialized()
+        if (dist_on and torch.distributed.get_world_size() > 1) or self.mode != 'MOL' or len(mels_list) == 0:
+            # multi-rank jobs shard each utterance's folds; the RAW head is served fold-strided: one call each
+            return [self.generate(m, p, True, target, overlap, mu_law) for m, p in zip(mels_list, save_paths)]
+        t_start = time.time()
+        self.eval()
+        hop = self.hop_length
+        geos, wave_lens, streams_m, streams_a, draws = [], [], [], [], []
+        with torch.no_grad():
+            for m in mels_list:
+                m = torch.as_tensor(m, device=device).float()
+                T = m.size(-1)
+                geo = fold_geometry(T * hop, target, overlap)
+                geos.append(geo); wave_lens.append((T - 1) * hop)
+                m_up, aux = self.conditioning(F.pad(m, (self.pad, self.pad)), 0, T)
+                streams_m.append(m_up); streams_a.append(aux)
+                if self.gen_rng == 'torch':
+                    draws.append(self._reference_draws(geo, geo.seg_len)[0])     # same order as sequential generate() calls
+            S, stride = geos[0].seg_len, geos[0].seg_stride
+            B = sum(g.n_seg for g in geos)
+            row0, row_end, base = [], [], 0
+            for g in geos:                                       # utterance streams laid end to end
+                row0 += [base + i * stride for i in range(g.n_seg)]
+                row_end += [base + g.total_len] * g.n_seg
+                base += g.total_len
+            m_all, a_all = torch.cat(streams_m, 0).contiguous(), torch.cat(streams_a, 0).contiguous()
+            t_row0 = torch.tensor(row0, dtype=torch.int64, device=device)
+            t_end = torch.tensor(row_end, dtype=torch.int64, device=device)
+            uniforms = None
+            if self.gen_rng == 'torch':
+                mix = torch.cat([u[:, :10 * g.n_seg] for u, g in zip(draws, geos)], 1)
+                logi = torch.cat([u[:, 10 * g.n_seg:] for u, g in zip(draws, geos)], 1)
+                uniforms = torch.cat([mix, logi], 1).contiguous().to(device, non_blocking=True)
+            elif self.gen_rng != 'philox':
+                raise ValueError(f"gen_rng must be 'torch' or 'philox', got {self.gen_rng!r}")
+            engine = self._get_engine(device)
+            out = torch.empty((B, S), dtype=torch.float32, device=device)
+            engine.generate(mels_up=m_all.data_ptr(), aux=a_all.data_ptr(), L=m_all.shape[0], n_seg=B, seg_len=S,
+                            seg_stride=stride, out=out.data_ptr(),
+                            uniforms=uniforms.data_ptr() if uniforms is not None else 0,
+                            philox_seed=int(self.gen_philox_seed), fold_row0=t_row0.data_ptr(),
+                            fold_row_end=t_end.data_ptr(), stream=torch.cuda.current_stream(device).cuda_stream)
+            torch.cuda.current_stream(device).synchronize()
+            engine.check()
+            samples = out.cpu().numpy().astype(np.float64)
+        wavs, f0 = [], 0
+        for g, wl, path in zip(geos, wave_lens, save_paths):
+            wav = self._epilogue(samples[f0:f0 + g.n_seg].copy(), g, True, wl, False)
+            f0 += g.n_seg
+            if path is not None:
+                save_wav(wav, path, self.sample_rate)
+            wavs.append(wav)
+        self.train()
+        self.gen_stats.update(wall_s=time.time() - t_start, n_seg=B, seg_len=S, engine=engine.name,
+                              launches=engine.launch_count, utterances=len(geos))
+        return wavs
 
     # ------------------------------------------------------------------ reference helpers kept for callers
     def gen_display(self, i, seq_len, b_size, start):
