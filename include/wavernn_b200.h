@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define WRNN_ABI_VERSION 2
+#define WRNN_ABI_VERSION 3
 
 enum {
   WRNN_OK = 0,
@@ -119,6 +119,18 @@ typedef struct {
    * (WaveRNN.generate_many; the reference vocodes sentences one at a time, gen_tacotron.py:139-163). */
   const int64_t *fold_row0;
   const int64_t *fold_row_end;
+  /* Optional frame-rate conditioning (device; tcgen05 engine).  When mel_frames != NULL the kernel builds each
+   * conditioning row itself and mels_up / aux are ignored (may be NULL; L stays the stream length in samples):
+   *   aux row n  = aux_frames[n / hop]                      (Stretch2d is a nearest-neighbour repeat, :57-61)
+   *   mel row n  = sum_{d<5} up_taps[n % hop][d] * mel_frames[n / hop + d]
+   * mel_frames [T + 2*pad, feat] is the zero-padded mel, aux_frames [T, 4*aux] the MelResNet output, and
+   * up_taps [hop, 5] the composed impulse response of the three stretch+conv stages of UpsampleNetwork
+   * (fatchord_version.py:73-88), exact for every output sample that survives the `indent` crop.             */
+  const float *mel_frames;
+  const float *aux_frames;
+  const float *up_taps;
+  int32_t hop;
+  int32_t reserved0;
 } wrnn_job;
 
 int wrnn_abi_version(void);

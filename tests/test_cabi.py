@@ -27,13 +27,13 @@ def test_header_symbols_are_exported(lib):
     assert declared == set(cabi.EXPORTS), declared ^ set(cabi.EXPORTS)
     for sym in declared:
         assert getattr(lib, sym) is not None
-    assert lib.wrnn_abi_version() == 2
+    assert lib.wrnn_abi_version() == 3
 
 
 def test_struct_layouts_match_header():
     assert ctypes.sizeof(cabi.WrnnCfg) == 8 * 4
     assert ctypes.sizeof(cabi.WrnnWeights) == 16 * ctypes.sizeof(ctypes.c_void_p)
-    assert ctypes.sizeof(cabi.WrnnJob) == 8 * 4 + 4 * 4 + 2 * 8 + 2 * 8 + 3 * 8 + 2 * 8
+    assert ctypes.sizeof(cabi.WrnnJob) == 8 * 4 + 4 * 4 + 2 * 8 + 2 * 8 + 3 * 8 + 2 * 8 + 3 * 8 + 2 * 4
     assert cabi.WrnnJob.seg_first.offset == 40 and cabi.WrnnJob.uniforms.offset == 48 and cabi.WrnnJob.out.offset == 80
 
 

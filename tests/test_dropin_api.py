@@ -116,3 +116,27 @@ def test_public_surface_matches_reference_class():
         b = inspect.signature(getattr(W.WaveRNN, name))
         assert list(a.parameters) == list(b.parameters), name
     assert list(inspect.signature(ref.WaveRNN.__init__).parameters) == list(inspect.signature(W.WaveRNN.__init__).parameters)
+
+
+def test_upsample_taps_reproduce_the_interpolation_cascade():
+    """The 5-tap-per-phase table the kernel uses for in-kernel conditioning == UpsampleNetwork's stretch+conv cascade
+    (reference fatchord_version.py:73-88), for freshly initialised and for perturbed (as-if-trained) conv weights."""
+    m = helpers.make_model(0, "MOL").eval()
+    for perturb in (False, True):
+        if perturb:
+            with torch.no_grad():
+                for layer in m.upsample.up_layers:
+                    if hasattr(layer, "weight"):
+                        layer.weight.mul_(0.9).add_(0.01 * torch.randn_like(layer.weight))
+        taps = m.upsample_taps(torch.device("cpu")).numpy().astype(np.float64)
+        assert taps.shape == (275, 5) and (np.abs(taps) > 0).sum(1).max() <= 4
+        T = 37
+        mp = torch.nn.functional.pad(helpers.make_mel(T, 2), (2, 2))
+        with torch.no_grad():
+            full_m, full_a = m.upsample(mp)
+            aux_fr = m.upsample.resnet(mp)[0].T.numpy()
+        xp = mp[0].T.numpy().astype(np.float64)
+        n = np.arange(T * 275)
+        rec = sum(taps[n % 275, d][:, None] * xp[n // 275 + d] for d in range(5))
+        np.testing.assert_allclose(rec, full_m[0].numpy(), atol=2e-6)
+        np.testing.assert_array_equal(np.repeat(aux_fr, 275, 0), full_a[0].numpy())

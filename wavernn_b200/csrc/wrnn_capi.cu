@@ -121,7 +121,12 @@ void wrnn_destroy(wrnn_t* h) {
 
 static int validate(const wrnn_t* h, const wrnn_job* job, bool host) {
   if (!h || !h->engine || !job) { set_error("null handle or job"); return WRNN_E_INVALID; }
-  if (!job->mels_up || !job->aux || !job->out) { set_error("mels_up, aux and out are required"); return WRNN_E_INVALID; }
+  if (!job->out) { set_error("out is required"); return WRNN_E_INVALID; }
+  if (job->mel_frames) {
+    if (!job->aux_frames || !job->up_taps || job->hop <= 0) { set_error("mel_frames needs aux_frames, up_taps and hop"); return WRNN_E_INVALID; }
+    if (host) { set_error("frame-rate conditioning is a device-pointer feature (use wrnn_generate)"); return WRNN_E_INVALID; }
+    if (job->L >= (1ll << 31)) { set_error("frame-rate conditioning: stream longer than 2^31 samples"); return WRNN_E_INVALID; }
+  } else if (!job->mels_up || !job->aux) { set_error("mels_up and aux (or mel_frames / aux_frames / up_taps) are required"); return WRNN_E_INVALID; }
   if (job->n_seg <= 0 || job->seg_len <= 0 || job->L <= 0 || job->seg_stride <= 0) {
     set_error("n_seg, seg_len, L and seg_stride must be positive"); return WRNN_E_INVALID;
   }

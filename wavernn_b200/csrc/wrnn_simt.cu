@@ -439,7 +439,10 @@ class SimtEngine : public Engine {
     return WRNN_OK;
   }
 
+  bool supports(const wrnn_job& job) const override { return job.mel_frames == nullptr; }   // upsampled streams only
+
   int generate(const wrnn_job& job, cudaStream_t stream) override {
+    if (job.mel_frames) { set_error("the SIMT engine takes the upsampled conditioning streams (mels_up / aux)"); return WRNN_E_INVALID; }
     WRNN_CUDA_OK(cudaSetDevice(device));
     const int Bp = (job.n_seg + FT - 1) / FT * FT;
     const size_t need = ((size_t)4 * H * Bp + Bp + (size_t)P * NSTATE * Bp + (size_t)cfg.n_classes * Bp) * sizeof(float);

@@ -89,6 +89,7 @@ struct TcParams {
   const float* uniforms; unsigned long long seed, offset;
   float* out; const float* x_force; float* logits_out;
   const long long* fold_row0; const long long* fold_row_end;   // optional per-fold conditioning windows (job-wide, [n_total])
+  const float* mel_frames; const float* aux_frames; const float* up_taps; int hop;   // optional frame-rate conditioning
   unsigned char* xch;        // [4 vectors][2 parities][n_groups * SBO_H] activation images
   unsigned* counters;        // [4] monotonically increasing arrival counters
   int* abort_flag;
@@ -354,6 +355,29 @@ __global__ void __launch_bounds__(NT, 1) wrnn_tc_kernel(const TcParams p) {
       const float* s = (c8 < FEAT / 8) ? p.mels_up + row * FEAT + c8 * 8 : p.aux + row * (4 * AUXD) + (c8 - FEAT / 8) * 8;
       return reinterpret_cast<const float4*>(s);
     };
+    // the 8 conditioning values (fold f, columns 8*c8 .. 8*c8+7) of step n: from the upsampled streams, or built here
+    // from frame-rate tensors (UpsampleNetwork's stretch+conv cascade collapsed into 5 taps per output phase)
+    auto cond_chunk = [&](int f, int c8, int n, float4& a, float4& b) {
+      a = make_float4(0.f, 0.f, 0.f, 0.f); b = a;
+      const long long row = row0_of(f) + n;
+      if (row >= end_of(f)) return;
+      if (!p.mel_frames) { const float4* s = src_of(c8, row); a = __ldg(s); b = __ldg(s + 1); return; }
+      const unsigned r = (unsigned)row, frame = r / (unsigned)p.hop, phase = r - frame * (unsigned)p.hop;
+      if (c8 >= FEAT / 8) {
+        const float4* s = reinterpret_cast<const float4*>(p.aux_frames + (size_t)frame * (4 * AUXD) + (c8 - FEAT / 8) * 8);
+        a = __ldg(s); b = __ldg(s + 1);
+        return;
+      }
+      const float* k = p.up_taps + phase * 5;
+#pragma unroll
+      for (int d = 0; d < 5; ++d) {
+        const float wgt = __ldg(k + d);
+        const float4* s = reinterpret_cast<const float4*>(p.mel_frames + (size_t)(frame + d) * FEAT + c8 * 8);
+        const float4 x0 = __ldg(s), x1 = __ldg(s + 1);
+        a.x = fmaf(wgt, x0.x, a.x); a.y = fmaf(wgt, x0.y, a.y); a.z = fmaf(wgt, x0.z, a.z); a.w = fmaf(wgt, x0.w, a.w);
+        b.x = fmaf(wgt, x1.x, b.x); b.y = fmaf(wgt, x1.y, b.y); b.z = fmaf(wgt, x1.z, b.z); b.w = fmaf(wgt, x1.w, b.w);
+      }
+    };
     auto store_task = [&](int f, int c8, const float4& a, const float4& b) {
       uint4 v;
       v.x = pack2<FMT>(a.x, a.y); v.y = pack2<FMT>(a.z, a.w); v.z = pack2<FMT>(b.x, b.y); v.w = pack2<FMT>(b.z, b.w);
@@ -366,9 +390,7 @@ __global__ void __launch_bounds__(NT, 1) wrnn_tc_kernel(const TcParams p) {
         const int task = st + j * 128;
         creg[j][0] = make_float4(0.f, 0.f, 0.f, 0.f); creg[j][1] = creg[j][0];
         if (task < n_tasks) {
-          const int f = task / KQ, c8 = task % KQ;
-          const long long row = row0_of(f) + n;
-          if (row < end_of(f)) { const float4* s = src_of(c8, row); creg[j][0] = __ldg(s); creg[j][1] = __ldg(s + 1); }
+          cond_chunk(task / KQ, task % KQ, n, creg[j][0], creg[j][1]);
         }
       }
     };
@@ -382,9 +404,8 @@ __global__ void __launch_bounds__(NT, 1) wrnn_tc_kernel(const TcParams p) {
       } else {
         for (int task = st; task < n_tasks; task += 128) {
           const int f = task / KQ, c8 = task % KQ;
-          const long long row = row0_of(f) + n;
-          float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
-          if (row < end_of(f)) { const float4* s = src_of(c8, row); a = __ldg(s); b = __ldg(s + 1); }
+          float4 a, b;
+          cond_chunk(f, c8, n, a, b);
           store_task(f, c8, a, b);
         }
       }
@@ -494,6 +515,7 @@ class TcEngine : public Engine {
     p.uniforms = job.uniforms; p.seed = job.philox_seed; p.offset = job.philox_offset;
     p.out = job.out; p.x_force = job.x_force; p.logits_out = job.logits_out;
     p.fold_row0 = reinterpret_cast<const long long*>(job.fold_row0); p.fold_row_end = reinterpret_cast<const long long*>(job.fold_row_end);
+    p.mel_frames = job.mel_frames; p.aux_frames = job.aux_frames; p.up_taps = job.up_taps; p.hop = job.hop;
     p.xch = static_cast<unsigned char*>(d_scratch_);
     p.counters = static_cast<unsigned*>(d_sync_);
     p.abort_flag = reinterpret_cast<int*>(static_cast<unsigned*>(d_sync_) + 8);

@@ -150,6 +150,8 @@ class WaveRNN(nn.Module):
         self.gen_engine = 'auto'        # 'auto' | 'simt' | 'tcgen05'
         self.gen_philox_seed = 0
         self.gen_upsample_chunk = 2048  # mel frames per UpsampleNetwork call (bounds HBM intermediates)
+        self.gen_conditioning = 'kernel'  # 'kernel': frame-rate tensors, rows built inside the kernel (tcgen05 engine)
+        #                                   'torch' : materialise UpsampleNetwork's (T*hop, 208) output like the reference
         self.gen_verbose = True
         self.gen_stats = {}             # filled by generate(): timings, engine name, ...
         self._engine = None
@@ -231,6 +233,31 @@ class WaveRNN(nn.Module):
         m = torch.cat(outs_m, dim=0) if len(outs_m) > 1 else outs_m[0]
         a = torch.cat(outs_a, dim=0) if len(outs_a) > 1 else outs_a[0]
         return m.contiguous().float(), a.contiguous().float()
+
+    def upsample_taps(self, device) -> torch.Tensor:
+        """(hop, 5) fp32: composed impulse response of UpsampleNetwork's three stretch+conv stages (reference
+        :73-80) per output phase -- mel_up[n] = sum_d taps[n % hop][d] * mel_padded[n // hop + d].  Obtained by
+        pushing a unit impulse through the module's own layers (exact for every sample that survives the
+        `indent` crop, :88; checked in tests/test_dropin_api.py).  Cached per weight version."""
+        up = self.upsample
+        key = (str(device),) + tuple((l.weight.data_ptr(), l.weight._version) for l in up.up_layers if hasattr(l, 'weight'))
+        if getattr(self, '_taps_key', None) != key:
+            hop, n_fr, c = up.total_scale, 9, 4
+            x = torch.zeros(1, 1, n_fr, device=device)
+            x[0, 0, c] = 1.0
+            with torch.no_grad():
+                y = up.stretch_mel(x)[0, 0]                                   # impulse at frame c
+            n = torch.arange(n_fr * hop, device=device)
+            d = c - n // hop + 2
+            keep = (d >= 0) & (d < 5)
+            taps = torch.zeros(hop, 5, device=device)
+            taps[(n % hop)[keep], d[keep]] = y[keep]
+            self._taps, self._taps_key = taps.contiguous(), key
+        return self._taps
+
+    def _kernel_conditioning_ok(self) -> bool:
+        return (self.gen_conditioning == 'kernel' and self.mode == 'MOL' and self.gen_precision != 'fp32'
+                and self.gen_engine in ('auto', 'tcgen05'))
 
     # ------------------------------------------------------------------ randomness
     def _reference_draws(self, geo: FoldGeometry, steps: int):
@@ -314,6 +341,29 @@ class WaveRNN(nn.Module):
         if shard.n_seg == 0:
             return torch.zeros((0, S), dtype=torch.float32, device=device)
         engine = self._get_engine(device)
+        out = torch.empty((shard.n_seg, S), dtype=torch.float32, device=device)
+        if self._kernel_conditioning_ok() and x_force is None and not want_logits:
+            # frame-rate conditioning: the kernel builds every (T*hop, 208) row itself from the padded mel, the
+            # MelResNet frames and the 5-tap interpolation table -- nothing of size T*hop is materialised
+            T = mels_padded.size(-1) - 2 * self.pad
+            mel_fr = mels_padded[0].transpose(0, 1).contiguous().float()                  # (T + 2 pad, feat)
+            aux_fr = self.upsample.resnet(mels_padded)[0].transpose(0, 1).contiguous().float()   # (T, 4*aux)
+            taps = self.upsample_taps(device)
+            f = torch.arange(shard.seg_first, shard.seg_first + shard.n_seg, device=device, dtype=torch.int64)
+            row0 = (f * geo.seg_stride).contiguous()
+            row_end = torch.full_like(row0, T * self.hop_length)
+            engine.generate(mels_up=0, aux=0, L=T * self.hop_length, n_seg=shard.n_seg, seg_len=geo.seg_len,
+                            seg_stride=geo.seg_stride, out=out.data_ptr(), seg_first=shard.seg_first, steps=steps,
+                            uniforms=uniforms.data_ptr() if uniforms is not None else 0,
+                            philox_seed=int(self.gen_philox_seed), fold_row0=row0.data_ptr(),
+                            fold_row_end=row_end.data_ptr(), mel_frames=mel_fr.data_ptr(), aux_frames=aux_fr.data_ptr(),
+                            up_taps=taps.data_ptr(), hop=self.hop_length,
+                            stream=torch.cuda.current_stream(device).cuda_stream)
+            torch.cuda.current_stream(device).synchronize()
+            engine.check()
+            self.gen_stats.update(engine=engine.name, grid_ctas=engine.grid_ctas, launches=engine.launch_count,
+                                  conditioning='kernel')
+            return out
         m_up, aux = self.conditioning(mels_padded, shard.frame_lo, shard.frame_hi)
         off = shard.row_lo - shard.frame_lo * self.hop_length
         n_rows = shard.row_hi - shard.row_lo
@@ -321,7 +371,6 @@ class WaveRNN(nn.Module):
         aux = aux[off:off + n_rows]
         if off:
             m_up, aux = m_up.contiguous(), aux.contiguous()
-        out = torch.empty((shard.n_seg, S), dtype=torch.float32, device=device)
         logits = (torch.empty((S, shard.n_seg, self.n_classes), dtype=torch.float32, device=device)
                   if want_logits else None)
         xf = None
@@ -338,7 +387,8 @@ class WaveRNN(nn.Module):
                         stream=torch.cuda.current_stream(device).cuda_stream)
         torch.cuda.current_stream(device).synchronize()
         engine.check()
-        self.gen_stats.update(engine=engine.name, grid_ctas=engine.grid_ctas, launches=engine.launch_count)
+        self.gen_stats.update(engine=engine.name, grid_ctas=engine.grid_ctas, launches=engine.launch_count,
+                              conditioning='torch')
         del m_up, aux, uniforms, expo, xf
         return (out, logits) if want_logits else out
 
