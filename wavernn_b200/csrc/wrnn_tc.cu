@@ -99,7 +99,7 @@ struct TcParams {
 // ------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------
-template <int FMT>
+template <int FMT, bool FRAMES>
 __global__ void __launch_bounds__(NT, 1) wrnn_tc_kernel(const TcParams p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const float* fv = reinterpret_cast<const float*>(smem + OFF_VEC);
@@ -361,7 +361,7 @@ __global__ void __launch_bounds__(NT, 1) wrnn_tc_kernel(const TcParams p) {
       a = make_float4(0.f, 0.f, 0.f, 0.f); b = a;
       const long long row = row0_of(f) + n;
       if (row >= end_of(f)) return;
-      if (!p.mel_frames) { const float4* s = src_of(c8, row); a = __ldg(s); b = __ldg(s + 1); return; }
+      if constexpr (!FRAMES) { const float4* s = src_of(c8, row); a = __ldg(s); b = __ldg(s + 1); return; }
       const unsigned r = (unsigned)row, frame = r / (unsigned)p.hop, phase = r - frame * (unsigned)p.hop;
       if (c8 >= FEAT / 8) {
         const float4* s = reinterpret_cast<const float4*>(p.aux_frames + (size_t)frame * (4 * AUXD) + (c8 - FEAT / 8) * 8);
@@ -383,15 +383,51 @@ __global__ void __launch_bounds__(NT, 1) wrnn_tc_kernel(const TcParams p) {
       v.x = pack2<FMT>(a.x, a.y); v.y = pack2<FMT>(a.z, a.w); v.z = pack2<FMT>(b.x, b.y); v.w = pack2<FMT>(b.z, b.w);
       *reinterpret_cast<uint4*>(smem + OFF_COND + (f >> 3) * SBO_Q + c8 * 128 + (f & 7) * 16) = v;
     };
+    // The (fold, chunk) tasks of a staging thread are the same for the whole launch: hoist everything that does not
+    // depend on the step.  In FRAMES mode (frame, phase) of the next row are advanced incrementally -- cond_fetch is
+    // called for n = 0, 1, 2, ... in order -- so the step loop has no division.
+    int tk_c8[COND_TASKS]; long long tk_left[COND_TASKS];           // rows left in the fold's window: row n exists iff n < left
+    const float* tk_src[COND_TASKS]; unsigned tk_frame[COND_TASKS], tk_phase[COND_TASKS];
+#pragma unroll
+    for (int j = 0; j < COND_TASKS; ++j) {
+      const int task = st + j * 128;
+      tk_c8[j] = -1; tk_left[j] = 0; tk_src[j] = nullptr; tk_frame[j] = 0; tk_phase[j] = 0;
+      if (deferred && task < n_tasks) {
+        const int f = task / KQ, c8 = task % KQ;
+        const long long r0 = row0_of(f);
+        tk_c8[j] = c8; tk_left[j] = end_of(f) - r0;
+        if constexpr (FRAMES) { tk_frame[j] = (unsigned)r0 / (unsigned)p.hop; tk_phase[j] = (unsigned)r0 - tk_frame[j] * (unsigned)p.hop; }
+        else tk_src[j] = (c8 < FEAT / 8) ? p.mels_up + r0 * FEAT + c8 * 8 : p.aux + r0 * (4 * AUXD) + (c8 - FEAT / 8) * 8;
+      }
+    }
     auto cond_fetch = [&](int n) {
       if (!deferred) return;
 #pragma unroll
       for (int j = 0; j < COND_TASKS; ++j) {
-        const int task = st + j * 128;
         creg[j][0] = make_float4(0.f, 0.f, 0.f, 0.f); creg[j][1] = creg[j][0];
-        if (task < n_tasks) {
-          cond_chunk(task / KQ, task % KQ, n, creg[j][0], creg[j][1]);
+        const int c8 = tk_c8[j];
+        if (c8 >= 0 && n < tk_left[j]) {
+          if constexpr (!FRAMES) {
+            const float4* s = reinterpret_cast<const float4*>(tk_src[j] + (size_t)n * (c8 < FEAT / 8 ? FEAT : 4 * AUXD));
+            creg[j][0] = __ldg(s); creg[j][1] = __ldg(s + 1);
+          } else if (c8 >= FEAT / 8) {
+            const float4* s = reinterpret_cast<const float4*>(p.aux_frames + (size_t)tk_frame[j] * (4 * AUXD) + (c8 - FEAT / 8) * 8);
+            creg[j][0] = __ldg(s); creg[j][1] = __ldg(s + 1);
+          } else {
+            const float* k = p.up_taps + tk_phase[j] * 5;
+            const float* m = p.mel_frames + (size_t)tk_frame[j] * FEAT + c8 * 8;
+            float4 a = creg[j][0], b = creg[j][1];
+#pragma unroll
+            for (int d = 0; d < 5; ++d) {
+              const float wgt = __ldg(k + d);
+              const float4 x0 = __ldg(reinterpret_cast<const float4*>(m + d * FEAT)), x1 = __ldg(reinterpret_cast<const float4*>(m + d * FEAT) + 1);
+              a.x = fmaf(wgt, x0.x, a.x); a.y = fmaf(wgt, x0.y, a.y); a.z = fmaf(wgt, x0.z, a.z); a.w = fmaf(wgt, x0.w, a.w);
+              b.x = fmaf(wgt, x1.x, b.x); b.y = fmaf(wgt, x1.y, b.y); b.z = fmaf(wgt, x1.z, b.z); b.w = fmaf(wgt, x1.w, b.w);
+            }
+            creg[j][0] = a; creg[j][1] = b;
+          }
         }
+        if constexpr (FRAMES) { if (++tk_phase[j] == (unsigned)p.hop) { tk_phase[j] = 0; ++tk_frame[j]; } }
       }
     };
     auto cond_store = [&](int n) {
@@ -460,7 +496,11 @@ class TcEngine : public Engine {
   }
   const char* name() const override { return cfg.precision == WRNN_PREC_BF16 ? "tcgen05-bf16" : "tcgen05-fp16"; }
   int grid_ctas() const override { return P; }
-  const void* kernel() const { return cfg.precision == WRNN_PREC_BF16 ? (const void*)wrnn_tc_kernel<1> : (const void*)wrnn_tc_kernel<0>; }
+  // FRAMES = conditioning rows built in the kernel from frame-rate tensors (wrnn_job::mel_frames)
+  const void* kernel(bool frames) const {
+    if (cfg.precision == WRNN_PREC_BF16) return frames ? (const void*)wrnn_tc_kernel<1, true> : (const void*)wrnn_tc_kernel<1, false>;
+    return frames ? (const void*)wrnn_tc_kernel<0, true> : (const void*)wrnn_tc_kernel<0, false>;
+  }
 
   int init(const HostWeights& w) {
     Folded f; fold(w, f);
@@ -495,7 +535,8 @@ class TcEngine : public Engine {
     WRNN_CUDA_OK(cudaMemset(d_sync_, 0, 256));
     scratch_bytes_ = (size_t)4 * 2 * 8 * SBO_H;          // 4 vectors x 2 parities x (up to 8 row groups)
     WRNN_CUDA_OK(cudaMalloc(&d_scratch_, scratch_bytes_));
-    WRNN_CUDA_OK(cudaFuncSetAttribute(kernel(), cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    WRNN_CUDA_OK(cudaFuncSetAttribute(kernel(false), cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    WRNN_CUDA_OK(cudaFuncSetAttribute(kernel(true), cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     int n_sm = 0;
     WRNN_CUDA_OK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device));
     if (n_sm < P) { set_error("tcgen05 engine needs >= 128 SMs for its co-resident weight shards"); return WRNN_E_NO_DEVICE; }
@@ -529,7 +570,7 @@ class TcEngine : public Engine {
       p.n_seg = job.n_seg - f0 < MT ? job.n_seg - f0 : MT;
       WRNN_CUDA_OK(cudaMemsetAsync(d_sync_, 0, 32, stream));                       // arrival counters (the abort flag is sticky)
       void* args[] = {&p};
-      WRNN_CUDA_OK(cudaLaunchCooperativeKernel(kernel(), dim3(P), dim3(NT), args, SMEM_BYTES, stream));
+      WRNN_CUDA_OK(cudaLaunchCooperativeKernel(kernel(job.mel_frames != nullptr), dim3(P), dim3(NT), args, SMEM_BYTES, stream));
       ++launches;
     }
     last_steps_ = p.steps;

@@ -418,14 +418,20 @@ class WaveRNN(nn.Module):
         self.eval()
         hop = self.hop_length
         geos, wave_lens, streams_m, streams_a, draws = [], [], [], [], []
+        frames = self._kernel_conditioning_ok()          # same conditioning path as generate() -> identical samples
         with torch.no_grad():
             for m in mels_list:
                 m = torch.as_tensor(m, device=device).float()
                 T = m.size(-1)
                 geo = fold_geometry(T * hop, target, overlap)
                 geos.append(geo); wave_lens.append((T - 1) * hop)
-                m_up, aux = self.conditioning(F.pad(m, (self.pad, self.pad)), 0, T)
-                streams_m.append(m_up); streams_a.append(aux)
+                mp = F.pad(m, (self.pad, self.pad))
+                if frames:       # frame-rate tensors, T + 2*pad rows each so mel and aux share one frame index
+                    streams_m.append(mp[0].transpose(0, 1).float())
+                    streams_a.append(F.pad(self.upsample.resnet(mp)[0].transpose(0, 1).float(), (0, 0, 0, 2 * self.pad)))
+                else:
+                    m_up, aux = self.conditioning(mp, 0, T)
+                    streams_m.append(m_up); streams_a.append(aux)
                 if self.gen_rng == 'torch':
                     draws.append(self._reference_draws(geo, geo.seg_len)[0])     # same order as sequential generate() calls
             S, stride = geos[0].seg_len, geos[0].seg_stride
@@ -434,7 +440,7 @@ class WaveRNN(nn.Module):
             for g in geos:                                       # utterance streams laid end to end
                 row0 += [base + i * stride for i in range(g.n_seg)]
                 row_end += [base + g.total_len] * g.n_seg
-                base += g.total_len
+                base += g.total_len + (2 * self.pad * hop if frames else 0)
             m_all, a_all = torch.cat(streams_m, 0).contiguous(), torch.cat(streams_a, 0).contiguous()
             t_row0 = torch.tensor(row0, dtype=torch.int64, device=device)
             t_end = torch.tensor(row_end, dtype=torch.int64, device=device)
@@ -447,11 +453,13 @@ class WaveRNN(nn.Module):
                 raise ValueError(f"gen_rng must be 'torch' or 'philox', got {self.gen_rng!r}")
             engine = self._get_engine(device)
             out = torch.empty((B, S), dtype=torch.float32, device=device)
-            engine.generate(mels_up=m_all.data_ptr(), aux=a_all.data_ptr(), L=m_all.shape[0], n_seg=B, seg_len=S,
-                            seg_stride=stride, out=out.data_ptr(),
+            cond = (dict(mels_up=0, aux=0, mel_frames=m_all.data_ptr(), aux_frames=a_all.data_ptr(),
+                         up_taps=self.upsample_taps(device).data_ptr(), hop=hop) if frames
+                    else dict(mels_up=m_all.data_ptr(), aux=a_all.data_ptr()))
+            engine.generate(L=base, n_seg=B, seg_len=S, seg_stride=stride, out=out.data_ptr(),
                             uniforms=uniforms.data_ptr() if uniforms is not None else 0,
                             philox_seed=int(self.gen_philox_seed), fold_row0=t_row0.data_ptr(),
-                            fold_row_end=t_end.data_ptr(), stream=torch.cuda.current_stream(device).cuda_stream)
+                            fold_row_end=t_end.data_ptr(), stream=torch.cuda.current_stream(device).cuda_stream, **cond)
             torch.cuda.current_stream(device).synchronize()
             engine.check()
             samples = out.cpu().numpy().astype(np.float64)
