@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define WRNN_ABI_VERSION 3
+#define WRNN_ABI_VERSION 4
 
 enum {
   WRNN_OK = 0,
@@ -51,6 +51,9 @@ enum { WRNN_PREC_F16 = 0, WRNN_PREC_FP32 = 1, WRNN_PREC_BF16 = 2 };
 
 /* Which kernel family executes the job.  AUTO picks the fastest that supports it. */
 enum { WRNN_ENGINE_AUTO = 0, WRNN_ENGINE_SIMT = 1, WRNN_ENGINE_TCGEN05 = 2 };
+
+/* Where frame-rate conditioning (wrnn_job::mel_frames) is turned into per-sample rows. */
+enum { WRNN_COND_AUTO = 0, WRNN_COND_EXPAND = 1, WRNN_COND_IN_KERNEL = 2 };
 
 typedef struct wrnn_handle wrnn_t;
 
@@ -119,18 +122,25 @@ typedef struct {
    * (WaveRNN.generate_many; the reference vocodes sentences one at a time, gen_tacotron.py:139-163). */
   const int64_t *fold_row0;
   const int64_t *fold_row_end;
-  /* Optional frame-rate conditioning (device; tcgen05 engine).  When mel_frames != NULL the kernel builds each
-   * conditioning row itself and mels_up / aux are ignored (may be NULL; L stays the stream length in samples):
+  /* Optional frame-rate conditioning (device; tcgen05 engine).  When mel_frames != NULL the library builds the
+   * conditioning rows itself and mels_up / aux are ignored (may be NULL; L stays the stream length in samples):
    *   aux row n  = aux_frames[n / hop]                      (Stretch2d is a nearest-neighbour repeat, :57-61)
    *   mel row n  = sum_{d<5} up_taps[n % hop][d] * mel_frames[n / hop + d]
    * mel_frames [T + 2*pad, feat] is the zero-padded mel, aux_frames [T, 4*aux] the MelResNet output, and
    * up_taps [hop, 5] the composed impulse response of the three stretch+conv stages of UpsampleNetwork
-   * (fatchord_version.py:73-88), exact for every output sample that survives the `indent` crop.             */
+   * (fatchord_version.py:73-88), exact for every output sample that survives the `indent` crop.
+   * The frame tensors always describe the WHOLE stream: without fold tables, fold b reads rows
+   * (seg_first + b)*seg_stride + t  (so a rank's shard passes the same tensors and its seg_first).
+   * cond_mode picks where the rows are formed (same arithmetic, bit-identical samples):
+   *   WRNN_COND_AUTO     : EXPAND when the job has no fold tables, else IN_KERNEL
+   *   WRNN_COND_EXPAND   : an HBM-rate pre-pass writes each 64-fold tile's rows to engine scratch
+   *                        (<= 64*seg_stride*832 B) just before that tile's persistent launch
+   *   WRNN_COND_IN_KERNEL: the persistent kernel's staging warps form the rows step by step (no scratch) */
   const float *mel_frames;
   const float *aux_frames;
   const float *up_taps;
   int32_t hop;
-  int32_t reserved0;
+  int32_t cond_mode;
 } wrnn_job;
 
 int wrnn_abi_version(void);

@@ -12,6 +12,7 @@ import pytest
 import torch
 
 import helpers
+from wavernn_b200 import cabi
 from gpu_helpers import run_engine
 from oracle import contract as C
 from oracle import wavernn_oracle as O
@@ -255,3 +256,18 @@ def test_in_kernel_conditioning_equals_materialised_upsample(mol):
     d = np.abs(wavs["kernel"] - wavs["torch"]).max()
     print("in-kernel vs materialised conditioning: max diff", d, "| vs reference", np.abs(wavs["kernel"] - g["wav"]).max())
     assert d <= 1e-4 and np.abs(wavs["kernel"] - g["wav"]).max() <= 2e-2
+
+
+def test_conditioning_pre_pass_and_in_kernel_rows_are_bit_identical(mol):
+    """ABI v4 cond_mode: the per-tile HBM-rate pre-pass (COND_EXPAND, default for strided folds) and the rows formed
+    by the persistent kernel's staging warps (COND_IN_KERNEL) use the same fmaf order -> identical waveforms."""
+    model = mol["model"]
+    mel = helpers.make_mel(41, 5)
+    wavs = {}
+    for mode in (cabi.COND_EXPAND, cabi.COND_IN_KERNEL, cabi.COND_AUTO):
+        model.gen_cond_mode = mode
+        torch.manual_seed(7)
+        wavs[mode] = model.generate(mel, None, True, 2750, 275, False)
+    model.gen_cond_mode = cabi.COND_AUTO
+    assert np.array_equal(wavs[cabi.COND_EXPAND], wavs[cabi.COND_IN_KERNEL])
+    assert np.array_equal(wavs[cabi.COND_EXPAND], wavs[cabi.COND_AUTO])

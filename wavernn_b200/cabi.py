@@ -16,7 +16,8 @@ WRNN_OK, WRNN_E_INVALID, WRNN_E_CUDA, WRNN_E_NO_DEVICE, WRNN_E_WATCHDOG, WRNN_E_
 MODE_MOL, MODE_RAW = 0, 1
 PREC_F16, PREC_FP32, PREC_BF16 = 0, 1, 2
 ENGINE_AUTO, ENGINE_SIMT, ENGINE_TCGEN05 = 0, 1, 2
-ABI_VERSION = 3
+COND_AUTO, COND_EXPAND, COND_IN_KERNEL = 0, 1, 2
+ABI_VERSION = 4
 
 EXPORTS = ("wrnn_abi_version", "wrnn_last_error", "wrnn_create", "wrnn_destroy", "wrnn_generate",
            "wrnn_check", "wrnn_generate_host", "wrnn_engine_name", "wrnn_grid_ctas", "wrnn_launch_count")
@@ -52,7 +53,7 @@ class WrnnJob(C.Structure):
                 ("out", C.c_void_p), ("x_force", C.c_void_p), ("logits_out", C.c_void_p),
                 ("fold_row0", C.c_void_p), ("fold_row_end", C.c_void_p),
                 ("mel_frames", C.c_void_p), ("aux_frames", C.c_void_p), ("up_taps", C.c_void_p),
-                ("hop", C.c_int32), ("reserved0", C.c_int32)]
+                ("hop", C.c_int32), ("cond_mode", C.c_int32)]
 
 
 _lib = None
@@ -151,12 +152,13 @@ class Engine:
     def generate(self, *, mels_up: int, aux: int, L: int, n_seg: int, seg_len: int, seg_stride: int, out: int,
                  seg_first: int = 0, steps: int = 0, uniforms: int = 0, expo: int = 0, philox_seed: int = 0,
                  philox_offset: int = 0, x_force: int = 0, logits_out: int = 0, fold_row0: int = 0, fold_row_end: int = 0,
-                 mel_frames: int = 0, aux_frames: int = 0, up_taps: int = 0, hop: int = 0, stream: int = 0):
+                 mel_frames: int = 0, aux_frames: int = 0, up_taps: int = 0, hop: int = 0, cond_mode: int = 0,
+                 stream: int = 0):
         """All buffer arguments are raw device addresses (ints).  Asynchronous."""
         job = WrnnJob(mels_up, aux, L, seg_stride, n_seg, seg_len, seg_first, steps, uniforms or None,
                       expo or None, philox_seed, philox_offset, out, x_force or None, logits_out or None,
                       fold_row0 or None, fold_row_end or None, mel_frames or None, aux_frames or None, up_taps or None,
-                      hop, 0)
+                      hop, cond_mode)
         _check(self.lib, self.lib.wrnn_generate(self._h, C.byref(job), C.c_void_p(stream or None)))
 
     def check(self):

@@ -125,6 +125,8 @@ static int validate(const wrnn_t* h, const wrnn_job* job, bool host) {
   if (job->mel_frames) {
     if (!job->aux_frames || !job->up_taps || job->hop <= 0) { set_error("mel_frames needs aux_frames, up_taps and hop"); return WRNN_E_INVALID; }
     if (host) { set_error("frame-rate conditioning is a device-pointer feature (use wrnn_generate)"); return WRNN_E_INVALID; }
+    if (job->cond_mode < WRNN_COND_AUTO || job->cond_mode > WRNN_COND_IN_KERNEL) { set_error("cond_mode must be a WRNN_COND_* value"); return WRNN_E_INVALID; }
+    if (job->cond_mode == WRNN_COND_EXPAND && job->fold_row0) { set_error("WRNN_COND_EXPAND needs strided folds (no fold tables)"); return WRNN_E_INVALID; }
     if (job->L >= (1ll << 31)) { set_error("frame-rate conditioning: stream longer than 2^31 samples"); return WRNN_E_INVALID; }
   } else if (!job->mels_up || !job->aux) { set_error("mels_up and aux (or mel_frames / aux_frames / up_taps) are required"); return WRNN_E_INVALID; }
   if (job->n_seg <= 0 || job->seg_len <= 0 || job->L <= 0 || job->seg_stride <= 0) {

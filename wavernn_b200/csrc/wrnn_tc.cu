@@ -84,6 +84,7 @@ static_assert(TC_Q1 + N_Q <= TMEM_COLS, "TMEM budget");
 struct TcParams {
   const unsigned char* blob;
   const float* mels_up; const float* aux; long long L; long long seg_stride;
+  long long row_base;        // rows are numbered (global fold)*seg_stride - row_base (tile-local conditioning scratch)
   int n_seg, steps, out_pitch, seg_first;   // n_seg = folds of THIS launch's tile (<= 64)
   int f0, n_total;                         // first fold of the tile / folds of the whole job (indexing of the job-wide arrays)
   const float* uniforms; unsigned long long seed, offset;
@@ -95,6 +96,41 @@ struct TcParams {
   int* abort_flag;
   long long* prof;           // cycle counters of CTA 0 (fold thread 0: [0..4], driver lane 0: [5..7])
 };
+
+// ------------------------------------------------------------------------------------------
+// conditioning pre-pass (WRNN_COND_EXPAND): rows [r_lo, r_lo + n_rows) of the per-sample conditioning
+// stream from the frame-rate tensors -- the whole UpsampleNetwork tail (three stretch+conv stages as a
+// 5-tap table, aux as a nearest repeat; reference fatchord_version.py:73-88) as one HBM-bound pass.
+// One thread per float4 of a row (20 of mel, 32 of aux); 832 B written per row, the frames come from L2.
+// The tap sum uses the same fmaf order as the in-kernel staging, so both modes give identical rows.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) wrnn_expand_rows_kernel(const float* __restrict__ mel_frames, const float* __restrict__ aux_frames,
+                                                               const float* __restrict__ taps, int hop, long long r_lo, long long n_rows,
+                                                               float* __restrict__ m_out, float* __restrict__ a_out) {
+  constexpr int QM = FEAT / 4, QA = 4 * AUXD / 4, QR = QM + QA;
+  const long long total = n_rows * QR;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long rl = i / QR;
+    const int q = (int)(i - rl * QR);
+    const unsigned r = (unsigned)(r_lo + rl);
+    const unsigned fr = r / (unsigned)hop, ph = r - fr * (unsigned)hop;
+    if (q >= QM) {
+      __stcs(reinterpret_cast<float4*>(a_out + rl * (4 * AUXD)) + (q - QM),
+             __ldg(reinterpret_cast<const float4*>(aux_frames + (size_t)fr * (4 * AUXD)) + (q - QM)));
+    } else {
+      const float* k = taps + ph * 5;
+      const float* m = mel_frames + (size_t)fr * FEAT + q * 4;
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int d = 0; d < 5; ++d) {
+        const float wgt = __ldg(k + d);
+        const float4 x = __ldg(reinterpret_cast<const float4*>(m + d * FEAT));
+        a.x = fmaf(wgt, x.x, a.x); a.y = fmaf(wgt, x.y, a.y); a.z = fmaf(wgt, x.z, a.z); a.w = fmaf(wgt, x.w, a.w);
+      }
+      __stcs(reinterpret_cast<float4*>(m_out + rl * FEAT) + q, a);
+    }
+  }
+}
 
 // ------------------------------------------------------------------------------------------
 // the kernel
@@ -349,7 +385,10 @@ __global__ void __launch_bounds__(NT, 1) wrnn_tc_kernel(const TcParams p) {
     const bool deferred = n_tasks <= COND_TASKS * 128;     // n_seg <= 24: loads fly a whole step before use
     float4 creg[COND_TASKS][2];
     // conditioning window of fold f of this tile: the strided fold, or the caller's tables (several utterances in one job)
-    auto row0_of = [&](int f) -> long long { return p.fold_row0 ? __ldg(p.fold_row0 + p.f0 + f) : (long long)(p.f0 + f) * p.seg_stride; };
+    // strided windows: streams are indexed from the job's first fold, frame tensors from the stream's first sample
+    auto row0_of = [&](int f) -> long long {
+      return p.fold_row0 ? __ldg(p.fold_row0 + p.f0 + f) : (long long)(p.f0 + f + (FRAMES ? p.seg_first : 0)) * p.seg_stride - p.row_base;
+    };
     auto end_of = [&](int f) -> long long { return p.fold_row_end ? __ldg(p.fold_row_end + p.f0 + f) : p.L; };
     auto src_of = [&](int c8, long long row) -> const float4* {
       const float* s = (c8 < FEAT / 8) ? p.mels_up + row * FEAT + c8 * 8 : p.aux + row * (4 * AUXD) + (c8 - FEAT / 8) * 8;
@@ -492,7 +531,7 @@ class TcEngine : public Engine {
  public:
   ~TcEngine() override {
     cudaSetDevice(device);
-    cudaFree(d_blob_); cudaFree(d_scratch_); cudaFree(d_sync_);
+    cudaFree(d_blob_); cudaFree(d_scratch_); cudaFree(d_sync_); cudaFree(d_cond_);
   }
   const char* name() const override { return cfg.precision == WRNN_PREC_BF16 ? "tcgen05-bf16" : "tcgen05-fp16"; }
   int grid_ctas() const override { return P; }
@@ -563,14 +602,46 @@ class TcEngine : public Engine {
     p.prof = reinterpret_cast<long long*>(static_cast<unsigned char*>(d_sync_) + 64);
     WRNN_CUDA_OK(cudaMemsetAsync(d_sync_, 0, 256, stream));
     p.n_total = job.n_seg;
+    // frame-rate conditioning: rows formed by the pre-pass into tile-local scratch (stream kernel), or in the kernel
+    const bool frames = job.mel_frames != nullptr;
+    const bool expand = frames && (job.cond_mode == WRNN_COND_EXPAND || (job.cond_mode == WRNN_COND_AUTO && !job.fold_row0));
+    if (expand && job.fold_row0) { set_error("WRNN_COND_EXPAND needs strided folds (no fold_row0 / fold_row_end tables)"); return WRNN_E_INVALID; }
+    if (expand) {
+      const int nt = job.n_seg < MT ? job.n_seg : MT;
+      long long rows = (long long)(nt - 1) * job.seg_stride + p.steps;
+      if (rows > job.L) rows = job.L;
+      const size_t need = (size_t)rows * CDIM * sizeof(float);
+      if (need > cond_bytes_) {
+        cudaFree(d_cond_); d_cond_ = nullptr; cond_bytes_ = 0;      // (cudaFree waits for earlier launches that read it)
+        WRNN_CUDA_OK(cudaMalloc(&d_cond_, need));
+        cond_bytes_ = need;
+      }
+    }
     // In this latency-bound regime a step costs the same for 1 or 64 folds, so larger jobs run as consecutive
     // tiles of 64 folds (one persistent launch each) at the full per-tile rate.
     for (int f0 = 0; f0 < job.n_seg; f0 += MT) {
       p.f0 = f0;
       p.n_seg = job.n_seg - f0 < MT ? job.n_seg - f0 : MT;
+      if (expand) {
+        const long long r_lo = (long long)(job.seg_first + f0) * job.seg_stride;
+        long long r_hi = r_lo + (long long)(p.n_seg - 1) * job.seg_stride + p.steps;
+        if (r_hi > job.L) r_hi = job.L;
+        const long long n_rows = r_hi > r_lo ? r_hi - r_lo : 0;
+        float* m_out = static_cast<float*>(d_cond_);
+        float* a_out = m_out + (size_t)(cond_bytes_ / (CDIM * sizeof(float))) * FEAT;
+        if (n_rows > 0) {
+          const long long blocks = (n_rows * (CDIM / 4) + 255) / 256;
+          const int grid = (int)(blocks < 148 * 16 ? blocks : 148 * 16);
+          wrnn_expand_rows_kernel<<<grid, 256, 0, stream>>>(job.mel_frames, job.aux_frames, job.up_taps, job.hop, r_lo, n_rows, m_out, a_out);
+          WRNN_CUDA_OK(cudaGetLastError());
+          ++launches;
+        }
+        p.mels_up = m_out; p.aux = a_out; p.L = n_rows; p.row_base = (long long)f0 * job.seg_stride;
+        p.mel_frames = nullptr;
+      }
       WRNN_CUDA_OK(cudaMemsetAsync(d_sync_, 0, 32, stream));                       // arrival counters (the abort flag is sticky)
       void* args[] = {&p};
-      WRNN_CUDA_OK(cudaLaunchCooperativeKernel(kernel(job.mel_frames != nullptr), dim3(P), dim3(NT), args, SMEM_BYTES, stream));
+      WRNN_CUDA_OK(cudaLaunchCooperativeKernel(kernel(frames && !expand), dim3(P), dim3(NT), args, SMEM_BYTES, stream));
       ++launches;
     }
     last_steps_ = p.steps;
@@ -600,6 +671,7 @@ class TcEngine : public Engine {
 
  private:
   void *d_blob_ = nullptr, *d_scratch_ = nullptr, *d_sync_ = nullptr;
+  void* d_cond_ = nullptr; size_t cond_bytes_ = 0;   // WRNN_COND_EXPAND: one tile's conditioning rows ([rows, 80] then [rows, 128])
   size_t scratch_bytes_ = 0;
   int last_steps_ = 0;
 };

@@ -150,8 +150,9 @@ class WaveRNN(nn.Module):
         self.gen_engine = 'auto'        # 'auto' | 'simt' | 'tcgen05'
         self.gen_philox_seed = 0
         self.gen_upsample_chunk = 2048  # mel frames per UpsampleNetwork call (bounds HBM intermediates)
-        self.gen_conditioning = 'kernel'  # 'kernel': frame-rate tensors, rows built inside the kernel (tcgen05 engine)
+        self.gen_conditioning = 'kernel'  # 'kernel': frame-rate tensors go to the library, which forms the rows (tcgen05 engine)
         #                                   'torch' : materialise UpsampleNetwork's (T*hop, 208) output like the reference
+        self.gen_cond_mode = 0            # cabi.COND_AUTO | COND_EXPAND (HBM-rate pre-pass per tile) | COND_IN_KERNEL
         self.gen_verbose = True
         self.gen_stats = {}             # filled by generate(): timings, engine name, ...
         self._engine = None
@@ -343,22 +344,19 @@ class WaveRNN(nn.Module):
         engine = self._get_engine(device)
         out = torch.empty((shard.n_seg, S), dtype=torch.float32, device=device)
         if self._kernel_conditioning_ok() and x_force is None and not want_logits:
-            # frame-rate conditioning: the kernel builds every (T*hop, 208) row itself from the padded mel, the
-            # MelResNet frames and the 5-tap interpolation table -- nothing of size T*hop is materialised
+            # frame-rate conditioning: the library forms every (T*hop, 208) row itself from the padded mel, the
+            # MelResNet frames and the 5-tap interpolation table (an HBM-rate pre-pass per 64-fold tile, or inside the
+            # persistent kernel -- cabi.COND_*); torch never materialises anything of size T*hop
             T = mels_padded.size(-1) - 2 * self.pad
             mel_fr = mels_padded[0].transpose(0, 1).contiguous().float()                  # (T + 2 pad, feat)
             aux_fr = self.upsample.resnet(mels_padded)[0].transpose(0, 1).contiguous().float()   # (T, 4*aux)
             taps = self.upsample_taps(device)
-            f = torch.arange(shard.seg_first, shard.seg_first + shard.n_seg, device=device, dtype=torch.int64)
-            row0 = (f * geo.seg_stride).contiguous()
-            row_end = torch.full_like(row0, T * self.hop_length)
             engine.generate(mels_up=0, aux=0, L=T * self.hop_length, n_seg=shard.n_seg, seg_len=geo.seg_len,
                             seg_stride=geo.seg_stride, out=out.data_ptr(), seg_first=shard.seg_first, steps=steps,
                             uniforms=uniforms.data_ptr() if uniforms is not None else 0,
-                            philox_seed=int(self.gen_philox_seed), fold_row0=row0.data_ptr(),
-                            fold_row_end=row_end.data_ptr(), mel_frames=mel_fr.data_ptr(), aux_frames=aux_fr.data_ptr(),
-                            up_taps=taps.data_ptr(), hop=self.hop_length,
-                            stream=torch.cuda.current_stream(device).cuda_stream)
+                            philox_seed=int(self.gen_philox_seed), mel_frames=mel_fr.data_ptr(),
+                            aux_frames=aux_fr.data_ptr(), up_taps=taps.data_ptr(), hop=self.hop_length,
+                            cond_mode=int(self.gen_cond_mode), stream=torch.cuda.current_stream(device).cuda_stream)
             torch.cuda.current_stream(device).synchronize()
             engine.check()
             self.gen_stats.update(engine=engine.name, grid_ctas=engine.grid_ctas, launches=engine.launch_count,
