@@ -169,6 +169,19 @@ const char *wrnn_engine_name(const wrnn_t *h);
 int wrnn_grid_ctas(const wrnn_t *h);
 int64_t wrnn_launch_count(const wrnn_t *h);
 
+/* Host helper for parity mode: replays torch's default CPU generator (MT19937) natively, so the
+ * draws the reference makes before / inside its loop cost a few ms instead of ~30.
+ *   state : the generator's 624 words and its position `pos` in [0, 624] (624 = block exhausted)
+ *   skip  : outputs to discard first -- the reference builds two nn.GRUCell per generate() call
+ *           (fatchord_version.py:178-179 via :266-271), whose reset_parameters() draws one value
+ *           per parameter element
+ *   out   : n floats  lo + u24 * 2^-24 * (hi - lo), u24 = low 24 bits of each tempered output --
+ *           torch's CPU uniform_() for float32 (utils/distribution.py:106,118 via torch.rand_like
+ *           on a CPU tensor).  out may be NULL with n = 0 (skip only).
+ * Returns the new position; `state` is updated in place.                               */
+int32_t wrnn_mt19937_uniform(uint32_t *state, int32_t pos, uint64_t skip, float *out, uint64_t n,
+                             float lo, float hi);
+
 #ifdef __cplusplus
 }
 #endif

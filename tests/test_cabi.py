@@ -23,7 +23,7 @@ def lib():
 
 def test_header_symbols_are_exported(lib):
     header = (ROOT / "include" / "wavernn_b200.h").read_text()
-    declared = set(re.findall(r"\b(wrnn_[a-z_]+)\s*\(", header))
+    declared = set(re.findall(r"\b(wrnn_[a-z0-9_]+)\s*\(", header))
     assert declared == set(cabi.EXPORTS), declared ^ set(cabi.EXPORTS)
     for sym in declared:
         assert getattr(lib, sym) is not None

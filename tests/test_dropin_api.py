@@ -140,3 +140,26 @@ def test_upsample_taps_reproduce_the_interpolation_cascade():
         rec = sum(taps[n % 275, d][:, None] * xp[n // 275 + d] for d in range(5))
         np.testing.assert_allclose(rec, full_m[0].numpy(), atol=2e-6)
         np.testing.assert_array_equal(np.repeat(aux_fr, 275, 0), full_a[0].numpy())
+
+
+@pytest.mark.parametrize("mode", ["MOL", "RAW"])
+def test_native_generator_replay_equals_torch_operators(mode):
+    """cabi.torch_rng_uniform / wrnn_mt19937_uniform: the native replay of torch's CPU generator gives the same
+    draws as the reference's own sequence (two nn.GRUCell ctors, then uniform_ / exponential_) and leaves the
+    generator in the same state."""
+    import torch
+    from wavernn_b200 import cabi
+    from wavernn_b200.sharding import fold_geometry
+    if not cabi.is_built():
+        pytest.skip("library not built")
+    assert cabi.torch_rng_replay_ok()
+    model = helpers.make_model(0, mode, "cpu")
+    geo = fold_geometry(30 * 275, 2750, 275)
+    got = {}
+    for native in (True, False):
+        model.gen_native_rng = native
+        torch.manual_seed(4321)
+        torch.rand(77)                                   # start mid-block
+        u, e = model._reference_draws(geo, 300 if mode == "MOL" else 5)
+        got[native] = (u if u is not None else e, torch.rand(9))
+    assert torch.equal(got[True][0], got[False][0]) and torch.equal(got[True][1], got[False][1])

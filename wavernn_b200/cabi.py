@@ -20,7 +20,8 @@ COND_AUTO, COND_EXPAND, COND_IN_KERNEL = 0, 1, 2
 ABI_VERSION = 4
 
 EXPORTS = ("wrnn_abi_version", "wrnn_last_error", "wrnn_create", "wrnn_destroy", "wrnn_generate",
-           "wrnn_check", "wrnn_generate_host", "wrnn_engine_name", "wrnn_grid_ctas", "wrnn_launch_count")
+           "wrnn_check", "wrnn_generate_host", "wrnn_engine_name", "wrnn_grid_ctas", "wrnn_launch_count",
+           "wrnn_mt19937_uniform")
 
 _fp = C.POINTER(C.c_float)
 
@@ -92,6 +93,8 @@ def load() -> C.CDLL:
     lib.wrnn_grid_ctas.argtypes = [C.c_void_p]
     lib.wrnn_launch_count.restype = C.c_int64
     lib.wrnn_launch_count.argtypes = [C.c_void_p]
+    lib.wrnn_mt19937_uniform.restype = C.c_int32
+    lib.wrnn_mt19937_uniform.argtypes = [C.c_void_p, C.c_int32, C.c_uint64, C.c_void_p, C.c_uint64, C.c_float, C.c_float]
     if lib.wrnn_abi_version() != ABI_VERSION:
         raise RuntimeError(f"wavernn_b200: ABI mismatch (lib {lib.wrnn_abi_version()} != binding {ABI_VERSION})")
     _lib = lib
@@ -179,3 +182,67 @@ class Engine:
 def _torch():
     import torch
     return torch
+
+
+# ---------------------------------------------------------------------------------------------
+# torch CPU generator replay (parity mode's host-side cost; see csrc/wrnn_hostrng.cu)
+# ---------------------------------------------------------------------------------------------
+# Layout of torch.get_rng_state() for the CPU generator (CPUGeneratorImplStateLegacy): seed u64 @0, left i32 @8,
+# seeded i32 @12, next u64 @16, 624 state words as u64 @24, then the cached-normal fields (untouched here).
+_MT_N, _MT_OFF, _STATE_BYTES = 624, 24, 5056
+
+
+def torch_rng_uniform(skip: int, n: int, lo: float, hi: float, out=None, generator=None):
+    """Advance torch's CPU generator by `skip` discarded 32-bit outputs and then fill `out` (a contiguous CPU float32
+    tensor with n elements, e.g. pinned) with what `torch.empty(n).uniform_(lo, hi)` would have produced -- natively.
+    The generator (default: the global one) is left in exactly the state torch would have left it in."""
+    import numpy as np
+    import torch
+    lib = load()
+    st = (generator.get_state() if generator is not None else torch.get_rng_state()).clone()
+    a = st.numpy()
+    if a.size != _STATE_BYTES:
+        raise RuntimeError("unexpected torch CPU generator state size")
+    left = int(a[8:12].view(np.int32)[0])
+    if not (1 <= left <= _MT_N):
+        raise RuntimeError("unexpected torch CPU generator state (left)")
+    words = a[_MT_OFF:_MT_OFF + 8 * _MT_N].view(np.uint64)
+    mt = np.ascontiguousarray(words.astype(np.uint32))
+    if out is None:
+        out = torch.empty(n, dtype=torch.float32)
+    assert out.dtype == torch.float32 and out.is_contiguous() and out.numel() >= n and out.device.type == 'cpu'
+    pos = lib.wrnn_mt19937_uniform(mt.ctypes.data, _MT_N + 1 - left, int(skip), out.data_ptr() if n else None, int(n),
+                                   float(lo), float(hi))
+    if pos < 0:
+        raise RuntimeError("wrnn_mt19937_uniform rejected its arguments")
+    words[:] = mt
+    a[8:12].view(np.int32)[0] = _MT_N + 1 - pos
+    a[16:24].view(np.uint64)[0] = pos
+    if generator is not None:
+        generator.set_state(st)
+    else:
+        torch.set_rng_state(st)
+    return out
+
+
+_rng_replay_ok = None
+
+
+def torch_rng_replay_ok() -> bool:
+    """One-time self-check of the native replay against torch itself (private generators, a skip that crosses
+    blocks, the reference's uniform range).  False -> callers use torch's own operators (slower, same numbers)."""
+    global _rng_replay_ok
+    if _rng_replay_ok is None:
+        import torch
+        try:
+            g1, g2 = torch.Generator(), torch.Generator()
+            g1.manual_seed(20240607); g2.manual_seed(20240607)
+            torch.empty(1531).uniform_(-0.04, 0.04, generator=g1)
+            want = torch.empty(2000).uniform_(1e-5, 1.0 - 1e-5, generator=g1)
+            got = torch_rng_uniform(1531, 2000, 1e-5, 1.0 - 1e-5, generator=g2)
+            tail_w = torch.empty(700).uniform_(generator=g1)
+            tail_g = torch.empty(700).uniform_(generator=g2)
+            _rng_replay_ok = bool(torch.equal(want, got) and torch.equal(tail_w, tail_g))
+        except Exception:
+            _rng_replay_ok = False
+    return _rng_replay_ok

@@ -1,0 +1,93 @@
+// Host-side replay of torch's default CPU generator (MT19937) for parity mode.
+//
+// The reference draws all of its randomness from torch's global CPU generator: two nn.GRUCell constructions per
+// generate() call (fatchord_version.py:178-179 -> :266-271; reset_parameters() draws one uniform per parameter
+// element, 3.2 M values that are thrown away) and then 11 uniforms per fold and step inside the loop
+// (utils/distribution.py:106,118).  Reproducing that stream with torch operators costs ~30 ms of single-thread CPU
+// time per call -- a fifth of the whole B200 job.  Here the discarded part is skipped with bare state twists (no
+// tempering, no stores) and the used part is written straight into the caller's (pinned) staging buffer.
+//
+// The caller (wavernn_b200/vocoder.py) reads / writes the generator state through torch.get_rng_state() /
+// set_rng_state() and self-checks this routine against torch before trusting it.
+#include <cmath>
+#include <cstdint>
+
+#include "../../include/wavernn_b200.h"
+
+namespace {
+
+constexpr int N = 624, M = 397;
+constexpr uint32_t UPPER = 0x80000000u, LOWER = 0x7fffffffu, MAG = 0x9908b0dfu;
+
+inline uint32_t mix(uint32_t a, uint32_t b, uint32_t far) {
+  const uint32_t y = (a & UPPER) | (b & LOWER);
+  return far ^ (y >> 1) ^ ((0u - (y & 1u)) & MAG);
+}
+
+// next block of 624 words, in place.  The first loop only reads words that are still old, the second reads words
+// written at least 227 iterations earlier: both vectorise.
+void twist(uint32_t* __restrict__ mt) {
+  int i = 0;
+  for (; i < N - M; ++i) mt[i] = mix(mt[i], mt[i + 1], mt[i + M]);
+  for (; i < N - 1; ++i) mt[i] = mix(mt[i], mt[i + 1], mt[i + M - N]);
+  mt[N - 1] = mix(mt[N - 1], mt[0], mt[M - 1]);
+}
+
+inline uint32_t temper(uint32_t y) {
+  y ^= y >> 11;
+  y ^= (y << 7) & 0x9d2c5680u;
+  y ^= (y << 15) & 0xefc60000u;
+  y ^= y >> 18;
+  return y;
+}
+
+// One body, two instantiations: with the FMA unit (every x86-64 host a B200 sits in) the conversion is one
+// instruction per draw; otherwise libm's correctly rounded fmaf gives the same bits.
+template <bool HW>
+inline __attribute__((always_inline)) void convert_body(const uint32_t* s, float* o, uint64_t take, float range, float lo) {
+  constexpr float kInv = 1.0f / 16777216.0f;
+  for (uint64_t i = 0; i < take; ++i) {
+    const float x = (float)(int32_t)(temper(s[i]) & 0xffffffu) * kInv;
+    o[i] = HW ? __builtin_fmaf(x, range, lo) : std::fmaf(x, range, lo);
+  }
+}
+template <bool HW> void convert(const uint32_t* s, float* o, uint64_t take, float range, float lo);
+#if defined(__x86_64__)
+template <> __attribute__((target("fma,avx2"))) void convert<true>(const uint32_t* s, float* o, uint64_t take, float range, float lo) {
+  convert_body<true>(s, o, take, range, lo);
+}
+#else
+template <> void convert<true>(const uint32_t* s, float* o, uint64_t take, float range, float lo) { convert_body<false>(s, o, take, range, lo); }
+#endif
+template <> void convert<false>(const uint32_t* s, float* o, uint64_t take, float range, float lo) { convert_body<false>(s, o, take, range, lo); }
+
+}  // namespace
+
+extern "C" int32_t wrnn_mt19937_uniform(uint32_t* state, int32_t pos, uint64_t skip, float* out, uint64_t n, float lo, float hi) {
+  if (!state || pos < 0 || pos > N || (n && !out)) return -1;
+  // discard: whole blocks cost one twist each
+  while (skip) {
+    if (pos == N) { twist(state); pos = 0; }
+    const uint64_t take = skip < (uint64_t)(N - pos) ? skip : (uint64_t)(N - pos);
+    pos += (int32_t)take;
+    skip -= take;
+  }
+  // torch's uniform_real<float>: x = (y & (2^24 - 1)) * 2^-24 ; x * (hi - lo) + lo with one rounding (its CPU kernels
+  // are built with FMA contraction)
+  const float range = hi - lo;
+#if defined(__x86_64__)
+  const bool hw = __builtin_cpu_supports("fma") && __builtin_cpu_supports("avx2");
+#else
+  const bool hw = false;
+#endif
+  uint64_t done = 0;
+  while (done < n) {
+    if (pos == N) { twist(state); pos = 0; }
+    const uint64_t take = (n - done) < (uint64_t)(N - pos) ? (n - done) : (uint64_t)(N - pos);
+    if (hw) convert<true>(state + pos, out + done, take, range, lo);
+    else convert<false>(state + pos, out + done, take, range, lo);
+    pos += (int32_t)take;
+    done += take;
+  }
+  return pos;
+}

@@ -149,6 +149,8 @@ class WaveRNN(nn.Module):
         self.gen_precision = 'fp16'     # 'fp16' | 'bf16' tensor-core operands | 'fp32' strict SIMT mode
         self.gen_engine = 'auto'        # 'auto' | 'simt' | 'tcgen05'
         self.gen_philox_seed = 0
+        self.gen_native_rng = True      # replay torch's CPU generator natively (self-checked; False = torch operators)
+        self._draw_buf = None
         self.gen_upsample_chunk = 2048  # mel frames per UpsampleNetwork call (bounds HBM intermediates)
         self.gen_conditioning = 'kernel'  # 'kernel': frame-rate tensors go to the library, which forms the rows (tcgen05 engine)
         #                                   'torch' : materialise UpsampleNetwork's (T*hop, 208) output like the reference
@@ -261,11 +263,32 @@ class WaveRNN(nn.Module):
                 and self.gen_engine in ('auto', 'tcgen05'))
 
     # ------------------------------------------------------------------ randomness
-    def _reference_draws(self, geo: FoldGeometry, steps: int):
-        """Consumes torch's default CPU generator exactly as the reference's generate() does."""
-        nn.GRUCell(self.rnn1.input_size, self.rnn1.hidden_size)     # :178 get_gru_cell(self.rnn1)
-        nn.GRUCell(self.rnn2.input_size, self.rnn2.hidden_size)     # :179
+    def _reference_draws(self, geo: FoldGeometry, steps: int, reuse_buffer: bool = False):
+        """Consumes torch's default CPU generator exactly as the reference's generate() does: two nn.GRUCell
+        constructions (:178-179, one uniform per parameter element, discarded) and then the loop's draws.
+        With `gen_native_rng` the generator is replayed natively (cabi.torch_rng_uniform: the discarded part is skipped,
+        the used part written straight into a pinned staging buffer) -- same numbers, same final generator state,
+        ~10x less host time; it is self-checked against torch once per process."""
         B = geo.n_seg
+        native = bool(self.gen_native_rng) and cabi.is_built() and cabi.torch_rng_replay_ok()
+        if native:
+            skip = sum(3 * g.hidden_size * (g.input_size + g.hidden_size + 2) for g in (self.rnn1, self.rnn2))
+            if self.mode == 'MOL':
+                n = steps * 11 * B
+                buf = None
+                if torch.cuda.is_available():
+                    if reuse_buffer:        # one job at a time: the caller synchronises before the next call
+                        if self._draw_buf is None or self._draw_buf.numel() < n:
+                            self._draw_buf = torch.empty(n, dtype=torch.float32, pin_memory=True)
+                        buf = self._draw_buf
+                    else:
+                        buf = torch.empty(n, dtype=torch.float32, pin_memory=True)
+                u = cabi.torch_rng_uniform(skip, n, 1e-5, 1.0 - 1e-5, out=buf)
+                return u[:n].view(steps, 11 * B), None
+            cabi.torch_rng_uniform(skip, 0, 0.0, 1.0)
+        else:
+            nn.GRUCell(self.rnn1.input_size, self.rnn1.hidden_size)     # :178 get_gru_cell(self.rnn1)
+            nn.GRUCell(self.rnn2.input_size, self.rnn2.hidden_size)     # :179
         if self.mode == 'MOL':
             u = torch.empty(steps, 11 * B).uniform_(1e-5, 1.0 - 1e-5)   # distribution.py:106,118
             return u, None
@@ -328,12 +351,19 @@ class WaveRNN(nn.Module):
         Returns the (n_seg_local, S) float32 device tensor of samples (pre-xfade)."""
         S = steps or geo.seg_len
         uniforms = expo = None
+        frames = self._kernel_conditioning_ok() and x_force is None and not want_logits and shard.n_seg > 0
+        if frames:      # enqueue the frame-rate GPU work first: it overlaps the host-side RNG replay below
+            T = mels_padded.size(-1) - 2 * self.pad
+            mel_fr = mels_padded[0].transpose(0, 1).contiguous().float()                  # (T + 2 pad, feat)
+            aux_fr = self.upsample.resnet(mels_padded)[0].transpose(0, 1).contiguous().float()   # (T, 4*aux)
+            taps = self.upsample_taps(device)
         if self.gen_rng == 'torch' or draws is not None:
-            u_all, e_all = draws if draws is not None else self._reference_draws(geo, S)
+            u_all, e_all = draws if draws is not None else self._reference_draws(geo, S, reuse_buffer=True)
             f0, n = shard.seg_first, shard.n_seg
             B = geo.n_seg
             if u_all is not None:
-                u_loc = torch.cat([u_all[:, 10 * f0:10 * (f0 + n)], u_all[:, 10 * B + f0:10 * B + f0 + n]], dim=1)
+                u_loc = u_all if (f0 == 0 and n == B) else \
+                    torch.cat([u_all[:, 10 * f0:10 * (f0 + n)], u_all[:, 10 * B + f0:10 * B + f0 + n]], dim=1)
                 uniforms = u_loc.contiguous().to(device, non_blocking=True)
             if e_all is not None:
                 expo = e_all[:, f0:f0 + n].contiguous().to(device, non_blocking=True)
@@ -343,14 +373,10 @@ class WaveRNN(nn.Module):
             return torch.zeros((0, S), dtype=torch.float32, device=device)
         engine = self._get_engine(device)
         out = torch.empty((shard.n_seg, S), dtype=torch.float32, device=device)
-        if self._kernel_conditioning_ok() and x_force is None and not want_logits:
+        if frames:
             # frame-rate conditioning: the library forms every (T*hop, 208) row itself from the padded mel, the
             # MelResNet frames and the 5-tap interpolation table (an HBM-rate pre-pass per 64-fold tile, or inside the
             # persistent kernel -- cabi.COND_*); torch never materialises anything of size T*hop
-            T = mels_padded.size(-1) - 2 * self.pad
-            mel_fr = mels_padded[0].transpose(0, 1).contiguous().float()                  # (T + 2 pad, feat)
-            aux_fr = self.upsample.resnet(mels_padded)[0].transpose(0, 1).contiguous().float()   # (T, 4*aux)
-            taps = self.upsample_taps(device)
             engine.generate(mels_up=0, aux=0, L=T * self.hop_length, n_seg=shard.n_seg, seg_len=geo.seg_len,
                             seg_stride=geo.seg_stride, out=out.data_ptr(), seg_first=shard.seg_first, steps=steps,
                             uniforms=uniforms.data_ptr() if uniforms is not None else 0,
