@@ -158,15 +158,20 @@ def time_cpu_port(sample_steps: int, repeats: int = 1, warmup: int = 0):
         torch.manual_seed(1234)
         _, dt = torch_port.generate_segments_torch(sd, mels_f, aux_f, steps=40)
         trials[n] = dt
-    best = min(trials, key=trials.get)
+    # the 40-step sweep is noisy on a shared host: time the full sample on the two best counts, keep the faster
+    finals = {}
+    for n in sorted(trials, key=trials.get)[:2]:
+        torch.set_num_threads(n)
+        ts = []
+        for i in range(warmup + repeats):
+            torch.manual_seed(1234)
+            _, dt = torch_port.generate_segments_torch(sd, mels_f, aux_f, steps=sample_steps)
+            if i >= warmup:
+                ts.append(dt)
+        finals[n] = ts
+    best = min(finals, key=lambda n: float(np.mean(finals[n])))
     torch.set_num_threads(best)
-    cores = best
-    times = []
-    for i in range(warmup + repeats):
-        torch.manual_seed(1234)
-        _, dt = torch_port.generate_segments_torch(sd, mels_f, aux_f, steps=sample_steps)
-        if i >= warmup:
-            times.append(dt)
+    cores, times = best, finals[best]
     return dict(B=B, steps=sample_steps, seconds=times, cores=cores, threads=torch.get_num_threads(),
                 host_cores=os.cpu_count() or 1, sweep={str(k): round(40 * B / v, 1) for k, v in trials.items()})
 
