@@ -29,7 +29,15 @@ def main():
     model.gen_rng = "philox"
     model.gen_philox_seed = 7
     wav_p = model.generate(mel, None, True, 2750, 275, False)
-    ok = err <= 2e-2 and np.isfinite(wav_p).all()
+    # generate_many: the folds of four utterances sharded as one job == one sharded generate() per utterance
+    model.gen_rng = "torch"
+    mels = [helpers.make_mel(T, seed) for T, seed in ((30, 0), (26, 3), (41, 5), (22, 7))]
+    torch.manual_seed(99)
+    seq = [model.generate(m, None, True, 2750, 275, False) for m in mels]
+    torch.manual_seed(99)
+    many = model.generate_many(mels, [None] * 4, 2750, 275, False)
+    many_ok = model.gen_stats["world"] == world and all(a.shape == b.shape and np.abs(a - b).max() <= 1e-6 for a, b in zip(seq, many))
+    ok = err <= 2e-2 and np.isfinite(wav_p).all() and many_ok
     flag = torch.tensor([1.0 if ok else 0.0, err], device=f"cuda:{local}")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     gathered = [torch.zeros(wav_p.shape[0], dtype=torch.float64, device=f"cuda:{local}") for _ in range(world)]
@@ -37,7 +45,7 @@ def main():
     same = all(torch.equal(gathered[0], x) for x in gathered)
     if rank == 0:
         print(f"multi-gpu check: world={world} engine={model.gen_stats.get('engine')} max|wav-ref|={err:.3e} "
-              f"philox identical on all ranks={same} -> {'OK' if flag[0].item() == 1.0 and same else 'FAIL'}")
+               f"generate_many==generate: {many_ok} philox identical on all ranks={same} -> {'OK' if flag[0].item() == 1.0 and same else 'FAIL'}")
     dist.destroy_process_group()
     sys.exit(0 if (flag[0].item() == 1.0 and same) else 1)
 

@@ -335,7 +335,7 @@ class WaveRNN(nn.Module):
             output = out_all.cpu().numpy().astype(np.float64)                    # :243-245
 
         wav = self._epilogue(output, geo, batched, wave_len, mu_law)
-        if save_path is not None:
+        if save_path is not None and rank == 0:                                  # one writer per job
             save_wav(wav, save_path, self.sample_rate)                           # :260
         self.train()                                                             # :262
         elapsed = time.time() - t_start
@@ -435,8 +435,10 @@ class WaveRNN(nn.Module):
         draws are made in that order)."""
         device = self._require_cuda()
         dist_on = torch.distributed.is_available() and torch.distributed.is_initialized()
-        if (dist_on and torch.distributed.get_world_size() > 1) or self.mode != 'MOL' or len(mels_list) == 0:
-            # multi-rank jobs shard each utterance's folds; the RAW head is served fold-strided: one call each
+        rank = torch.distributed.get_rank() if dist_on else 0
+        world = torch.distributed.get_world_size() if dist_on else 1
+        if self.mode != 'MOL' or len(mels_list) == 0:
+            # the RAW head is served fold-strided by the SIMT engine: one call per utterance
             return [self.generate(m, p, True, target, overlap, mu_law) for m, p in zip(mels_list, save_paths)]
         t_start = time.time()
         self.eval()
@@ -468,35 +470,45 @@ class WaveRNN(nn.Module):
             m_all, a_all = torch.cat(streams_m, 0).contiguous(), torch.cat(streams_a, 0).contiguous()
             t_row0 = torch.tensor(row0, dtype=torch.int64, device=device)
             t_end = torch.tensor(row_end, dtype=torch.int64, device=device)
+            # the job's folds (all utterances, in order) are sharded over the ranks like generate()'s: contiguous
+            # blocks, no data-path collective, one all-gather of the sample blocks
+            job = FoldGeometry(base, target, overlap, B, S, stride, base)
+            shard = shard_folds(job, rank, world, hop)
+            f_lo, n_loc = shard.seg_first, shard.n_seg
             uniforms = None
             if self.gen_rng == 'torch':
                 mix = torch.cat([u[:, :10 * g.n_seg] for u, g in zip(draws, geos)], 1)
                 logi = torch.cat([u[:, 10 * g.n_seg:] for u, g in zip(draws, geos)], 1)
-                uniforms = torch.cat([mix, logi], 1).contiguous().to(device, non_blocking=True)
+                uniforms = torch.cat([mix[:, 10 * f_lo:10 * (f_lo + n_loc)], logi[:, f_lo:f_lo + n_loc]], 1) \
+                    .contiguous().to(device, non_blocking=True)
             elif self.gen_rng != 'philox':
                 raise ValueError(f"gen_rng must be 'torch' or 'philox', got {self.gen_rng!r}")
             engine = self._get_engine(device)
-            out = torch.empty((B, S), dtype=torch.float32, device=device)
-            cond = (dict(mels_up=0, aux=0, mel_frames=m_all.data_ptr(), aux_frames=a_all.data_ptr(),
-                         up_taps=self.upsample_taps(device).data_ptr(), hop=hop) if frames
-                    else dict(mels_up=m_all.data_ptr(), aux=a_all.data_ptr()))
-            engine.generate(L=base, n_seg=B, seg_len=S, seg_stride=stride, out=out.data_ptr(),
-                            uniforms=uniforms.data_ptr() if uniforms is not None else 0,
-                            philox_seed=int(self.gen_philox_seed), fold_row0=t_row0.data_ptr(),
-                            fold_row_end=t_end.data_ptr(), stream=torch.cuda.current_stream(device).cuda_stream, **cond)
-            torch.cuda.current_stream(device).synchronize()
-            engine.check()
+            out = torch.empty((n_loc, S), dtype=torch.float32, device=device)
+            if n_loc:
+                cond = (dict(mels_up=0, aux=0, mel_frames=m_all.data_ptr(), aux_frames=a_all.data_ptr(),
+                             up_taps=self.upsample_taps(device).data_ptr(), hop=hop) if frames
+                        else dict(mels_up=m_all.data_ptr(), aux=a_all.data_ptr()))
+                engine.generate(L=base, n_seg=n_loc, seg_len=S, seg_stride=stride, out=out.data_ptr(), seg_first=f_lo,
+                                uniforms=uniforms.data_ptr() if uniforms is not None else 0,
+                                philox_seed=int(self.gen_philox_seed), fold_row0=t_row0[f_lo:].data_ptr(),
+                                fold_row_end=t_end[f_lo:].data_ptr(),
+                                stream=torch.cuda.current_stream(device).cuda_stream, **cond)
+                torch.cuda.current_stream(device).synchronize()
+                engine.check()
+            if world > 1:
+                out = gather_segments(out, shard, job)
             samples = out.cpu().numpy().astype(np.float64)
         wavs, f0 = [], 0
         for g, wl, path in zip(geos, wave_lens, save_paths):
             wav = self._epilogue(samples[f0:f0 + g.n_seg].copy(), g, True, wl, False)
             f0 += g.n_seg
-            if path is not None:
+            if path is not None and rank == 0:
                 save_wav(wav, path, self.sample_rate)
             wavs.append(wav)
         self.train()
         self.gen_stats.update(wall_s=time.time() - t_start, n_seg=B, seg_len=S, engine=engine.name,
-                              launches=engine.launch_count, utterances=len(geos))
+                              launches=engine.launch_count, utterances=len(geos), world=world)
         return wavs
 
     # ------------------------------------------------------------------ reference helpers kept for callers
