@@ -51,11 +51,11 @@ def frames_for(n_gpus: int) -> int:
     return L // HOP
 
 
-def build_model(device):
+def build_model(device, mode="MOL"):
     from wavernn_b200 import WaveRNN
     torch.manual_seed(0)
     with contextlib.redirect_stdout(io.StringIO()):
-        m = WaveRNN(**CTOR)
+        m = WaveRNN(**dict(CTOR, mode=mode))
     m.gen_verbose = False
     return m.to(device)
 
@@ -214,9 +214,12 @@ def run_ours(args):
         os.environ.setdefault("NCCL_DEBUG", "WARN")       # keep NCCL's version banner off stdout (one JSON line only)
         dist.init_process_group("nccl", device_id=device)
 
-    model = build_model(device)
+    cfg3 = args.workload == "cfg3"                     # BASELINE configs[2]: cfg2's mel with the 9-bit RAW head (mu-law)
+    model = build_model(device, "RAW" if cfg3 else "MOL")
     model.gen_precision, model.gen_engine = args.precision, args.engine
     cfg5 = args.workload == "cfg5"
+    if cfg3:
+        model.gen_rng = "philox"                       # (parity mode would stream 471 MB of Exp(1) draws per call)
     if cfg5:
         # BASELINE configs[4] (SURVEY 8d choice A): T=172,034 frames = 35.8 min -> exactly 4096 folds with the
         # reference's own target/overlap; the 4096 folds are sharded over the ranks (strong scaling); in-kernel RNG
@@ -237,7 +240,7 @@ def run_ours(args):
         m_up = m_up[off:off + shard.row_hi - shard.row_lo].contiguous()
         aux = aux[off:off + shard.row_hi - shard.row_lo].contiguous()
     f0, n = shard.seg_first, shard.n_seg
-    if cfg5:
+    if cfg5 or cfg3:
         u_all, uni_ptr, h2d_rng = None, 0, 0
     else:
         torch.manual_seed(1234)
@@ -281,7 +284,7 @@ def run_ours(args):
     # ---- end to end through the public API, host buffers --------------------------------
     def e2e_step():
         torch.manual_seed(1234)
-        return model.generate(mel_host, None, True, TARGET, OVERLAP, False)
+        return model.generate(mel_host, None, True, TARGET, OVERLAP, cfg3)
 
     if args.skip_e2e:
         t_e2e = float("nan")
@@ -308,27 +311,27 @@ def run_ours(args):
         peaks = measured_peaks()
         long_run = (t_dev / args.steps) > 1.0
         peak_tf = peaks["tflops_sustained"] if long_run else peaks["tflops"]
-        ach_tf = value / world * FLOP_PER_SAMPLE_MOL / 1e12          # per GPU
+        ach_tf = value / world * (8_143_872 if cfg3 else FLOP_PER_SAMPLE_MOL) / 1e12          # per GPU
         step_us = t_dev / args.steps / S_eff * 1e6
         cpu = None
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and not cfg3:
             r = time_cpu_port(args.cpu_sample_steps)
             v = r["B"] * r["steps"] / r["seconds"][0]
             cpu = {"value": v, "unit": "samples/s", "cores": r["cores"], "kind": "port",
                    "sample": f"{r['B']} folds x first {r['steps']} of 12100 steps, torch CPU operators, best of thread sweep = {r['threads']} threads on {r['host_cores']} host cores; samples/s by threads: {r['sweep']}"}
         line = {
-            "metric": "audio samples/sec (22.05 kHz) batched MoL generate", "value": value, "unit": "samples/s",
+            "metric": "audio samples/sec (22.05 kHz) batched " + ("RAW 9-bit" if cfg3 else "MoL") + " generate", "value": value, "unit": "samples/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_dev / args.steps * 1e3,
             "higher_is_better": True, "scaling": "strong" if cfg5 else "weak", "vs_baseline": None,
             "dtype": {"fp16": "f16", "bf16": "bf16", "fp32": "f32"}[args.precision], "data": "synthetic",
             "config": {"workload": (f"cfg5: mel T={T} frames (35.8 min) -> {B_total} folds x {S} steps sharded over {world} GPU(s), "
                                     if cfg5 else
                                     f"cfg2 x{world}: mel T={T} frames -> {B_total} folds x {S} steps ({FOLDS_PER_GPU} folds per GPU), ")
-                                   + f"target={TARGET} overlap={OVERLAP}, MoL head, rnn_dims=512, random-init weights, torch.rand mel",
+                                   + f"target={TARGET} overlap={OVERLAP}, " + ("RAW head (bits=9, mu-law)" if cfg3 else "MoL head") + ", rnn_dims=512, random-init weights, torch.rand mel",
                        "engine": model.gen_stats.get("engine", engine.name), "grid_ctas": engine.grid_ctas,
                        "parallelism": f"folds sharded x{world}" if world > 1 else "single GPU",
                        "l2_policy": "no flush: the per-step conditioning stream (183 MB per 19 folds) exceeds the 126 MB L2",
-                       "rng": "in-kernel Philox4x32-10" if cfg5 else "reference-compatible torch CPU draws, resident in HBM for `value`"},
+                       "rng": "in-kernel Philox4x32-10" if (cfg5 or cfg3) else "reference-compatible torch CPU draws, resident in HBM for `value`"},
             "clocks": clocks, "gpu_launches": int(gpu_launches),
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(mel_host.numel() * 4 + h2d_rng),
                     "d2h_bytes_per_step": int(B_total * S * 4), "ms_per_step": t_e2e / args.steps * 1e3},
@@ -359,7 +362,7 @@ def main():
     ap.add_argument("--engine", default="auto", choices=["auto", "simt", "tcgen05"])
     ap.add_argument("--cpu-sample-steps", type=int, default=3000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg5"],
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg5"],
                     help="cfg2 (default, the headline config: 19 folds per GPU) or cfg5 (4096 folds of a 35.8-min mel, "
                          "sharded over the ranks, in-kernel Philox draws)")
     ap.add_argument("--seg-steps", type=int, default=0,

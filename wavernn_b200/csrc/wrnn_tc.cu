@@ -29,8 +29,12 @@
 //   warps 5-7  cond stagers : stream cond_{t+1} HBM -> registers -> fp16 operand image, one
 //                             step ahead of the recurrence
 //
-// One launch serves a tile of <= 64 folds (one M tile); larger jobs run tile after tile.  MoL head only:
-// the RAW 9-bit head and the fp32 strict mode are served by the SIMT engine (ENGINE_AUTO falls through).
+// One launch serves a tile of <= 64 folds (one M tile); larger jobs run tile after tile.
+// RAW 9-bit head (template RAW; reference :231-237): fc3 has 512 = 4 x 128 rows, so CTA c owns classes
+// [4c, 4c+4) like every other layer.  Categorical(softmax(l)).sample() == argmax_k(p_k / e_k), e ~ Exp(1),
+// == argmax_k(l_k - log e_k): each CTA publishes its best (score, class) per fold, a FIFTH exchange gathers the
+// 128 candidates per fold into every CTA, and every CTA reduces them identically (ties -> lowest class).
+// The fp32 strict mode is served by the SIMT engine (ENGINE_AUTO falls through).
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
@@ -87,12 +91,13 @@ struct TcParams {
   long long row_base;        // rows are numbered (global fold)*seg_stride - row_base (tile-local conditioning scratch)
   int n_seg, steps, out_pitch, seg_first;   // n_seg = folds of THIS launch's tile (<= 64)
   int f0, n_total;                         // first fold of the tile / folds of the whole job (indexing of the job-wide arrays)
-  const float* uniforms; unsigned long long seed, offset;
+  const float* uniforms; const float* expo; unsigned long long seed, offset;   // expo: RAW head, [steps, n_total, 512]
   float* out; const float* x_force; float* logits_out;
   const long long* fold_row0; const long long* fold_row_end;   // optional per-fold conditioning windows (job-wide, [n_total])
   const float* mel_frames; const float* aux_frames; const float* up_taps; int hop;   // optional frame-rate conditioning
   unsigned char* xch;        // [4 vectors][2 parities][n_groups * SBO_H] activation images
-  unsigned* counters;        // [4] monotonically increasing arrival counters
+  unsigned char* xch5;       // RAW: [2 parities][128 CTAs][n_groups * 8 folds] (score, class) candidates
+  unsigned* counters;        // [5] monotonically increasing arrival counters
   int* abort_flag;
   long long* prof;           // cycle counters of CTA 0 (fold thread 0: [0..4], driver lane 0: [5..7])
 };
@@ -135,7 +140,7 @@ __global__ void __launch_bounds__(256) wrnn_expand_rows_kernel(const float* __re
 // ------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------
-template <int FMT, bool FRAMES>
+template <int FMT, bool FRAMES, bool RAW>
 __global__ void __launch_bounds__(NT, 1) wrnn_tc_kernel(const TcParams p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const float* fv = reinterpret_cast<const float*>(smem + OFF_VEC);
@@ -150,6 +155,9 @@ __global__ void __launch_bounds__(NT, 1) wrnn_tc_kernel(const TcParams p) {
   const int n_groups = (B + 7) / 8;                    // real 8-row groups of the A images
   const uint32_t img_bytes = (uint32_t)n_groups * SBO_H;
   const size_t xch_stride = (size_t)2 * img_bytes;     // per vector: two parities
+  constexpr int GPS = RAW ? 5 : 4;                     // gathers (completions of bar_g) per step
+  constexpr int NCLS = 4 * P;                          // RAW classes
+  const uint32_t cand_bytes = (uint32_t)P * n_groups * 8 * 8;   // RAW: one parity of the candidate buffer
 
   // ---- one-time setup: weights -> smem images, barriers, TMEM --------------------------------
   {
@@ -213,7 +221,19 @@ __global__ void __launch_bounds__(NT, 1) wrnn_tc_kernel(const TcParams p) {
       float ur[11];
 #pragma unroll
       for (int i = 0; i < 11; ++i) ur[i] = 0.5f;
-      if (owns_fold) {
+      float ex[4] = {1.f, 1.f, 1.f, 1.f};                 // RAW: Exp(1) draws of this CTA's 4 classes
+      if constexpr (RAW) {
+        if (owns_fold) {
+          if (p.expo) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(p.expo + ((size_t)t * p.n_total + p.f0 + fold) * NCLS + u0));
+            ex[0] = v.x; ex[1] = v.y; ex[2] = v.z; ex[3] = v.w;
+          } else {                                        // same keying as the SIMT engine: block 16 + class/4
+            const Philox4 r = philox4x32_10((unsigned)t, (unsigned)(p.seg_first + p.f0 + fold), 16u + (unsigned)cta,
+                                            (unsigned)p.offset, (unsigned)p.seed, (unsigned)(p.seed >> 32));
+            ex[0] = -logf(u01(r.x)); ex[1] = -logf(u01(r.y)); ex[2] = -logf(u01(r.z)); ex[3] = -logf(u01(r.w));
+          }
+        }
+      } else if (owns_fold) {
         if (p.uniforms) {
           const float* u = p.uniforms + (size_t)t * 11 * p.n_total;
 #pragma unroll
@@ -304,8 +324,8 @@ __global__ void __launch_bounds__(NT, 1) wrnn_tc_kernel(const TcParams p) {
       }
       if (profiling) { const long long c = clock64(); tprof[3] += c - tp0; tp0 = c; }
 
-      // ---- E: logits = F3 y2 + b3, MoL sample (replicated in every CTA) -----------------------------
-      {
+      // ---- E: logits = F3 y2 + b3, sample ---------------------------------------------------------------
+      if constexpr (!RAW) {                                 // MoL: fc3 + sampler replicated in every CTA
         mbar_wait(bar_mma, n_mma & 1, p.abort_flag); ++n_mma;
         tc_fence_after();
         float lg[32];
@@ -321,6 +341,45 @@ __global__ void __launch_bounds__(NT, 1) wrnn_tc_kernel(const TcParams p) {
             for (int i = 0; i < 30; ++i) p.logits_out[((size_t)t * p.n_total + p.f0 + fold) * 30 + i] = lg[i];
           }
         }
+      } else {                                              // RAW: this CTA's 4 classes, then the candidate exchange
+        mbar_wait(bar_mma, n_mma & 1, p.abort_flag); ++n_mma;
+        tc_fence_after();
+        float lg[4];
+        tmem_ld_sum<4, KW>(tlane + TC_F3, N_F3, lg);
+        float best = -INFINITY; int bestk = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          lg[i] += b3[i];
+          const float sc = lg[i] - __logf(ex[i]);
+          if (sc > best) { best = sc; bestk = u0 + i; }
+        }
+        unsigned char* cand_out = p.xch5 + (size_t)par * cand_bytes;
+        if (owns_fold) {
+          *reinterpret_cast<uint2*>(cand_out + ((size_t)cta * n_groups * 8 + fold) * 8) = make_uint2(__float_as_uint(best), (unsigned)bestk);
+          if (p.logits_out)
+            *reinterpret_cast<float4*>(p.logits_out + ((size_t)t * p.n_total + p.f0 + fold) * NCLS + u0) = make_float4(lg[0], lg[1], lg[2], lg[3]);
+        }
+        signal(4);
+        // every CTA reduces the 128 candidates of each fold the same way; the two half-warps split the CTAs
+        mbar_wait(bar_g, (uint32_t)((GPS * t + 4) & 1), p.abort_flag);
+        const uint2* cand = reinterpret_cast<const uint2*>(smem + OFF_A);
+        const int fr = warp * 16 + (lane & 15), c0 = (lane >> 4) * (P / 2);
+        best = -INFINITY; bestk = 0x7fffffff;
+        if (fr < n_groups * 8) {
+#pragma unroll 8
+          for (int c = c0; c < c0 + P / 2; ++c) {
+            const uint2 v = cand[c * n_groups * 8 + fr];
+            const float sc = __uint_as_float(v.x);
+            if (sc > best) { best = sc; bestk = (int)v.y; }        // ascending class order: first maximum wins
+          }
+        }
+        {
+          const float ob = __shfl_xor_sync(0xffffffffu, best, 16);
+          const int ok = __shfl_xor_sync(0xffffffffu, bestk, 16);
+          if (ob > best || (ob == best && ok < bestk)) { best = ob; bestk = ok; }
+        }
+        x = 2.0f * (float)bestk / ((float)NCLS - 1.0f) - 1.0f;     // :235
+        if (owns_fold && cta == 0) p.out[(size_t)(p.f0 + fold) * p.out_pitch + t] = x;
       }
       if (profiling) { tprof[4] += clock64() - tp0; }
       // no early exit on abort: every wait is bounded and fails fast once the abort flag is up, and the
@@ -351,14 +410,14 @@ __global__ void __launch_bounds__(NT, 1) wrnn_tc_kernel(const TcParams p) {
 
     // D[64 folds, N] (+)= A[64, 16] * B[N, 16]^T per instruction; K advances by two core-matrix columns
     // (256 B => +16 in the descriptor's address field; no carry: every image ends below 256 KB)
-    auto launch = [&](int v, unsigned target, const unsigned char* img) {      // leader only
+    auto launch = [&](int v, unsigned target, const unsigned char* img, uint32_t bytes) {      // leader only
       long long c0 = 0;
       if (profiling) c0 = clock64();
       if (lane == 0) counter_wait(p.counters + v, target, p.abort_flag);        // acquire: all 128 producers have published
       __syncwarp();
       proxy_fence_global();                                                     // generic-proxy writes -> async-proxy (TMA) read
       if (profiling) t_poll += clock64() - c0;
-      tma_bulk_g2s(sA, img, img_bytes, bar_g);
+      tma_bulk_g2s(sA, img, bytes, bar_g);
     };
     auto quarter = [&](uint64_t db, uint32_t d_col, uint32_t idesc) {
       long long c0 = 0, c1 = 0;
@@ -497,9 +556,9 @@ __global__ void __launch_bounds__(NT, 1) wrnn_tc_kernel(const TcParams p) {
       const int par = t & 1;
       const unsigned target = (unsigned)P * (unsigned)(t + 1);
       const unsigned char* base = p.xch + (size_t)par * img_bytes;
-      if (leader) launch(0, target, base + 0 * xch_stride);
+      if (leader) launch(0, target, base + 0 * xch_stride, img_bytes);
       quarter(dS1, TC_S1 + q * N_S1, idesc_s1);
-      if (leader) launch(1, target, base + 1 * xch_stride);
+      if (leader) launch(1, target, base + 1 * xch_stride, img_bytes);
       quarter(dS2, TC_S2 + q * N_S2, idesc_s2);
       if (t + 1 < S) {
         // Conditioning of step t+1: queued behind S2 in the tensor pipe.  (Measured: placing this block after
@@ -510,10 +569,16 @@ __global__ void __launch_bounds__(NT, 1) wrnn_tc_kernel(const TcParams p) {
         if (q == 1) cond_chain(par ? TC_Q0 : TC_Q1);
         if (t + 2 < S) cond_fetch(t + 2);
       }
-      if (leader) launch(2, target, base + 2 * xch_stride);
+      if (leader) launch(2, target, base + 2 * xch_stride, img_bytes);
       quarter(dS3, TC_S3 + q * N_S3, idesc_s3);
-      if (leader) launch(3, target, base + 3 * xch_stride);
+      if (leader) launch(3, target, base + 3 * xch_stride, img_bytes);
       quarter(dF3, TC_F3 + q * N_F3, idesc_f3);
+      if constexpr (RAW) {
+        // fifth exchange: the per-CTA (score, class) candidates land in the (now idle) activation buffer; the fold
+        // warps wait on bar_g themselves, the issuers only keep their phase count in step
+        if (leader) launch(4, target, p.xch5 + (size_t)par * cand_bytes, cand_bytes);
+        mbar_wait(bar_g, n_g & 1, p.abort_flag); ++n_g;
+      }
     }
     if (profiling) { p.prof[5] = t_poll; p.prof[6] = t_gather; p.prof[7] = t_issue; }
   }
@@ -536,14 +601,18 @@ class TcEngine : public Engine {
   const char* name() const override { return cfg.precision == WRNN_PREC_BF16 ? "tcgen05-bf16" : "tcgen05-fp16"; }
   int grid_ctas() const override { return P; }
   // FRAMES = conditioning rows built in the kernel from frame-rate tensors (wrnn_job::mel_frames)
+  template <int FMT, bool FR>
+  const void* kernel_of() const {
+    return cfg.mode == WRNN_MODE_RAW ? (const void*)wrnn_tc_kernel<FMT, FR, true> : (const void*)wrnn_tc_kernel<FMT, FR, false>;
+  }
   const void* kernel(bool frames) const {
-    if (cfg.precision == WRNN_PREC_BF16) return frames ? (const void*)wrnn_tc_kernel<1, true> : (const void*)wrnn_tc_kernel<1, false>;
-    return frames ? (const void*)wrnn_tc_kernel<0, true> : (const void*)wrnn_tc_kernel<0, false>;
+    if (cfg.precision == WRNN_PREC_BF16) return frames ? kernel_of<1, true>() : kernel_of<1, false>();
+    return frames ? kernel_of<0, true>() : kernel_of<0, false>();
   }
 
   int init(const HostWeights& w) {
     Folded f; fold(w, f);
-    const bool bf = cfg.precision == WRNN_PREC_BF16;
+    const bool bf = cfg.precision == WRNN_PREC_BF16, raw = cfg.mode == WRNN_MODE_RAW;
     auto cvt = [&](double v) -> uint16_t { return bf ? f2bf((float)v) : f2h((float)v); };
     std::vector<unsigned char> blob((size_t)WEIGHT_BYTES * P, 0);
     CtaSlice s;
@@ -560,19 +629,22 @@ class TcEngine : public Engine {
         for (int r = 0; r < 7 * U; ++r) s1[img_index(r, k, H)] = cvt(s.S1[(size_t)r * H + k]);
         for (int r = 0; r < 4 * U; ++r) s2[img_index(r, k, H)] = cvt(s.S2[(size_t)r * H + k]);
         for (int r = 0; r < U; ++r) s3[img_index(r, k, H)] = cvt(s.S3[(size_t)r * H + k]);
-        for (int r = 0; r < cfg.n_classes; ++r) f3[img_index(r, k, H)] = cvt(w.f3w[(size_t)r * H + k]);
+        if (raw) { for (int r = 0; r < U; ++r) f3[img_index(r, k, H)] = cvt(w.f3w[(size_t)(c * U + r) * H + k]); }
+        else for (int r = 0; r < cfg.n_classes; ++r) f3[img_index(r, k, H)] = cvt(w.f3w[(size_t)r * H + k]);
       }
       for (int k = 0; k < CDIM; ++k)
         for (int r = 0; r < 8 * U; ++r) q[img_index(r, k, CDIM)] = cvt(s.Q[(size_t)r * CDIM + k]);
       for (int r = 0; r < 8 * U; ++r) { fv[r] = s.qk[r]; fv[32 + r] = s.vq[r]; }
       for (int r = 0; r < 3 * U; ++r) { fv[64 + r] = s.b1h[r]; fv[76 + r] = s.b2h[r]; }
-      for (int r = 0; r < cfg.n_classes; ++r) fv[88 + r] = w.f3b[r];
+      if (raw) { for (int r = 0; r < U; ++r) fv[88 + r] = w.f3b[c * U + r]; }
+      else for (int r = 0; r < cfg.n_classes; ++r) fv[88 + r] = w.f3b[r];
     }
     WRNN_CUDA_OK(cudaMalloc(&d_blob_, blob.size()));
     WRNN_CUDA_OK(cudaMemcpy(d_blob_, blob.data(), blob.size(), cudaMemcpyHostToDevice));
     WRNN_CUDA_OK(cudaMalloc(&d_sync_, 256));
     WRNN_CUDA_OK(cudaMemset(d_sync_, 0, 256));
-    scratch_bytes_ = (size_t)4 * 2 * 8 * SBO_H;          // 4 vectors x 2 parities x (up to 8 row groups)
+    xch5_off_ = (size_t)4 * 2 * 8 * SBO_H;               // 4 vectors x 2 parities x (up to 8 row groups)
+    scratch_bytes_ = xch5_off_ + (size_t)2 * P * MT * 8;   // + RAW candidates: 2 parities x 128 CTAs x 64 folds x 8 B
     WRNN_CUDA_OK(cudaMalloc(&d_scratch_, scratch_bytes_));
     WRNN_CUDA_OK(cudaFuncSetAttribute(kernel(false), cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     WRNN_CUDA_OK(cudaFuncSetAttribute(kernel(true), cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
@@ -582,7 +654,10 @@ class TcEngine : public Engine {
     return WRNN_OK;
   }
 
-  static bool supports_cfg(const wrnn_cfg& c) { return c.mode == WRNN_MODE_MOL && c.n_classes == 30 && c.precision != WRNN_PREC_FP32; }
+  static bool supports_cfg(const wrnn_cfg& c) {
+    if (c.precision == WRNN_PREC_FP32) return false;
+    return (c.mode == WRNN_MODE_MOL && c.n_classes == 30) || (c.mode == WRNN_MODE_RAW && c.n_classes == 4 * P);
+  }
   bool supports(const wrnn_job&) const override { return true; }   // any fold count: tiles of 64 folds, one launch each
 
   int generate(const wrnn_job& job, cudaStream_t stream) override {
@@ -592,11 +667,12 @@ class TcEngine : public Engine {
     p.mels_up = job.mels_up; p.aux = job.aux; p.L = job.L; p.seg_stride = job.seg_stride;
     p.n_seg = job.n_seg; p.steps = job.steps > 0 ? job.steps : job.seg_len; p.out_pitch = p.steps;
     p.seg_first = job.seg_first;
-    p.uniforms = job.uniforms; p.seed = job.philox_seed; p.offset = job.philox_offset;
+    p.uniforms = job.uniforms; p.expo = job.expo; p.seed = job.philox_seed; p.offset = job.philox_offset;
     p.out = job.out; p.x_force = job.x_force; p.logits_out = job.logits_out;
     p.fold_row0 = reinterpret_cast<const long long*>(job.fold_row0); p.fold_row_end = reinterpret_cast<const long long*>(job.fold_row_end);
     p.mel_frames = job.mel_frames; p.aux_frames = job.aux_frames; p.up_taps = job.up_taps; p.hop = job.hop;
     p.xch = static_cast<unsigned char*>(d_scratch_);
+    p.xch5 = p.xch + xch5_off_;
     p.counters = static_cast<unsigned*>(d_sync_);
     p.abort_flag = reinterpret_cast<int*>(static_cast<unsigned*>(d_sync_) + 8);
     p.prof = reinterpret_cast<long long*>(static_cast<unsigned char*>(d_sync_) + 64);
@@ -672,7 +748,7 @@ class TcEngine : public Engine {
  private:
   void *d_blob_ = nullptr, *d_scratch_ = nullptr, *d_sync_ = nullptr;
   void* d_cond_ = nullptr; size_t cond_bytes_ = 0;   // WRNN_COND_EXPAND: one tile's conditioning rows ([rows, 80] then [rows, 128])
-  size_t scratch_bytes_ = 0;
+  size_t scratch_bytes_ = 0, xch5_off_ = 0;
   int last_steps_ = 0;
 };
 
@@ -680,7 +756,7 @@ class TcEngine : public Engine {
 
 int make_tc_engine(const wrnn_cfg& cfg, const HostWeights& w, int device, Engine** out) {
   if (!TcEngine::supports_cfg(cfg)) {
-    set_error("tcgen05 engine (this build) serves the MoL head with fp16/bf16 operands");
+    set_error("tcgen05 engine serves the MoL head (30 classes) and the 9-bit RAW head (512 classes) with fp16/bf16 operands");
     return WRNN_E_INVALID;
   }
   TcEngine* e = new TcEngine();

@@ -259,8 +259,8 @@ class WaveRNN(nn.Module):
         return self._taps
 
     def _kernel_conditioning_ok(self) -> bool:
-        return (self.gen_conditioning == 'kernel' and self.mode == 'MOL' and self.gen_precision != 'fp32'
-                and self.gen_engine in ('auto', 'tcgen05'))
+        return (self.gen_conditioning == 'kernel' and self.gen_precision != 'fp32'
+                and self.gen_engine in ('auto', 'tcgen05') and (self.mode == 'MOL' or self.n_classes == 512))
 
     # ------------------------------------------------------------------ randomness
     def _reference_draws(self, geo: FoldGeometry, steps: int, reuse_buffer: bool = False):
@@ -380,6 +380,7 @@ class WaveRNN(nn.Module):
             engine.generate(mels_up=0, aux=0, L=T * self.hop_length, n_seg=shard.n_seg, seg_len=geo.seg_len,
                             seg_stride=geo.seg_stride, out=out.data_ptr(), seg_first=shard.seg_first, steps=steps,
                             uniforms=uniforms.data_ptr() if uniforms is not None else 0,
+                            expo=expo.data_ptr() if expo is not None else 0,
                             philox_seed=int(self.gen_philox_seed), mel_frames=mel_fr.data_ptr(),
                             aux_frames=aux_fr.data_ptr(), up_taps=taps.data_ptr(), hop=self.hop_length,
                             cond_mode=int(self.gen_cond_mode), stream=torch.cuda.current_stream(device).cuda_stream)
