@@ -169,6 +169,20 @@ const char *wrnn_engine_name(const wrnn_t *h);
 int wrnn_grid_ctas(const wrnn_t *h);
 int64_t wrnn_launch_count(const wrnn_t *h);
 
+/* The tail of generate() on the device (fatchord_version.py:243-258, :342-405; utils/dsp.py:98-103): float64
+ * mu-law expansion, cross-fade + overlap-add of the folds, final fade-out -- one HBM-bound pass, asynchronous on
+ * `stream`.  All pointers are DEVICE pointers.
+ *   samples [n_seg, seg_len] fp32 as written by wrnn_generate (after the all-gather on multi-GPU jobs)
+ *   fade_in / fade_out [overlap] float64: the windows of xfade_and_unfold (:385-391); NULL with overlap = 0 (unbatched)
+ *   mu_table [n_classes] float64 or NULL: expansion of label k (RAW head with mu_law)
+ *   tail [tail_len] float64 or NULL: linspace(1, 0, 20*hop) applied to the last tail_len samples (:255-258)
+ *   wav [wave_len] float64
+ * The tables are built by the caller with the reference's own numpy expressions, so the result is bit-identical
+ * to the host epilogue (multiplications and additions in the reference's order, folds ascending).            */
+int wrnn_epilogue(const float *samples, int32_t n_seg, int32_t seg_len, int64_t seg_stride, int32_t overlap,
+                  const double *fade_in, const double *fade_out, const double *mu_table, int32_t n_classes,
+                  const double *tail, int64_t tail_len, int64_t wave_len, double *wav, void *stream);
+
 /* Host helper for parity mode: replays torch's default CPU generator (MT19937) natively, so the
  * draws the reference makes before / inside its loop cost a few ms instead of ~30.
  *   state : the generator's 624 words and its position `pos` in [0, 624] (624 = block exhausted)

@@ -284,3 +284,18 @@ def test_conditioning_pre_pass_and_in_kernel_rows_are_bit_identical(mol):
     model.gen_cond_mode = cabi.COND_AUTO
     assert np.array_equal(wavs[cabi.COND_EXPAND], wavs[cabi.COND_IN_KERNEL])
     assert np.array_equal(wavs[cabi.COND_EXPAND], wavs[cabi.COND_AUTO])
+
+
+@pytest.mark.parametrize("mode,batched,mu_law", [("MOL", True, False), ("MOL", False, False), ("RAW", True, True), ("RAW", True, False)])
+def test_device_epilogue_is_bit_identical_to_the_host_epilogue(mode, batched, mu_law):
+    """wrnn_epilogue (mu-law expansion, cross-fade + overlap-add, fade-out; float64 on the device)
+    against the numpy restatement of fatchord_version.py:243-258 on the same samples."""
+    model = helpers.make_model(0, mode, "cuda")
+    model.gen_rng = "philox"
+    mel = helpers.make_mel(33, 2)
+    wavs = {}
+    for where in ("device", "host"):
+        model.gen_epilogue = where
+        wavs[where] = model.generate(mel, None, batched, 2750, 275, mu_law)
+    assert wavs["device"].dtype == np.float64 and wavs["device"].shape == wavs["host"].shape == ((33 - 1) * 275,)
+    assert np.array_equal(wavs["device"], wavs["host"])

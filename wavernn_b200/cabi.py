@@ -21,7 +21,7 @@ ABI_VERSION = 4
 
 EXPORTS = ("wrnn_abi_version", "wrnn_last_error", "wrnn_create", "wrnn_destroy", "wrnn_generate",
            "wrnn_check", "wrnn_generate_host", "wrnn_engine_name", "wrnn_grid_ctas", "wrnn_launch_count",
-           "wrnn_mt19937_uniform")
+           "wrnn_mt19937_uniform", "wrnn_epilogue")
 
 _fp = C.POINTER(C.c_float)
 
@@ -93,6 +93,9 @@ def load() -> C.CDLL:
     lib.wrnn_grid_ctas.argtypes = [C.c_void_p]
     lib.wrnn_launch_count.restype = C.c_int64
     lib.wrnn_launch_count.argtypes = [C.c_void_p]
+    lib.wrnn_epilogue.restype = C.c_int
+    lib.wrnn_epilogue.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p,
+                                  C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]
     lib.wrnn_mt19937_uniform.restype = C.c_int32
     lib.wrnn_mt19937_uniform.argtypes = [C.c_void_p, C.c_int32, C.c_uint64, C.c_void_p, C.c_uint64, C.c_float, C.c_float]
     if lib.wrnn_abi_version() != ABI_VERSION:
@@ -182,6 +185,14 @@ class Engine:
 def _torch():
     import torch
     return torch
+
+
+def epilogue(*, samples: int, n_seg: int, seg_len: int, seg_stride: int, overlap: int, fade_in: int, fade_out: int,
+             mu_table: int, n_classes: int, tail: int, tail_len: int, wave_len: int, wav: int, stream: int = 0):
+    """wrnn_epilogue with raw device addresses (ints; 0 = NULL).  Asynchronous on `stream`."""
+    lib = load()
+    _check(lib, lib.wrnn_epilogue(samples, n_seg, seg_len, seg_stride, overlap, fade_in or None, fade_out or None,
+                                  mu_table or None, n_classes, tail or None, tail_len, wave_len, wav, stream or None))
 
 
 # ---------------------------------------------------------------------------------------------

@@ -106,17 +106,16 @@ struct TcParams {
 // conditioning pre-pass (WRNN_COND_EXPAND): rows [r_lo, r_lo + n_rows) of the per-sample conditioning
 // stream from the frame-rate tensors -- the whole UpsampleNetwork tail (three stretch+conv stages as a
 // 5-tap table, aux as a nearest repeat; reference fatchord_version.py:73-88) as one HBM-bound pass.
-// One thread per float4 of a row (20 of mel, 32 of aux); 832 B written per row, the frames come from L2.
+// One thread per float4 of a row (20 of mel, 32 of aux), 8 rows per block pass; 832 B written per row, frames from L2.
 // The tap sum uses the same fmaf order as the in-kernel staging, so both modes give identical rows.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) wrnn_expand_rows_kernel(const float* __restrict__ mel_frames, const float* __restrict__ aux_frames,
-                                                               const float* __restrict__ taps, int hop, long long r_lo, long long n_rows,
-                                                               float* __restrict__ m_out, float* __restrict__ a_out) {
-  constexpr int QM = FEAT / 4, QA = 4 * AUXD / 4, QR = QM + QA;
-  const long long total = n_rows * QR;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const long long rl = i / QR;
-    const int q = (int)(i - rl * QR);
+constexpr int XP_ROWS = 8, XP_Q = CDIM / 4, XP_THREADS = XP_ROWS * XP_Q;      // 8 rows x 52 float4 per block pass
+__global__ void __launch_bounds__(XP_THREADS) wrnn_expand_rows_kernel(const float* __restrict__ mel_frames, const float* __restrict__ aux_frames,
+                                                                      const float* __restrict__ taps, int hop, long long r_lo, long long n_rows,
+                                                                      float* __restrict__ m_out, float* __restrict__ a_out) {
+  constexpr int QM = FEAT / 4;
+  const int rr = threadIdx.x / XP_Q, q = threadIdx.x - rr * XP_Q;            // row within the pass, float4 within the row
+  for (long long rl = (long long)blockIdx.x * XP_ROWS + rr; rl < n_rows; rl += (long long)gridDim.x * XP_ROWS) {
     const unsigned r = (unsigned)(r_lo + rl);
     const unsigned fr = r / (unsigned)hop, ph = r - fr * (unsigned)hop;
     if (q >= QM) {
@@ -706,9 +705,9 @@ class TcEngine : public Engine {
         float* m_out = static_cast<float*>(d_cond_);
         float* a_out = m_out + (size_t)(cond_bytes_ / (CDIM * sizeof(float))) * FEAT;
         if (n_rows > 0) {
-          const long long blocks = (n_rows * (CDIM / 4) + 255) / 256;
-          const int grid = (int)(blocks < 148 * 16 ? blocks : 148 * 16);
-          wrnn_expand_rows_kernel<<<grid, 256, 0, stream>>>(job.mel_frames, job.aux_frames, job.up_taps, job.hop, r_lo, n_rows, m_out, a_out);
+          const long long blocks = (n_rows + XP_ROWS - 1) / XP_ROWS;
+          const int grid = (int)(blocks < 148 * 8 ? blocks : 148 * 8);
+          wrnn_expand_rows_kernel<<<grid, XP_THREADS, 0, stream>>>(job.mel_frames, job.aux_frames, job.up_taps, job.hop, r_lo, n_rows, m_out, a_out);
           WRNN_CUDA_OK(cudaGetLastError());
           ++launches;
         }

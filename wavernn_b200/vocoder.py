@@ -152,6 +152,7 @@ class WaveRNN(nn.Module):
         self.gen_native_rng = True      # replay torch's CPU generator natively (self-checked; False = torch operators)
         self._draw_buf = None
         self.gen_upsample_chunk = 2048  # mel frames per UpsampleNetwork call (bounds HBM intermediates)
+        self.gen_epilogue = 'device'      # 'device': wrnn_epilogue (xfade / overlap-add / fade-out in one pass) | 'host': numpy
         self.gen_conditioning = 'kernel'  # 'kernel': frame-rate tensors go to the library, which forms the rows (tcgen05 engine)
         #                                   'torch' : materialise UpsampleNetwork's (T*hop, 208) output like the reference
         self.gen_cond_mode = 0            # cabi.COND_AUTO | COND_EXPAND (HBM-rate pre-pass per tile) | COND_IN_KERNEL
@@ -332,9 +333,7 @@ class WaveRNN(nn.Module):
                 out_all = gather_segments(out_local, shard, geo)
             else:
                 out_all = out_local
-            output = out_all.cpu().numpy().astype(np.float64)                    # :243-245
-
-        wav = self._epilogue(output, geo, batched, wave_len, mu_law)
+            wav = self._finish(out_all, geo, batched, wave_len, mu_law)          # :243-258
         if save_path is not None and rank == 0:                                  # one writer per job
             save_wav(wav, save_path, self.sample_rate)                           # :260
         self.train()                                                             # :262
@@ -416,6 +415,45 @@ class WaveRNN(nn.Module):
                               conditioning='torch')
         del m_up, aux, uniforms, expo, xf
         return (out, logits) if want_logits else out
+
+    def _finish(self, samples: torch.Tensor, geo: FoldGeometry, batched, wave_len, mu_law) -> np.ndarray:
+        """(n_seg, S) fp32 samples -> float64 waveform: on the device (`gen_epilogue='device'`, wrnn_epilogue: one pass,
+        bit-identical to the host version by construction) or with the host numpy restatement of :243-258."""
+        if (self.gen_epilogue == 'device' and samples.is_cuda and wave_len >= 20 * self.hop_length
+                and (not batched or geo.overlap > 0)):
+            tabs = self._epilogue_tables(geo, batched, mu_law, samples.device)
+            wav = torch.empty(wave_len, dtype=torch.float64, device=samples.device)
+            samples = samples.contiguous()
+            p = lambda t: 0 if t is None else t.data_ptr()
+            cabi.epilogue(samples=samples.data_ptr(), n_seg=samples.shape[0], seg_len=samples.shape[1],
+                          seg_stride=geo.seg_stride, overlap=geo.overlap if batched else 0, fade_in=p(tabs['fade_in']),
+                          fade_out=p(tabs['fade_out']), mu_table=p(tabs['mu']), n_classes=self.n_classes,
+                          tail=p(tabs['tail']), tail_len=20 * self.hop_length, wave_len=wave_len, wav=wav.data_ptr(),
+                          stream=torch.cuda.current_stream(samples.device).cuda_stream)
+            return wav.cpu().numpy()
+        output = samples.cpu().numpy().astype(np.float64)                        # :243-245
+        return self._epilogue(output, geo, batched, wave_len, mu_law)
+
+    def _epilogue_tables(self, geo: FoldGeometry, batched, mu_law, device):
+        """float64 weight tables of the epilogue, built with the reference's own numpy expressions (:255, :379-391,
+        utils/dsp.py:98-103) and cached on the device."""
+        key = (geo.overlap if batched else 0, bool(mu_law), self.n_classes, self.hop_length, str(device))
+        if getattr(self, '_ep_key', None) != key:
+            to = lambda a: None if a is None else torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(device)
+            fade_in = fade_out = mu = None
+            if key[0] > 0:
+                silence_len = key[0] // 2
+                t = np.linspace(-1, 1, key[0] - silence_len, dtype=np.float64)
+                fade_in = np.concatenate([np.zeros(silence_len), np.sqrt(0.5 * (1 + t))])
+                fade_out = np.concatenate([np.ones(silence_len), np.sqrt(0.5 * (1 - t))])
+            if mu_law:      # the kernel's samples are x_k = 2k/(n-1) - 1 in fp32 (:235): expand exactly those values
+                n = self.n_classes
+                x32 = np.float32(2) * np.arange(n, dtype=np.float32) / np.float32(n - 1) - np.float32(1)
+                mu = decode_mu_law(x32.astype(np.float64), n, False)
+            self._ep_tabs = dict(fade_in=to(fade_in), fade_out=to(fade_out), mu=to(mu),
+                                 tail=to(np.linspace(1, 0, 20 * self.hop_length)))
+            self._ep_key = key
+        return self._ep_tabs
 
     def _epilogue(self, output: np.ndarray, geo: FoldGeometry, batched, wave_len, mu_law) -> np.ndarray:
         """numpy float64 tail of the reference (:247-258)."""
@@ -499,10 +537,9 @@ class WaveRNN(nn.Module):
                 engine.check()
             if world > 1:
                 out = gather_segments(out, shard, job)
-            samples = out.cpu().numpy().astype(np.float64)
         wavs, f0 = [], 0
         for g, wl, path in zip(geos, wave_lens, save_paths):
-            wav = self._epilogue(samples[f0:f0 + g.n_seg].copy(), g, True, wl, False)
+            wav = self._finish(out[f0:f0 + g.n_seg], g, True, wl, False)
             f0 += g.n_seg
             if path is not None and rank == 0:
                 save_wav(wav, path, self.sample_rate)
