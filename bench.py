@@ -194,7 +194,7 @@ def run_reference_arm(args):
             "cpu_baseline": {"value": value, "unit": "samples/s", "cores": r["cores"], "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "x_realtime": value / 22050.0}
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------
@@ -211,7 +211,6 @@ def run_ours(args):
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG", "WARN")       # keep NCCL's version banner off stdout (one JSON line only)
         dist.init_process_group("nccl", device_id=device)
 
     cfg3 = args.workload == "cfg3"                     # BASELINE configs[2]: cfg2's mel with the 9-bit RAW head (mu-law)
@@ -347,12 +346,33 @@ def run_ours(args):
             line["cpu_baseline"] = cpu
         if args.seg_steps or args.skip_e2e:
             line["partial"] = "profiling run (--seg-steps/--skip-e2e): NOT a bench value"
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_JSON_OUT = None
+
+
+def guard_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries below us write there too (NCCL prints its version banner
+    to fd 1 whenever NCCL_DEBUG is VERSION/WARN/INFO in the environment): keep a private handle on the real stdout
+    for the JSON line and point fd 1 at stderr for everything else."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    guard_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
