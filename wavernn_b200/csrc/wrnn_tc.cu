@@ -23,11 +23,11 @@
 // identical samples), which removes the fifth exchange of the step.
 //
 // Warp roles (no CTA-wide barrier inside the step loop):
-//   warps 0-3  fold warps   : TMEM -> registers (sum of the K-quarter partials), gates / relu / sampler, publish, signal
-//   warp  4    driver       : polls arrival counters, launches the TMA gather, issues every
-//                             tcgen05.mma chain (warp-uniform, elect.sync-predicated)
-//   warps 5-7  cond stagers : stream cond_{t+1} HBM -> registers -> fp16 operand image, one
-//                             step ahead of the recurrence
+//   warps 0-3  fold warps : TMEM -> registers (sum of the K-quarter partials), gates / relu / sampler, publish, signal
+//   warps 4-7  issuers    : warp 4+q owns the K quarter [128q, 128q+128) of every K=512 chain (8 tcgen05.mma each,
+//                           warp-uniform, elect.sync-predicated, own accumulator columns).  Warp 4 also polls the
+//                           arrival counters and launches the TMA gathers; warp 5 issues the conditioning chain; all
+//                           four stream cond_{t+1} HBM -> registers (a step ahead) -> fp16 operand image.
 //
 // One launch serves a tile of <= 64 folds (one M tile); larger jobs run tile after tile.
 // RAW 9-bit head (template RAW; reference :231-237): fc3 has 512 = 4 x 128 rows, so CTA c owns classes
@@ -59,7 +59,6 @@ constexpr int KC = H / 8;          // 64 16-byte chunks per activation row
 constexpr int SBO_H = KC * 128;    // 8192: byte stride between 8-row groups, K = 512 images
 constexpr int KQ = CDIM / 8;       // 26 chunks per conditioning row
 constexpr int SBO_Q = KQ * 128;    // 3328
-constexpr int N_STAGERS = 96;      // threads of warps 5-7
 
 constexpr int N_S1 = 32, N_S2 = 16, N_S3 = 8, N_F3 = 32, N_Q = 32;
 // shared memory map (bytes)
