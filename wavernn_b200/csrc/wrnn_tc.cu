@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(XP_THREADS) wrnn_expand_rows_kernel(const floa
 // ------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------
-template <int FMT, bool FRAMES, bool RAW, int CL>
+template <int FMT, bool FRAMES, bool RAW>
 __global__ void __launch_bounds__(NT, 1) wrnn_tc_kernel(const TcParams p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const float* fv = reinterpret_cast<const float*>(smem + OFF_VEC);
@@ -415,11 +415,7 @@ __global__ void __launch_bounds__(NT, 1) wrnn_tc_kernel(const TcParams p) {
       __syncwarp();
       proxy_fence_global();                                                     // generic-proxy writes -> async-proxy (TMA) read
       if (profiling) t_poll += clock64() - c0;
-      if constexpr (CL == 1) tma_bulk_g2s(sA, img, bytes, bar_g);
-      else {                                                                    // this CTA's slice -> all CL CTAs of the cluster
-        const uint32_t slice = bytes / CL, off = cluster_ctarank() * slice;
-        tma_bulk_g2s_multicast(sA + off, img + off, slice, bytes, bar_g, (uint16_t)((1u << CL) - 1u));
-      }
+      tma_bulk_g2s(sA, img, bytes, bar_g);
     };
     auto quarter = [&](uint64_t db, uint32_t d_col, uint32_t idesc) {
       long long c0 = 0, c1 = 0;
@@ -587,7 +583,6 @@ __global__ void __launch_bounds__(NT, 1) wrnn_tc_kernel(const TcParams p) {
 
   tc_fence_before();
   __syncthreads();
-  if constexpr (CL > 1) cluster_sync_all();             // no CTA leaves while a peer may still multicast into it
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "n"(TMEM_COLS));
 }
 
@@ -604,18 +599,13 @@ class TcEngine : public Engine {
   const char* name() const override { return cfg.precision == WRNN_PREC_BF16 ? "tcgen05-bf16" : "tcgen05-fp16"; }
   int grid_ctas() const override { return P; }
   // FRAMES = conditioning rows built in the kernel from frame-rate tensors (wrnn_job::mel_frames)
-  // CL = thread-block cluster size: with CL > 1 every gather is 1/CL of the image per CTA, multicast to the cluster
   template <int FMT, bool FR>
-  const void* kernel_of(int cl) const {
-    if constexpr (!FR) {
-      if (cl == 4) return cfg.mode == WRNN_MODE_RAW ? (const void*)wrnn_tc_kernel<FMT, false, true, 4> : (const void*)wrnn_tc_kernel<FMT, false, false, 4>;
-      if (cl == 2) return cfg.mode == WRNN_MODE_RAW ? (const void*)wrnn_tc_kernel<FMT, false, true, 2> : (const void*)wrnn_tc_kernel<FMT, false, false, 2>;
-    }
-    return cfg.mode == WRNN_MODE_RAW ? (const void*)wrnn_tc_kernel<FMT, FR, true, 1> : (const void*)wrnn_tc_kernel<FMT, FR, false, 1>;
+  const void* kernel_of() const {
+    return cfg.mode == WRNN_MODE_RAW ? (const void*)wrnn_tc_kernel<FMT, FR, true> : (const void*)wrnn_tc_kernel<FMT, FR, false>;
   }
-  const void* kernel(bool frames, int cl = 1) const {
-    if (cfg.precision == WRNN_PREC_BF16) return frames ? kernel_of<1, true>(1) : kernel_of<1, false>(cl);
-    return frames ? kernel_of<0, true>(1) : kernel_of<0, false>(cl);
+  const void* kernel(bool frames) const {
+    if (cfg.precision == WRNN_PREC_BF16) return frames ? kernel_of<1, true>() : kernel_of<1, false>();
+    return frames ? kernel_of<0, true>() : kernel_of<0, false>();
   }
 
   int init(const HostWeights& w) {
@@ -656,22 +646,6 @@ class TcEngine : public Engine {
     WRNN_CUDA_OK(cudaMalloc(&d_scratch_, scratch_bytes_));
     WRNN_CUDA_OK(cudaFuncSetAttribute(kernel(false), cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     WRNN_CUDA_OK(cudaFuncSetAttribute(kernel(true), cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    // optional cluster launch (WRNN_TC_CLUSTER = 2 | 4): multicast gathers; needs P / CL co-resident clusters
-    if (const char* e = getenv("WRNN_TC_CLUSTER")) {
-      const int cl = atoi(e);
-      if (cl == 2 || cl == 4) {
-        WRNN_CUDA_OK(cudaFuncSetAttribute(kernel(false, cl), cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        cudaLaunchConfig_t lc{};
-        lc.gridDim = dim3(P); lc.blockDim = dim3(NT); lc.dynamicSmemBytes = SMEM_BYTES;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = cl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-        lc.attrs = at; lc.numAttrs = 1;
-        int n_clusters = 0;
-        if (cudaOccupancyMaxActiveClusters(&n_clusters, kernel(false, cl), &lc) == cudaSuccess && n_clusters >= P / cl) cluster_ = cl;
-        else cudaGetLastError();
-        fprintf(stderr, "[wrnn_tc] WRNN_TC_CLUSTER=%d: max active clusters %d (need %d) -> cluster size %d\n", cl, n_clusters, P / cl, cluster_);
-      }
-    }
     int n_sm = 0;
     WRNN_CUDA_OK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device));
     if (n_sm < P) { set_error("tcgen05 engine needs >= 128 SMs for its co-resident weight shards"); return WRNN_E_NO_DEVICE; }
@@ -741,18 +715,7 @@ class TcEngine : public Engine {
       }
       WRNN_CUDA_OK(cudaMemsetAsync(d_sync_, 0, 32, stream));                       // arrival counters (the abort flag is sticky)
       void* args[] = {&p};
-      const bool in_kernel_frames = frames && !expand;
-      if (cluster_ > 1 && !in_kernel_frames) {
-        cudaLaunchConfig_t lc{};
-        lc.gridDim = dim3(P); lc.blockDim = dim3(NT); lc.dynamicSmemBytes = SMEM_BYTES; lc.stream = stream;
-        cudaLaunchAttribute at[2];
-        at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = cluster_; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-        at[1].id = cudaLaunchAttributeCooperative; at[1].val.cooperative = 1;
-        lc.attrs = at; lc.numAttrs = 2;
-        WRNN_CUDA_OK(cudaLaunchKernelExC(&lc, kernel(false, cluster_), args));
-      } else {
-        WRNN_CUDA_OK(cudaLaunchCooperativeKernel(kernel(in_kernel_frames), dim3(P), dim3(NT), args, SMEM_BYTES, stream));
-      }
+      WRNN_CUDA_OK(cudaLaunchCooperativeKernel(kernel(frames && !expand), dim3(P), dim3(NT), args, SMEM_BYTES, stream));
       ++launches;
     }
     last_steps_ = p.steps;
@@ -785,7 +748,6 @@ class TcEngine : public Engine {
   void* d_cond_ = nullptr; size_t cond_bytes_ = 0;   // WRNN_COND_EXPAND: one tile's conditioning rows ([rows, 80] then [rows, 128])
   size_t scratch_bytes_ = 0, xch5_off_ = 0;
   int last_steps_ = 0;
-  int cluster_ = 1;          // thread-block cluster size of the stream kernel (1 = plain cooperative launch)
 };
 
 }  // namespace

@@ -42,19 +42,6 @@ __device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, uint
                "@e cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n\t}\n"
                :: "r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
 }
-// Cluster variant: every CTA of the cluster pulls 1/CL of the image from L2 and multicasts it into the same offset
-// of all CL shared memories (each CTA's own mbarrier, same offset, counts the bytes of all CL slices).
-__device__ __forceinline__ void tma_bulk_g2s_multicast(uint32_t dst, const void* src, uint32_t slice_bytes, uint32_t total_bytes,
-                                                       uint32_t mbar, uint16_t cta_mask) {
-  asm volatile("{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
-               "@e mbarrier.arrive.expect_tx.shared::cta.b64 _, [%3], %4;\n\t"
-               "@e cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %5;\n\t}\n"
-               :: "r"(dst), "l"(src), "r"(slice_bytes), "r"(mbar), "r"(total_bytes), "h"(cta_mask) : "memory");
-}
-__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void proxy_fence_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
