@@ -213,6 +213,8 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
 
+    if args.workload == "cfg4":
+        return run_cfg4(args, device, rank, world, local)
     cfg3 = args.workload == "cfg3"                     # BASELINE configs[2]: cfg2's mel with the 9-bit RAW head (mu-law)
     model = build_model(device, "RAW" if cfg3 else "MOL")
     model.gen_precision, model.gen_engine = args.precision, args.engine
@@ -351,6 +353,69 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_cfg4(args, device, rank, world, local):
+    """BASELINE configs[3] without the text front-end ('16 synthetic mels of 150-800 frames'): the folds of
+    16 utterances vocoded as ONE job through WaveRNN.generate_many (sharded over the ranks, one all-gather).  Tacotron
+    itself is out of scope and stays torch.  The whole call is host-facing, so `value` and `e2e` are the same
+    end-to-end measurement (host mels in, float64 waveforms out), stated in `config`."""
+    import torch.distributed as dist
+    model = build_model(device)
+    model.gen_precision, model.gen_engine, model.gen_rng = args.precision, args.engine, "philox"
+    rs = np.random.RandomState(0)
+    frames = [int(t) for t in rs.randint(150, 801, size=16)]
+    torch.manual_seed(0)
+    mels = [torch.rand(1, 80, T).pin_memory() for T in frames]
+    from wavernn_b200.sharding import fold_geometry
+    S = TARGET + 2 * OVERLAP
+    folds = [fold_geometry(T * HOP, TARGET, OVERLAP).n_seg for T in frames]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(device)
+
+    def step():
+        return model.generate_many(mels, [None] * len(mels), TARGET, OVERLAP, False)
+
+    for _ in range(args.warmup):
+        step()
+    engine = model._get_engine(device)
+    launches0 = engine.launch_count
+    with ClockSampler(local) as clk:
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            wavs = step()
+        barrier()
+        t = time.perf_counter() - t0
+    assert all(np.isfinite(w).all() for w in wavs)
+    tt = torch.tensor([t], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    t = float(tt.item())
+    if rank == 0:
+        units = sum(folds) * S * args.steps
+        value = units / t
+        peaks = measured_peaks()
+        ach_tf = value / world * FLOP_PER_SAMPLE_MOL / 1e12
+        emit({"metric": "audio samples/sec (22.05 kHz) batched MoL generate", "value": value, "unit": "samples/s",
+              "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t / args.steps * 1e3,
+              "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+              "config": {"workload": f"cfg4: 16 synthetic utterances of {min(frames)}-{max(frames)} mel frames ({sum(frames)} frames, "
+                                     f"{sum(frames) * HOP / 22050:.1f} s of audio) -> {sum(folds)} folds x {S} steps in ONE generate_many job, "
+                                     f"sharded over {world} GPU(s); Tacotron not included (torch, out of scope)",
+                         "engine": model.gen_stats.get("engine"), "rng": "in-kernel Philox4x32-10",
+                         "note": "value == e2e: the job is timed end to end through the public call (host mels in, float64 waveforms out)"},
+              "clocks": clk.summary(), "gpu_launches": int(engine.launch_count - launches0),
+              "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": int(sum(frames) * 80 * 4),
+                      "d2h_bytes_per_step": int(sum((T - 1) * HOP for T in frames) * 8), "ms_per_step": t / args.steps * 1e3},
+              "roofline": {"bound": "tensor", "achieved": ach_tf, "peak": peaks["tflops"], "unit": "TFLOP/s",
+                           "frac": ach_tf / peaks["tflops"], "traffic": None, "peak_source": peaks["src"]},
+              "x_realtime": value / 22050.0, "delivered_audio_x_realtime": sum((T - 1) * HOP for T in frames) * args.steps / t / 22050.0})
+    if world > 1:
+        dist.destroy_process_group()
+
+
 _JSON_OUT = None
 
 
@@ -382,7 +447,7 @@ def main():
     ap.add_argument("--engine", default="auto", choices=["auto", "simt", "tcgen05"])
     ap.add_argument("--cpu-sample-steps", type=int, default=3000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg5"],
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg4", "cfg5"],
                     help="cfg2 (default, the headline config: 19 folds per GPU) or cfg5 (4096 folds of a 35.8-min mel, "
                          "sharded over the ranks, in-kernel Philox draws)")
     ap.add_argument("--seg-steps", type=int, default=0,
