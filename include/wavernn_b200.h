@@ -169,6 +169,14 @@ const char *wrnn_engine_name(const wrnn_t *h);
 int wrnn_grid_ctas(const wrnn_t *h);
 int64_t wrnn_launch_count(const wrnn_t *h);
 
+/* The conditioning pre-pass on its own (what WRNN_COND_EXPAND runs per tile): rows [row_lo, row_lo + n_rows) of the
+ * per-sample stream -- mels_up [n_rows, feat], aux [n_rows, 4*aux] -- from the frame-rate tensors of wrnn_job
+ * (same arithmetic, so the rows are bit-identical to the ones a frame-rate job forms internally).  All DEVICE
+ * pointers; asynchronous on `stream`.  mel_frames must hold frames up to (row_lo + n_rows - 1) / hop + 4.
+ * Used by WaveRNN.generate_many to lay several utterances end to end for one job with fold tables.           */
+int wrnn_expand_conditioning(const float *mel_frames, const float *aux_frames, const float *up_taps, int32_t hop,
+                             int64_t row_lo, int64_t n_rows, float *mels_up, float *aux, void *stream);
+
 /* The tail of generate() on the device (fatchord_version.py:243-258, :342-405; utils/dsp.py:98-103): float64
  * mu-law expansion, cross-fade + overlap-add of the folds, final fade-out -- one HBM-bound pass, asynchronous on
  * `stream`.  All pointers are DEVICE pointers.

@@ -21,7 +21,7 @@ ABI_VERSION = 4
 
 EXPORTS = ("wrnn_abi_version", "wrnn_last_error", "wrnn_create", "wrnn_destroy", "wrnn_generate",
            "wrnn_check", "wrnn_generate_host", "wrnn_engine_name", "wrnn_grid_ctas", "wrnn_launch_count",
-           "wrnn_mt19937_uniform", "wrnn_epilogue")
+           "wrnn_mt19937_uniform", "wrnn_epilogue", "wrnn_expand_conditioning")
 
 _fp = C.POINTER(C.c_float)
 
@@ -93,6 +93,9 @@ def load() -> C.CDLL:
     lib.wrnn_grid_ctas.argtypes = [C.c_void_p]
     lib.wrnn_launch_count.restype = C.c_int64
     lib.wrnn_launch_count.argtypes = [C.c_void_p]
+    lib.wrnn_expand_conditioning.restype = C.c_int
+    lib.wrnn_expand_conditioning.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int64,
+                                             C.c_void_p, C.c_void_p, C.c_void_p]
     lib.wrnn_epilogue.restype = C.c_int
     lib.wrnn_epilogue.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p,
                                   C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]
@@ -185,6 +188,13 @@ class Engine:
 def _torch():
     import torch
     return torch
+
+
+def expand_conditioning(*, mel_frames: int, aux_frames: int, up_taps: int, hop: int, row_lo: int, n_rows: int,
+                        mels_up: int, aux: int, stream: int = 0):
+    """wrnn_expand_conditioning with raw device addresses.  Asynchronous on `stream`."""
+    lib = load()
+    _check(lib, lib.wrnn_expand_conditioning(mel_frames, aux_frames, up_taps, hop, row_lo, n_rows, mels_up, aux, stream or None))
 
 
 def epilogue(*, samples: int, n_seg: int, seg_len: int, seg_stride: int, overlap: int, fade_in: int, fade_out: int,

@@ -205,4 +205,14 @@ int64_t wrnn_launch_count(const wrnn_t* h) {
   return (h && h->engine) ? h->engine->launches + (h->fallback ? h->fallback->launches : 0) : 0;
 }
 
+int wrnn_expand_conditioning(const float* mel_frames, const float* aux_frames, const float* up_taps, int32_t hop, int64_t row_lo,
+                             int64_t n_rows, float* mels_up, float* aux, void* stream) {
+  if (!mel_frames || !aux_frames || !up_taps || !mels_up || !aux || hop <= 0 || row_lo < 0 || n_rows <= 0 ||
+      row_lo + n_rows >= (1ll << 31)) {
+    set_error("wrnn_expand_conditioning: bad argument");
+    return WRNN_E_INVALID;
+  }
+  return expand_conditioning(mel_frames, aux_frames, up_taps, hop, row_lo, n_rows, mels_up, aux, static_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

@@ -37,6 +37,9 @@ class Engine {
 int make_simt_engine(const wrnn_cfg& cfg, const HostWeights& w, int device, Engine** out);
 // tcgen05 engine: 5th-gen tensor-core contractions with TMEM accumulators (bf16 operands).
 int make_tc_engine(const wrnn_cfg& cfg, const HostWeights& w, int device, Engine** out);
+// conditioning pre-pass (wrnn_tc.cu): rows [row_lo, row_lo + n_rows) of the per-sample stream from frame-rate tensors
+int expand_conditioning(const float* mel_frames, const float* aux_frames, const float* up_taps, int hop, long long row_lo,
+                        long long n_rows, float* mels_up, float* aux, cudaStream_t stream);
 
 }  // namespace wrnn
 

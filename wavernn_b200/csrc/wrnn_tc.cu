@@ -752,6 +752,16 @@ class TcEngine : public Engine {
 
 }  // namespace
 
+// C-ABI entry of the conditioning pre-pass (also used per tile by TcEngine::generate)
+int expand_conditioning(const float* mel_frames, const float* aux_frames, const float* up_taps, int hop, long long row_lo,
+                        long long n_rows, float* mels_up, float* aux, cudaStream_t stream) {
+  const long long blocks = (n_rows + XP_ROWS - 1) / XP_ROWS;
+  const int grid = (int)(blocks < 148 * 8 ? blocks : 148 * 8);
+  wrnn_expand_rows_kernel<<<grid, XP_THREADS, 0, stream>>>(mel_frames, aux_frames, up_taps, hop, row_lo, n_rows, mels_up, aux);
+  WRNN_CUDA_OK(cudaGetLastError());
+  return WRNN_OK;
+}
+
 int make_tc_engine(const wrnn_cfg& cfg, const HostWeights& w, int device, Engine** out) {
   if (!TcEngine::supports_cfg(cfg)) {
     set_error("tcgen05 engine serves the MoL head (30 classes) and the 9-bit RAW head (512 classes) with fp16/bf16 operands");

@@ -507,6 +507,17 @@ class WaveRNN(nn.Module):
                 row_end += [base + g.total_len] * g.n_seg
                 base += g.total_len + (2 * self.pad * hop if frames else 0)
             m_all, a_all = torch.cat(streams_m, 0).contiguous(), torch.cat(streams_a, 0).contiguous()
+            if frames:
+                # one HBM-rate pre-pass lays the x275 rows of all utterances end to end (same arithmetic as generate()'s
+                # per-tile pre-pass -> identical samples); the pad frames between utterances give rows no fold reads
+                n_rows = base - 2 * self.pad * hop
+                cs = torch.cuda.current_stream(device).cuda_stream
+                m_rows = torch.empty((n_rows, m_all.shape[1]), dtype=torch.float32, device=device)
+                a_rows = torch.empty((n_rows, a_all.shape[1]), dtype=torch.float32, device=device)
+                cabi.expand_conditioning(mel_frames=m_all.data_ptr(), aux_frames=a_all.data_ptr(),
+                                         up_taps=self.upsample_taps(device).data_ptr(), hop=hop, row_lo=0, n_rows=n_rows,
+                                         mels_up=m_rows.data_ptr(), aux=a_rows.data_ptr(), stream=cs)
+                m_all, a_all = m_rows, a_rows
             t_row0 = torch.tensor(row0, dtype=torch.int64, device=device)
             t_end = torch.tensor(row_end, dtype=torch.int64, device=device)
             # the job's folds (all utterances, in order) are sharded over the ranks like generate()'s: contiguous
@@ -525,10 +536,8 @@ class WaveRNN(nn.Module):
             engine = self._get_engine(device)
             out = torch.empty((n_loc, S), dtype=torch.float32, device=device)
             if n_loc:
-                cond = (dict(mels_up=0, aux=0, mel_frames=m_all.data_ptr(), aux_frames=a_all.data_ptr(),
-                             up_taps=self.upsample_taps(device).data_ptr(), hop=hop) if frames
-                        else dict(mels_up=m_all.data_ptr(), aux=a_all.data_ptr()))
-                engine.generate(L=base, n_seg=n_loc, seg_len=S, seg_stride=stride, out=out.data_ptr(), seg_first=f_lo,
+                cond = dict(mels_up=m_all.data_ptr(), aux=a_all.data_ptr())
+                engine.generate(L=m_all.shape[0], n_seg=n_loc, seg_len=S, seg_stride=stride, out=out.data_ptr(), seg_first=f_lo,
                                 uniforms=uniforms.data_ptr() if uniforms is not None else 0,
                                 philox_seed=int(self.gen_philox_seed), fold_row0=t_row0[f_lo:].data_ptr(),
                                 fold_row_end=t_end[f_lo:].data_ptr(),
