@@ -534,11 +534,21 @@ __global__ void __launch_bounds__(NT, 1) wrnn_tc_kernel(const TcParams p) {
           if (task < n_tasks) store_task(task / KQ, task % KQ, creg[j][0], creg[j][1]);
         }
       } else {
-        for (int task = st; task < n_tasks; task += 128) {
-          const int f = task / KQ, c8 = task % KQ;
-          float4 a, b;
-          cond_chunk(f, c8, n, a, b);
-          store_task(f, c8, a, b);
+        // more than 24 folds: up to 13 tasks per thread.  All loads are issued before the first use so their
+        // latencies overlap (one L2/HBM round trip per step instead of one per task -- this block sits between
+        // the S2 and S3 chains of the issuer warps).
+        constexpr int MAX_TASKS = (MT * KQ + 127) / 128;
+        float4 r[MAX_TASKS][2];
+#pragma unroll
+        for (int j = 0; j < MAX_TASKS; ++j) {
+          const int task = st + j * 128;
+          r[j][0] = make_float4(0.f, 0.f, 0.f, 0.f); r[j][1] = r[j][0];
+          if (task < n_tasks) cond_chunk(task / KQ, task % KQ, n, r[j][0], r[j][1]);
+        }
+#pragma unroll
+        for (int j = 0; j < MAX_TASKS; ++j) {
+          const int task = st + j * 128;
+          if (task < n_tasks) store_task(task / KQ, task % KQ, r[j][0], r[j][1]);
         }
       }
       proxy_fence_smem();
