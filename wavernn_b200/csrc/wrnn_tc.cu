@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(XP_THREADS) wrnn_expand_rows_kernel(const floa
 // ------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------
-template <int FMT, bool FRAMES, bool RAW>
+template <int FMT, bool FRAMES, bool RAW, bool BIG>
 __global__ void __launch_bounds__(NT, 1) wrnn_tc_kernel(const TcParams p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const float* fv = reinterpret_cast<const float*>(smem + OFF_VEC);
@@ -439,7 +439,9 @@ __global__ void __launch_bounds__(NT, 1) wrnn_tc_kernel(const TcParams p) {
     const int st = tid - 128;
     constexpr int COND_TASKS = 5;                          // (fold, 8-column chunk) tasks held in registers per thread
     const int n_tasks = B * KQ;
-    const bool deferred = n_tasks <= COND_TASKS * 128;     // n_seg <= 24: loads fly a whole step before use
+    // BIG = false (tile of <= 24 folds, host-selected): every task fits the per-thread registers and its loads fly a
+    // whole step before use; BIG = true: up to 13 tasks per thread, loaded and stored inside the block below
+    constexpr bool deferred = !BIG;
     float4 creg[COND_TASKS][2];
     // conditioning window of fold f of this tile: the strided fold, or the caller's tables (several utterances in one job)
     // strided windows: streams are indexed from the job's first fold, frame tensors from the stream's first sample
@@ -609,14 +611,17 @@ class TcEngine : public Engine {
   const char* name() const override { return cfg.precision == WRNN_PREC_BF16 ? "tcgen05-bf16" : "tcgen05-fp16"; }
   int grid_ctas() const override { return P; }
   // FRAMES = conditioning rows built in the kernel from frame-rate tensors (wrnn_job::mel_frames)
-  template <int FMT, bool FR>
+  template <int FMT, bool FR, bool BIG>
   const void* kernel_of() const {
-    return cfg.mode == WRNN_MODE_RAW ? (const void*)wrnn_tc_kernel<FMT, FR, true> : (const void*)wrnn_tc_kernel<FMT, FR, false>;
+    return cfg.mode == WRNN_MODE_RAW ? (const void*)wrnn_tc_kernel<FMT, FR, true, BIG> : (const void*)wrnn_tc_kernel<FMT, FR, false, BIG>;
   }
-  const void* kernel(bool frames) const {
-    if (cfg.precision == WRNN_PREC_BF16) return frames ? kernel_of<1, true>() : kernel_of<1, false>();
-    return frames ? kernel_of<0, true>() : kernel_of<0, false>();
+  // frames: rows formed in the kernel from frame-rate tensors; big: tile of more than SMALL_TILE folds
+  const void* kernel(bool frames, bool big) const {
+    if (cfg.precision == WRNN_PREC_BF16)
+      return frames ? (big ? kernel_of<1, true, true>() : kernel_of<1, true, false>()) : (big ? kernel_of<1, false, true>() : kernel_of<1, false, false>());
+    return frames ? (big ? kernel_of<0, true, true>() : kernel_of<0, true, false>()) : (big ? kernel_of<0, false, true>() : kernel_of<0, false, false>());
   }
+  static constexpr int SMALL_TILE = 24;     // 24 folds x 26 chunks = 624 <= 5 tasks x 128 staging threads
 
   int init(const HostWeights& w) {
     Folded f; fold(w, f);
@@ -654,8 +659,8 @@ class TcEngine : public Engine {
     xch5_off_ = (size_t)4 * 2 * 8 * SBO_H;               // 4 vectors x 2 parities x (up to 8 row groups)
     scratch_bytes_ = xch5_off_ + (size_t)2 * P * MT * 8;   // + RAW candidates: 2 parities x 128 CTAs x 64 folds x 8 B
     WRNN_CUDA_OK(cudaMalloc(&d_scratch_, scratch_bytes_));
-    WRNN_CUDA_OK(cudaFuncSetAttribute(kernel(false), cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    WRNN_CUDA_OK(cudaFuncSetAttribute(kernel(true), cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    for (int v = 0; v < 4; ++v)
+      WRNN_CUDA_OK(cudaFuncSetAttribute(kernel((v & 1) != 0, (v & 2) != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     int n_sm = 0;
     WRNN_CUDA_OK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device));
     if (n_sm < P) { set_error("tcgen05 engine needs >= 128 SMs for its co-resident weight shards"); return WRNN_E_NO_DEVICE; }
@@ -725,7 +730,7 @@ class TcEngine : public Engine {
       }
       WRNN_CUDA_OK(cudaMemsetAsync(d_sync_, 0, 32, stream));                       // arrival counters (the abort flag is sticky)
       void* args[] = {&p};
-      WRNN_CUDA_OK(cudaLaunchCooperativeKernel(kernel(frames && !expand), dim3(P), dim3(NT), args, SMEM_BYTES, stream));
+      WRNN_CUDA_OK(cudaLaunchCooperativeKernel(kernel(frames && !expand, p.n_seg > SMALL_TILE), dim3(P), dim3(NT), args, SMEM_BYTES, stream));
       ++launches;
     }
     last_steps_ = p.steps;
