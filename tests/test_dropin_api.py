@@ -163,3 +163,46 @@ def test_native_generator_replay_equals_torch_operators(mode):
         u, e = model._reference_draws(geo, 300 if mode == "MOL" else 5)
         got[native] = (u if u is not None else e, torch.rand(9))
     assert torch.equal(got[True][0], got[False][0]) and torch.equal(got[True][1], got[False][1])
+
+
+def _epilogue_kernel_emulation(samples, stride, overlap, tabs, n_classes, wave_len, tail_len):
+    """numpy restatement of csrc/wrnn_epilogue.cu (same table lookups, same order of float64 operations)."""
+    B, S = samples.shape
+    y = samples.astype(np.float64)
+    if tabs["mu"] is not None:
+        lbl = np.clip(np.rint((samples + np.float32(1)) * np.float32(0.5 * (n_classes - 1))).astype(np.int64), 0, n_classes - 1)
+        y = tabs["mu"].numpy()[lbl]
+    if overlap:
+        y[:, :overlap] = y[:, :overlap] * tabs["fade_in"].numpy()
+        y[:, S - overlap:] = y[:, S - overlap:] * tabs["fade_out"].numpy()
+    n = np.arange(wave_len)
+    i_hi = np.minimum(n // stride, B - 1)
+    k_hi = n - i_hi * stride
+    v = np.zeros(wave_len)
+    lo = (i_hi >= 1) & (k_hi + stride < S)
+    v[lo] = v[lo] + y[i_hi[lo] - 1, k_hi[lo] + stride]
+    hi = k_hi < S
+    v[hi] = v[hi] + y[i_hi[hi], k_hi[hi]]
+    v[wave_len - tail_len:] = v[wave_len - tail_len:] * tabs["tail"].numpy()
+    return v
+
+
+@pytest.mark.parametrize("mode,batched,mu_law", [("MOL", True, False), ("MOL", False, False), ("RAW", True, True)])
+def test_device_epilogue_tables_and_algorithm_equal_host_epilogue(mode, batched, mu_law):
+    """The float64 tables handed to wrnn_epilogue + the kernel's gather formulation (each output sample = at most two
+    fold samples, folds ascending) reproduce the reference's in-place cross-fade / overlap-add bit for bit.  (The CUDA
+    kernel itself is checked against the host epilogue in tests/test_gpu_parity.py.)"""
+    from wavernn_b200.sharding import fold_geometry, unbatched_geometry
+    model = helpers.make_model(0, mode, "cpu")
+    T, hop = 33, 275
+    geo = fold_geometry(T * hop, 2750, 275) if batched else unbatched_geometry(T * hop)
+    rs = np.random.RandomState(3)
+    if mode == "RAW":
+        samples = (np.float32(2) * rs.randint(0, 512, size=(geo.n_seg, geo.seg_len)).astype(np.float32) / np.float32(511) - np.float32(1))
+    else:
+        samples = rs.uniform(-1, 1, size=(geo.n_seg, geo.seg_len)).astype(np.float32)
+    wave_len = (T - 1) * hop
+    tabs = model._epilogue_tables(geo, batched, mu_law, torch.device("cpu"))
+    got = _epilogue_kernel_emulation(samples, geo.seg_stride, geo.overlap if batched else 0, tabs, model.n_classes, wave_len, 20 * hop)
+    want = model._epilogue(samples.astype(np.float64), geo, batched, wave_len, mu_law)
+    assert np.array_equal(got, want)
