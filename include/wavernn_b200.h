@@ -203,6 +203,13 @@ int wrnn_epilogue(const float *samples, int32_t n_seg, int32_t seg_len, int64_t 
  * Returns the new position; `state` is updated in place.                               */
 int32_t wrnn_mt19937_uniform(uint32_t *state, int32_t pos, uint64_t skip, float *out, uint64_t n,
                              float lo, float hi);
+/* Same stream, but the n_rows x row_len draws that follow `skip` are a matrix of which only the columns
+ * [a_lo, a_hi) and [b_lo, b_hi) (a_hi <= b_lo) are wanted: `out` is [n_rows, (a_hi-a_lo) + (b_hi-b_lo)], the other
+ * draws are discarded without being converted.  A rank of a sharded job needs only its own folds' columns of the
+ * reference's [steps, 11*B] draw matrix (10*B mixture draws fold-major, then B logistic draws per row).        */
+int32_t wrnn_mt19937_uniform_cols(uint32_t *state, int32_t pos, uint64_t skip, float *out, uint64_t n_rows,
+                                  uint64_t row_len, uint64_t a_lo, uint64_t a_hi, uint64_t b_lo, uint64_t b_hi,
+                                  float lo, float hi);
 
 #ifdef __cplusplus
 }

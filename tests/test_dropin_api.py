@@ -206,3 +206,29 @@ def test_device_epilogue_tables_and_algorithm_equal_host_epilogue(mode, batched,
     got = _epilogue_kernel_emulation(samples, geo.seg_stride, geo.overlap if batched else 0, tabs, model.n_classes, wave_len, 20 * hop)
     want = model._epilogue(samples.astype(np.float64), geo, batched, wave_len, mu_law)
     assert np.array_equal(got, want)
+
+
+def test_rank_local_draws_are_the_columns_of_the_full_draw_matrix():
+    """Sharded jobs: every rank advances torch's generator over the WHOLE (steps, 11*B) matrix of the reference's draws
+    but converts and keeps only its own folds' columns (wrnn_mt19937_uniform_cols)."""
+    import torch
+    from wavernn_b200 import cabi
+    from wavernn_b200.sharding import fold_geometry, shard_folds
+    if not cabi.is_built():
+        pytest.skip("library not built")
+    model = helpers.make_model(0, "MOL", "cpu")
+    geo = fold_geometry(60 * 275, 2750, 275)            # 6 folds (the last one zero-padded)
+    assert geo.n_seg == 6
+    torch.manual_seed(77)
+    full, _ = model._reference_draws(geo, 123)
+    after = torch.rand(4)
+    B = geo.n_seg
+    for world in (2, 3, 8):                             # 8 ranks: some own no fold at all
+        for rank in range(world):
+            sh = shard_folds(geo, rank, world, 275)
+            torch.manual_seed(77)
+            loc, _ = model._reference_draws(geo, 123, shard=sh)
+            f0, n = sh.seg_first, sh.n_seg
+            want = torch.cat([full[:, 10 * f0:10 * (f0 + n)], full[:, 10 * B + f0:10 * B + f0 + n]], 1)
+            assert loc.shape == (123, 11 * n) and torch.equal(loc, want), (world, rank)
+            assert torch.equal(torch.rand(4), after)                     # generator left where the full draw leaves it

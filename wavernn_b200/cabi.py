@@ -21,7 +21,7 @@ ABI_VERSION = 4
 
 EXPORTS = ("wrnn_abi_version", "wrnn_last_error", "wrnn_create", "wrnn_destroy", "wrnn_generate",
            "wrnn_check", "wrnn_generate_host", "wrnn_engine_name", "wrnn_grid_ctas", "wrnn_launch_count",
-           "wrnn_mt19937_uniform", "wrnn_epilogue", "wrnn_expand_conditioning")
+           "wrnn_mt19937_uniform", "wrnn_mt19937_uniform_cols", "wrnn_epilogue", "wrnn_expand_conditioning")
 
 _fp = C.POINTER(C.c_float)
 
@@ -101,6 +101,9 @@ def load() -> C.CDLL:
                                   C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]
     lib.wrnn_mt19937_uniform.restype = C.c_int32
     lib.wrnn_mt19937_uniform.argtypes = [C.c_void_p, C.c_int32, C.c_uint64, C.c_void_p, C.c_uint64, C.c_float, C.c_float]
+    lib.wrnn_mt19937_uniform_cols.restype = C.c_int32
+    lib.wrnn_mt19937_uniform_cols.argtypes = [C.c_void_p, C.c_int32, C.c_uint64, C.c_void_p, C.c_uint64, C.c_uint64,
+                                              C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_float, C.c_float]
     if lib.wrnn_abi_version() != ABI_VERSION:
         raise RuntimeError(f"wavernn_b200: ABI mismatch (lib {lib.wrnn_abi_version()} != binding {ABI_VERSION})")
     _lib = lib
@@ -213,10 +216,12 @@ def epilogue(*, samples: int, n_seg: int, seg_len: int, seg_stride: int, overlap
 _MT_N, _MT_OFF, _STATE_BYTES = 624, 24, 5056
 
 
-def torch_rng_uniform(skip: int, n: int, lo: float, hi: float, out=None, generator=None):
+def torch_rng_uniform(skip: int, n: int, lo: float, hi: float, out=None, generator=None, row_len: int = 0, cols=None):
     """Advance torch's CPU generator by `skip` discarded 32-bit outputs and then fill `out` (a contiguous CPU float32
     tensor with n elements, e.g. pinned) with what `torch.empty(n).uniform_(lo, hi)` would have produced -- natively.
-    The generator (default: the global one) is left in exactly the state torch would have left it in."""
+    The generator (default: the global one) is left in exactly the state torch would have left it in.
+    With `row_len` and `cols=((a_lo, a_hi), (b_lo, b_hi))` the n draws are read as an (n // row_len, row_len) matrix of
+    which only those two column ranges are kept (`out`: rows x (a_hi-a_lo + b_hi-b_lo)); the rest is skipped unconverted."""
     import numpy as np
     import torch
     lib = load()
@@ -229,11 +234,22 @@ def torch_rng_uniform(skip: int, n: int, lo: float, hi: float, out=None, generat
         raise RuntimeError("unexpected torch CPU generator state (left)")
     words = a[_MT_OFF:_MT_OFF + 8 * _MT_N].view(np.uint64)
     mt = np.ascontiguousarray(words.astype(np.uint32))
+    if cols is not None:
+        (a_lo, a_hi), (b_lo, b_hi) = cols
+        rows = n // row_len
+        assert row_len > 0 and rows * row_len == n
+        n_out = rows * ((a_hi - a_lo) + (b_hi - b_lo))
+    else:
+        n_out = n
     if out is None:
-        out = torch.empty(n, dtype=torch.float32)
-    assert out.dtype == torch.float32 and out.is_contiguous() and out.numel() >= n and out.device.type == 'cpu'
-    pos = lib.wrnn_mt19937_uniform(mt.ctypes.data, _MT_N + 1 - left, int(skip), out.data_ptr() if n else None, int(n),
-                                   float(lo), float(hi))
+        out = torch.empty(n_out, dtype=torch.float32)
+    assert out.dtype == torch.float32 and out.is_contiguous() and out.numel() >= n_out and out.device.type == 'cpu'
+    if cols is not None:
+        pos = lib.wrnn_mt19937_uniform_cols(mt.ctypes.data, _MT_N + 1 - left, int(skip), out.data_ptr(), rows, int(row_len),
+                                            int(a_lo), int(a_hi), int(b_lo), int(b_hi), float(lo), float(hi))
+    else:
+        pos = lib.wrnn_mt19937_uniform(mt.ctypes.data, _MT_N + 1 - left, int(skip), out.data_ptr() if n else None, int(n),
+                                       float(lo), float(hi))
     if pos < 0:
         raise RuntimeError("wrnn_mt19937_uniform rejected its arguments")
     words[:] = mt
@@ -263,7 +279,12 @@ def torch_rng_replay_ok() -> bool:
             got = torch_rng_uniform(1531, 2000, 1e-5, 1.0 - 1e-5, generator=g2)
             tail_w = torch.empty(700).uniform_(generator=g1)
             tail_g = torch.empty(700).uniform_(generator=g2)
-            _rng_replay_ok = bool(torch.equal(want, got) and torch.equal(tail_w, tail_g))
+            ok = torch.equal(want, got) and torch.equal(tail_w, tail_g)
+            want2 = torch.empty(40, 55).uniform_(1e-5, 1.0 - 1e-5, generator=g1)
+            got2 = torch_rng_uniform(0, 40 * 55, 1e-5, 1.0 - 1e-5, generator=g2, row_len=55, cols=((10, 30), (52, 54)))
+            ok = ok and torch.equal(torch.cat([want2[:, 10:30], want2[:, 52:54]], 1).reshape(-1), got2)
+            ok = ok and torch.equal(torch.empty(5).uniform_(generator=g1), torch.empty(5).uniform_(generator=g2))
+            _rng_replay_ok = bool(ok)
         except Exception:
             _rng_replay_ok = False
     return _rng_replay_ok

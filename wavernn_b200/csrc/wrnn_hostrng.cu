@@ -61,33 +61,63 @@ template <> void convert<true>(const uint32_t* s, float* o, uint64_t take, float
 #endif
 template <> void convert<false>(const uint32_t* s, float* o, uint64_t take, float range, float lo) { convert_body<false>(s, o, take, range, lo); }
 
+// position in the generator's output stream + the two operations the replay needs
+struct Stream {
+  uint32_t* state; int32_t pos; float range, lo; bool hw;
+  Stream(uint32_t* st, int32_t p, float lo_, float hi_) : state(st), pos(p), range(hi_ - lo_), lo(lo_) {
+#if defined(__x86_64__)
+    hw = __builtin_cpu_supports("fma") && __builtin_cpu_supports("avx2");
+#else
+    hw = false;
+#endif
+  }
+  void skip(uint64_t n) {                                // discard: whole blocks cost one twist each
+    while (n) {
+      if (pos == N) { twist(state); pos = 0; }
+      const uint64_t take = n < (uint64_t)(N - pos) ? n : (uint64_t)(N - pos);
+      pos += (int32_t)take;
+      n -= take;
+    }
+  }
+  // torch's uniform_real<float>: x = (y & (2^24 - 1)) * 2^-24 ; x * (hi - lo) + lo with one rounding (its CPU kernels
+  // are built with FMA contraction)
+  void draw(float* out, uint64_t n) {
+    uint64_t done = 0;
+    while (done < n) {
+      if (pos == N) { twist(state); pos = 0; }
+      const uint64_t take = (n - done) < (uint64_t)(N - pos) ? (n - done) : (uint64_t)(N - pos);
+      if (hw) convert<true>(state + pos, out + done, take, range, lo);
+      else convert<false>(state + pos, out + done, take, range, lo);
+      pos += (int32_t)take;
+      done += take;
+    }
+  }
+};
+
 }  // namespace
 
 extern "C" int32_t wrnn_mt19937_uniform(uint32_t* state, int32_t pos, uint64_t skip, float* out, uint64_t n, float lo, float hi) {
   if (!state || pos < 0 || pos > N || (n && !out)) return -1;
-  // discard: whole blocks cost one twist each
-  while (skip) {
-    if (pos == N) { twist(state); pos = 0; }
-    const uint64_t take = skip < (uint64_t)(N - pos) ? skip : (uint64_t)(N - pos);
-    pos += (int32_t)take;
-    skip -= take;
+  Stream s(state, pos, lo, hi);
+  s.skip(skip);
+  s.draw(out, n);
+  return s.pos;
+}
+
+extern "C" int32_t wrnn_mt19937_uniform_cols(uint32_t* state, int32_t pos, uint64_t skip, float* out, uint64_t n_rows, uint64_t row_len,
+                                             uint64_t a_lo, uint64_t a_hi, uint64_t b_lo, uint64_t b_hi, float lo, float hi) {
+  if (!state || pos < 0 || pos > N || a_lo > a_hi || a_hi > b_lo || b_lo > b_hi || b_hi > row_len) return -1;
+  if (!out && n_rows && (a_hi - a_lo) + (b_hi - b_lo) > 0) return -1;
+  Stream s(state, pos, lo, hi);
+  s.skip(skip);
+  const uint64_t wa = a_hi - a_lo, wb = b_hi - b_lo;
+  for (uint64_t r = 0; r < n_rows; ++r) {
+    float* o = out + r * (wa + wb);
+    s.skip(a_lo);
+    s.draw(o, wa);
+    s.skip(b_lo - a_hi);
+    s.draw(o + wa, wb);
+    s.skip(row_len - b_hi);
   }
-  // torch's uniform_real<float>: x = (y & (2^24 - 1)) * 2^-24 ; x * (hi - lo) + lo with one rounding (its CPU kernels
-  // are built with FMA contraction)
-  const float range = hi - lo;
-#if defined(__x86_64__)
-  const bool hw = __builtin_cpu_supports("fma") && __builtin_cpu_supports("avx2");
-#else
-  const bool hw = false;
-#endif
-  uint64_t done = 0;
-  while (done < n) {
-    if (pos == N) { twist(state); pos = 0; }
-    const uint64_t take = (n - done) < (uint64_t)(N - pos) ? (n - done) : (uint64_t)(N - pos);
-    if (hw) convert<true>(state + pos, out + done, take, range, lo);
-    else convert<false>(state + pos, out + done, take, range, lo);
-    pos += (int32_t)take;
-    done += take;
-  }
-  return pos;
+  return s.pos;
 }

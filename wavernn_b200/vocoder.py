@@ -264,7 +264,7 @@ class WaveRNN(nn.Module):
                 and self.gen_engine in ('auto', 'tcgen05') and (self.mode == 'MOL' or self.n_classes == 512))
 
     # ------------------------------------------------------------------ randomness
-    def _reference_draws(self, geo: FoldGeometry, steps: int, reuse_buffer: bool = False):
+    def _reference_draws(self, geo: FoldGeometry, steps: int, reuse_buffer: bool = False, shard=None):
         """Consumes torch's default CPU generator exactly as the reference's generate() does: two nn.GRUCell
         constructions (:178-179, one uniform per parameter element, discarded) and then the loop's draws.
         With `gen_native_rng` the generator is replayed natively (cabi.torch_rng_uniform: the discarded part is skipped,
@@ -275,17 +275,24 @@ class WaveRNN(nn.Module):
         if native:
             skip = sum(3 * g.hidden_size * (g.input_size + g.hidden_size + 2) for g in (self.rnn1, self.rnn2))
             if self.mode == 'MOL':
-                n = steps * 11 * B
+                # `shard`: only this rank's folds' columns of the (steps, 11*B) matrix are converted and kept --
+                # the result is the (steps, 11*n_local) block the kernel consumes, not the whole matrix
+                cols = None
+                n_keep = n = steps * 11 * B
+                if shard is not None and shard.n_seg < B:
+                    f0, nl = shard.seg_first, shard.n_seg
+                    cols = ((10 * f0, 10 * (f0 + nl)), (10 * B + f0, 10 * B + f0 + nl))
+                    n_keep = steps * 11 * nl
                 buf = None
                 if torch.cuda.is_available():
                     if reuse_buffer:        # one job at a time: the caller synchronises before the next call
-                        if self._draw_buf is None or self._draw_buf.numel() < n:
-                            self._draw_buf = torch.empty(n, dtype=torch.float32, pin_memory=True)
+                        if self._draw_buf is None or self._draw_buf.numel() < n_keep:
+                            self._draw_buf = torch.empty(n_keep, dtype=torch.float32, pin_memory=True)
                         buf = self._draw_buf
                     else:
-                        buf = torch.empty(n, dtype=torch.float32, pin_memory=True)
-                u = cabi.torch_rng_uniform(skip, n, 1e-5, 1.0 - 1e-5, out=buf)
-                return u[:n].view(steps, 11 * B), None
+                        buf = torch.empty(n_keep, dtype=torch.float32, pin_memory=True)
+                u = cabi.torch_rng_uniform(skip, n, 1e-5, 1.0 - 1e-5, out=buf, row_len=11 * B, cols=cols)
+                return u[:n_keep].view(steps, n_keep // steps), None
             cabi.torch_rng_uniform(skip, 0, 0.0, 1.0)
         else:
             nn.GRUCell(self.rnn1.input_size, self.rnn1.hidden_size)     # :178 get_gru_cell(self.rnn1)
@@ -357,11 +364,11 @@ class WaveRNN(nn.Module):
             aux_fr = self.upsample.resnet(mels_padded)[0].transpose(0, 1).contiguous().float()   # (T, 4*aux)
             taps = self.upsample_taps(device)
         if self.gen_rng == 'torch' or draws is not None:
-            u_all, e_all = draws if draws is not None else self._reference_draws(geo, S, reuse_buffer=True)
+            u_all, e_all = draws if draws is not None else self._reference_draws(geo, S, reuse_buffer=True, shard=shard)
             f0, n = shard.seg_first, shard.n_seg
             B = geo.n_seg
             if u_all is not None:
-                u_loc = u_all if (f0 == 0 and n == B) else \
+                u_loc = u_all if u_all.shape[1] == 11 * n else \
                     torch.cat([u_all[:, 10 * f0:10 * (f0 + n)], u_all[:, 10 * B + f0:10 * B + f0 + n]], dim=1)
                 uniforms = u_loc.contiguous().to(device, non_blocking=True)
             if e_all is not None:
