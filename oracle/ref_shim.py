@@ -127,3 +127,76 @@ def ref_generate(model, mels, batched, target, overlap, mu_law=False, seed=1234,
     out = dict(wav=np.asarray(wav), raw=grabbed.get("raw"))
     out["pre"] = grabbed.get("pre")
     return out
+
+
+# --------------------------------------------------------------------------------------
+# Tacotron front half of gen_tacotron.py (BASELINE configs[3]); container-only, fixtures only
+# --------------------------------------------------------------------------------------
+_ONES = ("zero one two three four five six seven eight nine ten eleven twelve thirteen fourteen fifteen sixteen "
+         "seventeen eighteen nineteen").split()
+_TENS = "zero ten twenty thirty forty fifty sixty seventy eighty ninety".split()
+
+
+def _number_to_words(n, andword="", zero="zero", group=0):
+    """Minimal stand-in for inflect.engine().number_to_words (utils/text/numbers.py:3,7): cardinals below one
+    million, which is all the fixture sentences contain."""
+    n = int(str(n).replace(",", "").split(".")[0] or 0)
+    if n < 20:
+        return _ONES[n]
+    if n < 100:
+        return _TENS[n // 10] + ("-" + _ONES[n % 10] if n % 10 else "")
+    if n < 1000:
+        return _ONES[n // 100] + " hundred" + (" " + _number_to_words(n % 100) if n % 100 else "")
+    return _number_to_words(n // 1000) + " thousand" + (" " + _number_to_words(n % 1000) if n % 1000 else "")
+
+
+def install_text_stubs():
+    """`unidecode` and `inflect` are absent here: ASCII pass-through and a small cardinal speller."""
+    if "unidecode" not in sys.modules:
+        uni = types.ModuleType("unidecode")
+        uni.unidecode = lambda s: s.encode("ascii", "ignore").decode("ascii")
+        sys.modules["unidecode"] = uni
+    if "inflect" not in sys.modules:
+        inf = types.ModuleType("inflect")
+        inf.engine = lambda: types.SimpleNamespace(number_to_words=_number_to_words)
+        sys.modules["inflect"] = inf
+
+
+def build_reference_tacotron():
+    """The reference's Tacotron with the shipped checkpoint, exactly as gen_tacotron.py:94-111 builds and loads it
+    (`.load()`, so the legacy `r` key is honoured, tacotron.py:452-454)."""
+    import contextlib
+    import tempfile
+    import torch
+    load_reference()
+    install_text_stubs()
+    from models.tacotron import Tacotron
+    from utils import hparams as hp
+    from utils.text.symbols import symbols
+    with contextlib.redirect_stdout(io.StringIO()):
+        tts = Tacotron(embed_dims=hp.tts_embed_dims, num_chars=len(symbols), encoder_dims=hp.tts_encoder_dims,
+                       decoder_dims=hp.tts_decoder_dims, n_mels=hp.num_mels, fft_bins=hp.num_mels,
+                       postnet_dims=hp.tts_postnet_dims, encoder_K=hp.tts_encoder_K, lstm_dims=hp.tts_lstm_dims,
+                       postnet_K=hp.tts_postnet_K, num_highways=hp.tts_num_highways, dropout=hp.tts_dropout,
+                       stop_threshold=hp.tts_stop_threshold)
+    zpath = os.path.join(REF_ROOT, "pretrained", "ljspeech.tacotron.r2.180k.zip")
+    with zipfile.ZipFile(zpath) as z, tempfile.TemporaryDirectory() as d:
+        z.extract("latest_weights.pyt", d)
+        tts.load(os.path.join(d, "latest_weights.pyt"))
+    return tts
+
+
+def tacotron_mels(sentences, seed=0):
+    """gen_tacotron.py:113-143: text -> ids -> Tacotron.generate -> (m + 4) / 8 clipped to [0, 1]."""
+    import torch
+    tts = build_reference_tacotron()
+    from utils import hparams as hp
+    from utils.text import text_to_sequence
+    out = []
+    for i, s in enumerate(sentences):
+        torch.manual_seed(seed + i)
+        _, m, _ = tts.generate(text_to_sequence(s.strip(), hp.tts_cleaner_names))
+        m = (m + 4) / 8
+        np.clip(m, 0, 1, out=m)
+        out.append(m.astype(np.float32))
+    return out

@@ -74,3 +74,26 @@ def first_exceed(diff, thr):
 
 def load_golden(name):
     return np.load(GOLDEN / name, allow_pickle=False)
+
+
+def tacotron_mels():
+    """The 16 Tacotron mels of BASELINE configs[3] (tests/golden/make_tacotron_mels.py), de-quantised: list of
+    (80, T) float32 in [0, 1]."""
+    g = load_golden("tacotron_mels.npz")
+    return [g[f"mel_{i:02d}"].astype(np.float32) / np.float32(65535.0) for i in range(16)]
+
+
+def mol_component_picks(logits, U):
+    """Mixture component chosen per (step, fold) (utils/distribution.py:106-108): argmax(logit - log(-log u)) with the
+    replayed draws U[S, 11*B].  logits (S, B, 30)."""
+    S, B = logits.shape[:2]
+    u = U[:S, :10 * B].reshape(S, B, 10).astype(np.float32)
+    return np.argmax(logits[:, :, :10] - np.log(-np.log(u)), axis=-1)
+
+
+def pretrained_state_dict():
+    """state_dict of the reference's shipped LJSpeech checkpoint (fixture copy under tests/golden/pretrained)."""
+    import zipfile
+    with zipfile.ZipFile(GOLDEN / "pretrained" / "ljspeech.wavernn.mol.800k.zip") as z:
+        blob = z.read("latest_weights.pyt")
+    return torch.load(io.BytesIO(blob), map_location="cpu")

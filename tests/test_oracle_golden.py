@@ -106,3 +106,33 @@ def test_short_input_raises_like_reference():
     with pytest.raises(ValueError):
         O.epilogue(np.zeros((1, 18 * 275), np.float32), batched=False, target=0, overlap=0, wave_len=17 * 275,
                    hop_length=275, mode="MOL", mu_law=False, n_classes=30)
+
+
+def test_oracle_tracks_reference_on_trained_checkpoint_fixture():
+    """The fp32 restatement on the reference's shipped checkpoint + a real Tacotron mel (fixtures made by
+    tests/golden/make_golden_trained.py from the unmodified reference): trained weights are chaotic, so agreement is a
+    prefix property -- 1e-4 for the first 1,500 steps of every fold -- plus teacher-forced logits to 1e-3."""
+    g = helpers.load_golden("trained_tacotron.npz")
+    sd = {k: v.numpy() for k, v in helpers.pretrained_state_dict().items()}
+    w = O.hot_weights(sd)
+    mel = helpers.tacotron_mels()[int(g["sentence"])]
+    m_up, aux = O.upsample_network(sd, O.pad_time(mel.T, 2).T, pad=2)
+    U = helpers.replay_uniforms(int(g["seed"]), 12100, 4)
+    kw = dict(n_seg=4, seg_len=12100, seg_stride=11550)
+    out = O.generate_segments(w, m_up, aux, uniforms=U, steps=1500, **kw)
+    assert np.abs(out - g["raw"][:, :1500]).max() <= 1e-4
+    _, lg = O.generate_segments(w, m_up, aux, uniforms=U, x_force=g["raw"].T.copy(), want_logits=True, steps=600, **kw)
+    assert np.abs(lg - g["logits"]).max() <= 1e-3
+
+
+def test_oracle_matches_reference_on_cfg1_at_stated_size():
+    """BASELINE configs[0]: T=100, unbatched, 27,500 sequential steps (random-init seed 0)."""
+    g = helpers.load_golden("trained_cfg1.npz")
+    model = helpers.make_model(0, "MOL")
+    sd = helpers.state_numpy(model)
+    mel = helpers.make_mel(100, 0)
+    U = helpers.replay_uniforms(int(g["seed"]), 27500, 1)
+    wav, pre = O.generate(O.hot_weights(sd), sd, mel[0].numpy(), batched=False, target=11000, overlap=550,
+                          uniforms=U, return_pre=True)
+    assert pre.shape == (1, 27500) and np.abs(pre - g["raw"]).max() <= 1e-4
+    assert np.abs(wav - g["wav"]).max() <= 1e-4

@@ -173,6 +173,24 @@ class Engine:
                       hop, cond_mode)
         _check(self.lib, self.lib.wrnn_generate(self._h, C.byref(job), C.c_void_p(stream or None)))
 
+    def generate_host(self, *, mels_up, aux, n_seg: int, seg_len: int, seg_stride: int, seg_first: int = 0, steps: int = 0,
+                      uniforms=None, expo=None, philox_seed: int = 0, philox_offset: int = 0, x_force=None,
+                      want_logits: bool = False):
+        """wrnn_generate_host: the same job with HOST buffers (numpy float32 arrays) -- the entry a non-torch caller
+        binds.  Copies in, runs, copies out, synchronises and checks.  Returns samples (n_seg, S)[, logits (S, n_seg, C)]."""
+        import numpy as np
+        f32 = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float32)
+        mels_up, aux, uniforms, expo, x_force = f32(mels_up), f32(aux), f32(uniforms), f32(expo), f32(x_force)
+        S = steps or seg_len
+        out = np.empty((n_seg, S), dtype=np.float32)
+        logits = np.empty((S, n_seg, self.n_classes), dtype=np.float32) if want_logits else None
+        ptr = lambda a: None if a is None else a.ctypes.data
+        job = WrnnJob(ptr(mels_up), ptr(aux), mels_up.shape[0], seg_stride, n_seg, seg_len, seg_first, steps, ptr(uniforms),
+                      ptr(expo), philox_seed, philox_offset, ptr(out), ptr(x_force), ptr(logits), None, None, None, None,
+                      None, 0, 0)
+        _check(self.lib, self.lib.wrnn_generate_host(self._h, C.byref(job)))
+        return (out, logits) if want_logits else out
+
     def check(self):
         _check(self.lib, self.lib.wrnn_check(self._h))
 
