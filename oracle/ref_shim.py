@@ -35,6 +35,26 @@ _ref_mod = None
 _captured_wavs = []
 
 
+def install_import_stubs():
+    """The three in-process shims that make the reference importable here: fake `librosa`
+    (only `librosa.output.write_wav` is reached on this path, utils/dsp.py:22-23) and `matplotlib`, and the
+    `np.cumproduct` alias NumPy 2 dropped (fatchord_version.py:68)."""
+    if "librosa" not in sys.modules:
+        lib = types.ModuleType("librosa")
+        lib.output = types.SimpleNamespace(
+            write_wav=lambda path, x, sr: _captured_wavs.append((str(path), np.array(x), sr)))
+        sys.modules["librosa"] = lib
+    if "matplotlib" not in sys.modules:
+        mpl = types.ModuleType("matplotlib")
+        mpl.use = lambda *a, **k: None
+        mpl.interactive = lambda *a, **k: None
+        plt = types.ModuleType("matplotlib.pyplot")
+        mpl.pyplot = plt
+        sys.modules.update({"matplotlib": mpl, "matplotlib.pyplot": plt})
+    if not hasattr(np, "cumproduct"):
+        np.cumproduct = np.cumprod
+
+
 def load_reference():
     """Returns the reference module `models.fatchord_version` (cached)."""
     global _ref_mod
@@ -43,17 +63,7 @@ def load_reference():
     if not available():
         raise RuntimeError(f"reference checkout not found at {REF_ROOT}")
     sys.path.insert(0, REF_ROOT)
-    lib = types.ModuleType("librosa")
-    lib.output = types.SimpleNamespace(
-        write_wav=lambda path, x, sr: _captured_wavs.append((str(path), np.array(x), sr)))
-    mpl = types.ModuleType("matplotlib")
-    mpl.use = lambda *a, **k: None
-    mpl.interactive = lambda *a, **k: None
-    plt = types.ModuleType("matplotlib.pyplot")
-    mpl.pyplot = plt
-    sys.modules.update({"librosa": lib, "matplotlib": mpl, "matplotlib.pyplot": plt})
-    if not hasattr(np, "cumproduct"):
-        np.cumproduct = np.cumprod
+    install_import_stubs()
     import models.fatchord_version as ref  # noqa: E402  (unmodified reference)
     from utils import hparams as hp  # noqa: E402
     if not hp.is_configured():

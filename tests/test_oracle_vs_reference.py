@@ -46,3 +46,31 @@ def test_dropin_class_loads_pretrained_checkpoint():
     missing = ours.load_state_dict(ref_shim.load_pretrained_state_dict(), strict=False)
     assert not missing.missing_keys and not missing.unexpected_keys
     assert ours.get_step() == 797232
+
+
+@pytest.mark.parametrize("mode", ["MOL", "RAW"])
+def test_training_forward_equals_reference_forward(mode):
+    """`WaveRNN.forward(x, mels)` (reference :131-167, what train_wavernn.py:91-155 calls) on identical
+    weights and inputs -- eval mode and train mode (BatchNorm batch statistics, running-stat updates, `step` counter)."""
+    ref_model = ref_shim.build_reference_model(seed=0, mode=mode)
+    ours = helpers.make_model(1, mode)                     # different init: everything must come from the state_dict
+    ours.load_state_dict(ref_model.state_dict())
+    torch.manual_seed(5)
+    mels = torch.rand(3, 80, 12 + 4)                       # (B, 80, T + 2*pad)
+    x = torch.rand(3, 12 * 275) * 2 - 1                    # (B, T*hop)
+    for train in (False, True):
+        ref_model.train(train); ours.train(train)
+        a, b = ref_model(x, mels), ours(x, mels)
+        assert a.shape == b.shape == (3, 12 * 275, 30 if mode == "MOL" else 512)
+        assert torch.equal(a, b) or (a - b).abs().max().item() <= 1e-6
+        assert ref_model.get_step() == ours.get_step()
+    sa, sb = ref_model.state_dict(), ours.state_dict()
+    assert sa.keys() == sb.keys()
+    for k in sa:                                           # BatchNorm running statistics moved identically
+        assert torch.allclose(sa[k].float(), sb[k].float(), rtol=0, atol=1e-6), k
+    # gradients of the training loss flow through the same parameters
+    ref_model.zero_grad(); ours.zero_grad()
+    ref_model(x, mels).square().mean().backward(); ours(x, mels).square().mean().backward()
+    ga = {k: p.grad for k, p in ref_model.named_parameters()}
+    for k, p in ours.named_parameters():
+        assert torch.allclose(p.grad, ga[k], rtol=1e-4, atol=1e-7), k
