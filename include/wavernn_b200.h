@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define WRNN_ABI_VERSION 4
+#define WRNN_ABI_VERSION 5
 
 enum {
   WRNN_OK = 0,
@@ -49,8 +49,13 @@ enum { WRNN_MODE_MOL = 0, WRNN_MODE_RAW = 1 };   /* fatchord_version.py:98-104 *
  *         parity tool (matches the reference to reassociation error).               */
 enum { WRNN_PREC_F16 = 0, WRNN_PREC_FP32 = 1, WRNN_PREC_BF16 = 2 };
 
-/* Which kernel family executes the job.  AUTO picks the fastest that supports it. */
-enum { WRNN_ENGINE_AUTO = 0, WRNN_ENGINE_SIMT = 1, WRNN_ENGINE_TCGEN05 = 2 };
+/* Which kernel family executes the job.  AUTO picks the fastest that supports it:
+ *   TCGEN05: weights stationary in the shared memory of 128 SMs, activations exchanged through L2 -- lowest latency
+ *            per step, tiles of <= 64 folds one after the other (BASELINE configs[1], [2]);
+ *   STREAM : activations stationary (one CTA per 16/32 folds, any number of CTAs), weights streamed from L2 every
+ *            step -- highest throughput for jobs with hundreds of folds (configs[3], [4]); MoL head;
+ *   SIMT   : CUDA-core engine, the only one with strict fp32 arithmetic.                                       */
+enum { WRNN_ENGINE_AUTO = 0, WRNN_ENGINE_SIMT = 1, WRNN_ENGINE_TCGEN05 = 2, WRNN_ENGINE_STREAM = 3 };
 
 /* Where frame-rate conditioning (wrnn_job::mel_frames) is turned into per-sample rows. */
 enum { WRNN_COND_AUTO = 0, WRNN_COND_EXPAND = 1, WRNN_COND_IN_KERNEL = 2 };

@@ -27,7 +27,7 @@ def test_header_symbols_are_exported(lib):
     assert declared == set(cabi.EXPORTS), declared ^ set(cabi.EXPORTS)
     for sym in declared:
         assert getattr(lib, sym) is not None
-    assert lib.wrnn_abi_version() == 4
+    assert lib.wrnn_abi_version() == cabi.ABI_VERSION == 5
 
 
 def test_struct_layouts_match_header():

@@ -232,3 +232,51 @@ def test_rank_local_draws_are_the_columns_of_the_full_draw_matrix():
             want = torch.cat([full[:, 10 * f0:10 * (f0 + n)], full[:, 10 * B + f0:10 * B + f0 + n]], 1)
             assert loc.shape == (123, 11 * n) and torch.equal(loc, want), (world, rank)
             assert torch.equal(torch.rand(4), after)                     # generator left where the full draw leaves it
+
+
+def test_kernel_conditioning_is_refused_for_geometries_the_tap_table_does_not_encode():
+    """The reference accepts any voc_pad / voc_upsample_factors (fatchord_version.py:64-89).  The 5-tap frame-rate
+    path is exact only for pad == 2 and an interpolation response that fits 5 frames; anything else must take the
+    materialised torch conditioning (which equals the reference's upsample by construction)."""
+    import contextlib, io
+    from wavernn_b200 import WaveRNN
+    base = dict(helpers.CTOR)
+
+    def build(**over):
+        with contextlib.redirect_stdout(io.StringIO()):
+            return WaveRNN(mode="MOL", **{**base, **over})
+    assert build()._kernel_conditioning_ok()
+    assert not build(pad=1)._kernel_conditioning_ok()
+    assert not build(pad=3)._kernel_conditioning_ok()
+    wide = build(upsample_factors=(1, 5, 55))              # first factor 1: the response spans more than 5 frames
+    assert wide.upsample.total_scale == 275 and not wide._kernel_conditioning_ok()
+    # the fallback path is the reference layout for every one of them
+    for m in (build(pad=1), build(pad=3), wide):
+        m.eval()
+        T = 9
+        mp = torch.nn.functional.pad(helpers.make_mel(T, 1), (m.pad, m.pad))
+        with torch.no_grad():
+            want_m, want_a = m.upsample(mp)
+            got_m, got_a = m.conditioning(mp, 0, T)
+        np.testing.assert_allclose(got_m.numpy(), want_m[0].numpy(), atol=1e-6)
+        np.testing.assert_allclose(got_a.numpy(), want_a[0].numpy(), atol=1e-6)
+
+
+def test_raw_reference_draws_keep_only_the_local_folds_and_are_bounded():
+    """RAW parity draws (one exponential_() of shape (B, 512) per step): a rank keeps its own folds' rows of the same
+    stream, and an over-large request fails with a pointer to gen_rng='philox' instead of exhausting host memory."""
+    from wavernn_b200.sharding import fold_geometry, shard_folds
+    m = helpers.make_model(0, "RAW")
+    m.gen_native_rng = False
+    geo = fold_geometry(22 * 275, 550, 55)
+    torch.manual_seed(3)
+    _, full = m._reference_draws(geo, 40)
+    assert full.shape == (40, geo.n_seg, 512)
+    np.testing.assert_array_equal(full.numpy(), helpers.replay_expo(3, 40, geo.n_seg, 512))
+    sh = shard_folds(geo, 1, 2, 275)
+    torch.manual_seed(3)
+    _, part = m._reference_draws(geo, 40, shard=sh)
+    np.testing.assert_array_equal(part.numpy(), full[:, sh.seg_first:sh.seg_first + sh.n_seg].numpy())
+    m.gen_max_draw_bytes = 1 << 20
+    with pytest.raises(RuntimeError, match="philox"):
+        m._reference_draws(geo, 660)

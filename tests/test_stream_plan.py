@@ -1,0 +1,191 @@
+"""The stream engine's packed weight stream and static step program (wavernn_b200/csrc/wrnn_stream_plan.h), checked
+WITHOUT a GPU: the library exports the plan for host-resident weights (wrnn_debug_stream_plan); this test interprets it
+with numpy exactly the way the kernel's issuer / epilogue warps do -- chunk by chunk, accumulator by accumulator,
+the h1 ping-pong buffers, in-place h2, the barrier fields as ordering assertions -- and compares samples and logits with
+the engine-arithmetic emulation oracle/contract.py (which tests/test_contract.py pins to the fp32 oracle, which
+tests/test_oracle_golden.py pins to the reference's fixtures).  What remains GPU-only is the PTX (descriptors, TMEM,
+mbarriers), covered by tests/test_gpu_stream.py."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import helpers
+from oracle import contract as CT
+from oracle import wavernn_oracle as O
+from wavernn_b200 import cabi
+
+H, CDIM, NB = 512, 208, 4
+B_COND, B_H1PREV, B_H1NEW, B_H2, B_Y1, B_Y2, B_NONE = 0, 1, 2, 3, 4, 5, 0xFF
+W_NONE, W_COND, W_H1NEW, W_H2NEW, W_Y1, W_Y2 = range(6)
+
+CHUNK = np.dtype([("bytes", "<u4"), ("acc", "u1"), ("nk", "u1"), ("b_buf", "u1"), ("b_buf2", "u1"), ("k0", "<u2"),
+                  ("flags", "u1"), ("wait_b", "u1"), ("wait_acc", "u1"), ("commit", "u1"), ("pad", "<u2")])
+
+
+def get_plan(sd, precision="fp16"):
+    lib = cabi.load()
+    lib.wrnn_debug_stream_plan.restype = C.c_int
+    lib.wrnn_debug_stream_plan.argtypes = [C.c_void_p] * 7
+    cfg = cabi.WrnnCfg(512, 512, 80, 32, 30, cabi.MODE_MOL, {"fp16": cabi.PREC_F16, "bf16": cabi.PREC_BF16}[precision], 3)
+    w = cabi.WrnnWeights()
+    keep = []
+    for field, key in zip(cabi.WEIGHT_FIELDS, cabi.WEIGHT_KEYS):
+        a = np.ascontiguousarray(sd[key], dtype=np.float32)
+        keep.append(a)
+        setattr(w, field, a.ctypes.data)
+    nb, nc = C.c_uint64(0), C.c_uint64(0)
+    assert lib.wrnn_debug_stream_plan(C.byref(cfg), C.byref(w), None, C.byref(nb), None, C.byref(nc), None) == 0
+    blob = np.zeros(nb.value, np.uint8)
+    prog = np.zeros(nc.value, CHUNK)
+    vec = np.zeros(4096 * 2 + 1536 * 2 + 128, np.float32)
+    assert lib.wrnn_debug_stream_plan(C.byref(cfg), C.byref(w), blob.ctypes.data, C.byref(nb), prog.ctypes.data, C.byref(nc),
+                                      vec.ctypes.data) == 0
+    v = dict(qk=vec[:4096], vq=vec[4096:8192], b1h=vec[8192:9728], b2h=vec[9728:11264], b3=vec[11264:])
+    return blob, prog, v
+
+
+def decode_tile(raw, kc, precision):
+    """[128 x kc] K-major no-swizzle operand image -> dense float32 (inverse of stream::tile_index)."""
+    bits = raw.view(np.uint16)
+    r, k = np.meshgrid(np.arange(128), np.arange(kc), indexing="ij")
+    idx = (r // 8) * (kc // 8) * 64 + (k // 8) * 64 + (r % 8) * 8 + (k % 8)
+    vals = bits[idx]
+    if precision == "fp16":
+        return vals.view(np.float16).astype(np.float32)
+    return (vals.astype(np.uint32) << 16).view(np.float32)
+
+
+def sig(x):
+    return (np.float32(1) / (np.float32(1) + np.exp(-x, dtype=np.float32))).astype(np.float32)
+
+
+def interpret(blob, prog, v, m_up, aux, U, *, n_seg, seg_len, seg_stride, steps, precision="fp16", x_force=None):
+    """One CTA of the stream kernel with NF = n_seg folds, in numpy."""
+    rnd = CT.rounder(precision)
+    NF = n_seg
+    L = m_up.shape[0]
+    cond_z = np.concatenate([np.concatenate([m_up, aux], 1).astype(np.float32), np.zeros((1, CDIM), np.float32)])
+    base = np.arange(NF) * seg_stride
+    X = [np.zeros((NF, H), np.float32), np.zeros((NF, H), np.float32)]       # h1 ping-pong (+ y1)
+    H2 = np.zeros((NF, H), np.float32); Y2 = np.zeros((NF, H), np.float32)
+    h1 = np.zeros((H, NF), np.float32); h2 = np.zeros((H, NF), np.float32)   # fp32 state, [unit][fold] like the kernel's scratch
+    x = np.zeros(NF, np.float32)
+    acc = np.zeros((16, 128, NF), np.float32)
+    out = np.zeros((NF, steps), np.float32); logits = np.zeros((steps, NF, 30), np.float32)
+    offs = np.concatenate([[0], np.cumsum(prog["bytes"].astype(np.int64))])
+    assert offs[-1] == blob.size
+    tiles = [decode_tile(blob[offs[i]:offs[i + 1]], int(c["nk"]) * 16, precision) for i, c in enumerate(prog)]
+    for t in range(steps):
+        cur = t & 1
+        cond = rnd(cond_z[np.minimum(base + t, L)])
+        ready = {W_COND}                      # staging runs ahead of the step
+        waited = set()
+        n_commit = [0] * NB                   # phase of each block within the step
+        acc_drained = [True] * NB
+        h2_touched = False
+        xs = x.copy()
+        for i, c in enumerate(prog):
+            def image(buf):
+                if buf == B_COND: return cond
+                if buf in (B_H1PREV, B_Y1): return X[cur]
+                if buf == B_H1NEW: return X[cur ^ 1]
+                return H2 if buf == B_H2 else Y2
+            if c["wait_acc"]:
+                blk = int(c["wait_acc"]) - 1
+                assert acc_drained[blk], f"chunk {i}: accumulators of block {blk} not drained"
+            blk_of_acc = int(c["acc"]) // 4
+            if c["wait_b"]:
+                assert int(c["wait_b"]) in ready, f"chunk {i} waits for operand {c['wait_b']} that no epilogue of this step produces before it"
+                waited.add(int(c["wait_b"]))
+            need = {B_COND: W_COND, B_H1NEW: W_H1NEW, B_Y1: W_Y1, B_Y2: W_Y2}
+            for buf in (int(c["b_buf"]), int(c["b_buf2"])):
+                if buf == B_NONE: continue
+                if buf in need: assert need[buf] in waited, f"chunk {i} reads operand {buf} without having waited for it"
+                if buf == B_H2 and h2_touched: assert W_H2NEW in waited, f"chunk {i} reads h2 while the GRU2 epilogue rewrites it"
+            k0, kc = int(c["k0"]), int(c["nk"]) * 16
+            a = int(c["acc"])
+            if c["flags"] & 1:
+                acc[a] = 0
+            acc_drained[blk_of_acc] = False
+            acc[a] += tiles[i] @ image(int(c["b_buf"]))[:, k0:k0 + kc].T
+            if c["b_buf2"] != B_NONE:
+                acc[a] += tiles[i] @ image(int(c["b_buf2"]))[:, k0:k0 + kc].T
+            if c["commit"]:
+                b = int(c["commit"]) - 1
+                ph = n_commit[b]; n_commit[b] += 1
+                u = slice(b * 128, b * 128 + 128)
+                if ph in (0, 1):                       # GRU1 / GRU2
+                    q0 = ph * 3 * H
+                    qk, vq, bh = v["qk"], v["vq"], (v["b2h"] if ph else v["b1h"])
+                    hs = h2 if ph else h1
+                    g = lambda j, arr: arr[q0 + j * H + b * 128: q0 + j * H + b * 128 + 128][:, None]
+                    gb = lambda j: bh[j * H + b * 128: j * H + b * 128 + 128][:, None]
+                    r = sig(acc[4 * b + 0] + g(0, qk) + xs[None, :] * g(0, vq) + gb(0))
+                    z = sig(acc[4 * b + 1] + g(1, qk) + xs[None, :] * g(1, vq) + gb(1))
+                    n = np.tanh(acc[4 * b + 2] + g(2, qk) + xs[None, :] * g(2, vq) + r * (acc[4 * b + 3] + gb(2))).astype(np.float32)
+                    hn = ((np.float32(1) - z) * n + z * hs[u]).astype(np.float32)
+                    hs[u] = hn
+                    (H2 if ph else X[cur ^ 1])[:, u] = rnd(hn).T
+                    if ph: h2_touched = True
+                    if n_commit == [ph + 1] * NB: ready.add(W_H2NEW if ph else W_H1NEW)
+                elif ph in (2, 3):                     # fc1 / fc2
+                    q0 = 6 * H + (ph - 2) * H
+                    y = np.maximum(acc[4 * b + (ph - 2)] + v["qk"][q0 + b * 128: q0 + b * 128 + 128][:, None]
+                                   + xs[None, :] * v["vq"][q0 + b * 128: q0 + b * 128 + 128][:, None], 0).astype(np.float32)
+                    (Y2 if ph == 3 else X[cur])[:, u] = rnd(y).T
+                    if n_commit == [ph + 1] * NB: ready.add(W_Y2 if ph == 3 else W_Y1)
+                else:                                  # fc3 + sampler
+                    assert b == 0 and ph == 4
+                    lg = (acc[2][:30] + v["b3"][:30, None]).T.astype(np.float32)
+                    logits[t] = lg
+                    u_t = U[t]
+                    x = O.mol_sample(lg, u_t[:10 * NF].reshape(NF, 10), u_t[10 * NF:11 * NF]).astype(np.float32)
+                    out[:, t] = x
+                    if x_force is not None:
+                        x = x_force[t].astype(np.float32)
+                acc_drained[b] = True
+        assert n_commit == [5, 4, 4, 4]
+    return out, logits
+
+
+@pytest.mark.skipif(not cabi.is_built(), reason="library not built")
+@pytest.mark.parametrize("precision", ["fp16", "bf16"])
+def test_stream_plan_interpreted_on_the_cpu_equals_the_engine_contract(precision):
+    model = helpers.make_model(0, "MOL")
+    sd = helpers.state_numpy(model)
+    w = O.hot_weights(sd)
+    blob, prog, v = get_plan(sd, precision)
+    # structure: the whole weight set once per step, one 16-byte record per chunk
+    assert blob.size == 2 * (4096 * 208 + (3 * 1536 + 2 * 512 + 128) * 512)
+    assert int((prog["nk"].astype(int) * np.where(prog["b_buf2"] == B_NONE, 1, 2)).sum()) == 32 * 13 + 36 * 32 + 4 * 64 + 4 * 32 + 32
+    assert set(np.unique(prog["bytes"])) == {4096, 16384} and prog["acc"].max() <= 15
+    rs = np.random.RandomState(1)
+    n_seg, seg_len, stride = 16, 40, 25
+    L = (n_seg - 1) * stride + 30                                  # the last folds run past the end of the stream
+    m_up, aux = rs.rand(L, 80).astype(np.float32), rs.randn(L, 128).astype(np.float32)
+    U = helpers.replay_uniforms(5, seg_len, n_seg)
+    kw = dict(n_seg=n_seg, seg_len=seg_len, seg_stride=stride)
+    out, lg = interpret(blob, prog, v, m_up, aux, U, steps=seg_len, precision=precision, **kw)
+    emu, lemu = CT.generate_segments(w, m_up, aux, uniforms=U, precision=precision, want_logits=True, **kw)
+    print(precision, "plan vs contract: samples", np.abs(out - emu).max(), "logits", np.abs(lg - lemu).max())
+    assert np.abs(lg - lemu).max() <= (1e-3 if precision == "fp16" else 2e-2)
+    assert np.abs(out - emu).max() <= (1e-3 if precision == "fp16" else 2e-2)
+
+
+@pytest.mark.skipif(not cabi.is_built(), reason="library not built")
+def test_stream_plan_on_the_trained_checkpoint_teacher_forced():
+    """Shipped checkpoint, real Tacotron mel, inputs forced to the reference's own samples: the interpreted plan's
+    logits stay within the fp16 tolerances stated for the GPU engines (tests/test_gpu_trained.py)."""
+    g = helpers.load_golden("trained_tacotron.npz")
+    sd = {k: v.numpy() for k, v in helpers.pretrained_state_dict().items()}
+    blob, prog, v = get_plan(sd, "fp16")
+    mel = helpers.tacotron_mels()[int(g["sentence"])]
+    m_up, aux = O.upsample_network(sd, O.pad_time(mel.T, 2).T, pad=2)
+    U = helpers.replay_uniforms(int(g["seed"]), 12100, 4)
+    steps = 120
+    out, lg = interpret(blob, prog, v, m_up, aux, U, n_seg=4, seg_len=12100, seg_stride=11550, steps=steps,
+                        x_force=g["raw"].T[:steps].copy())
+    e = np.abs(lg - g["logits"][:steps])
+    print("trained, teacher forced, interpreted plan: max", e.max(), "median", np.median(e))
+    assert e.max() <= 1e-1 and np.median(e) <= 1e-3

@@ -15,9 +15,9 @@ LIB_PATH = Path(__file__).with_name(LIB_NAME)
 WRNN_OK, WRNN_E_INVALID, WRNN_E_CUDA, WRNN_E_NO_DEVICE, WRNN_E_WATCHDOG, WRNN_E_BUSY = 0, -1, -2, -3, -4, -5
 MODE_MOL, MODE_RAW = 0, 1
 PREC_F16, PREC_FP32, PREC_BF16 = 0, 1, 2
-ENGINE_AUTO, ENGINE_SIMT, ENGINE_TCGEN05 = 0, 1, 2
+ENGINE_AUTO, ENGINE_SIMT, ENGINE_TCGEN05, ENGINE_STREAM = 0, 1, 2, 3
 COND_AUTO, COND_EXPAND, COND_IN_KERNEL = 0, 1, 2
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 EXPORTS = ("wrnn_abi_version", "wrnn_last_error", "wrnn_create", "wrnn_destroy", "wrnn_generate",
            "wrnn_check", "wrnn_generate_host", "wrnn_engine_name", "wrnn_grid_ctas", "wrnn_launch_count",
@@ -132,7 +132,7 @@ class Engine:
         cfg = WrnnCfg(rnn_dims, fc_dims, feat_dims, aux_dims, n_classes,
                       {"MOL": MODE_MOL, "RAW": MODE_RAW}[mode],
                       {"fp16": PREC_F16, "bf16": PREC_BF16, "fp32": PREC_FP32}[precision],
-                      {"auto": ENGINE_AUTO, "simt": ENGINE_SIMT, "tcgen05": ENGINE_TCGEN05}[engine])
+                      {"auto": ENGINE_AUTO, "simt": ENGINE_SIMT, "tcgen05": ENGINE_TCGEN05, "stream": ENGINE_STREAM}[engine])
         w = WrnnWeights()
         keep = []
         for field, key in zip(WEIGHT_FIELDS, WEIGHT_KEYS):

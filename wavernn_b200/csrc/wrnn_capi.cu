@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "wrnn_engine.h"
+#include "wrnn_stream_plan.h"
 
 namespace wrnn {
 static thread_local std::string g_last_error;
@@ -49,7 +50,7 @@ int wrnn_create(wrnn_t** out, const wrnn_cfg* cfg, const wrnn_weights* w, int de
   WRNN_CUDA_OK(cudaSetDevice(device));
   cudaDeviceProp prop;
   WRNN_CUDA_OK(cudaGetDeviceProperties(&prop, device));
-  if (prop.major != 10) {
+  if (prop.major != 10 || prop.minor != 0) {        // only an sm_100a cubin is built: sm_101 / sm_103 would fail at launch
     set_error(std::string("device '") + prop.name + "' is sm_" + std::to_string(prop.major * 10 + prop.minor) +
               "; this library is built for sm_100a only");
     return WRNN_E_NO_DEVICE;
@@ -75,7 +76,9 @@ int wrnn_create(wrnn_t** out, const wrnn_cfg* cfg, const wrnn_weights* w, int de
     engine = WRNN_ENGINE_SIMT;
   }
   if (engine == WRNN_ENGINE_AUTO) engine = WRNN_ENGINE_TCGEN05;
-  if (engine == WRNN_ENGINE_TCGEN05) {
+  if (engine == WRNN_ENGINE_STREAM) {
+    rc = make_stream_engine(*cfg, hw, device, &eng);
+  } else if (engine == WRNN_ENGINE_TCGEN05) {
     rc = make_tc_engine(*cfg, hw, device, &eng);
     if (rc != WRNN_OK && cfg->engine == WRNN_ENGINE_AUTO && rc == WRNN_E_INVALID) {
       // configuration outside the tensor-core engine's envelope: AUTO may pick the SIMT engine
@@ -95,8 +98,25 @@ int wrnn_create(wrnn_t** out, const wrnn_cfg* cfg, const wrnn_weights* w, int de
   return WRNN_OK;
 }
 
-// ENGINE_AUTO: jobs outside the tensor-core engine's envelope go to the SIMT engine (same arithmetic contract).
+// Folds from which ENGINE_AUTO hands a job to the stream engine: the persistent engine serves tiles of 64 folds one
+// after the other at ~15.5 us per step each, the stream engine serves all folds at once at ~one weight pass per step
+// (profiles/r02_stream.md), so it wins from a few tiles on.  WRNN_STREAM_MIN_FOLDS overrides (experiments).
+static int stream_min_folds() {
+  static const int v = [] { const char* e = getenv("WRNN_STREAM_MIN_FOLDS"); return e ? atoi(e) : 192; }();
+  return v;
+}
+
+// ENGINE_AUTO: many-fold MoL jobs go to the stream engine; jobs outside the tensor-core engine's envelope go to the
+// SIMT engine (same arithmetic contract).
 static int pick_engine(wrnn_t* h, const wrnn_job* job, Engine** out) {
+  if (h->auto_engine && h->host_weights && job->n_seg >= stream_min_folds() && h->engine->cfg.mode == WRNN_MODE_MOL &&
+      h->engine->cfg.n_classes == 30 && h->engine->cfg.precision != WRNN_PREC_FP32 && !h->stream_failed) {
+    if (!h->stream) {
+      const int rc = make_stream_engine(h->engine->cfg, *h->host_weights, h->engine->device, &h->stream);
+      if (rc != WRNN_OK) h->stream_failed = true;
+    }
+    if (h->stream && h->stream->supports(*job)) { *out = h->stream; return WRNN_OK; }
+  }
   if (h->engine->supports(*job)) { *out = h->engine; return WRNN_OK; }
   if (!h->auto_engine || !h->host_weights) {
     set_error(std::string("job is outside the envelope of engine '") + h->engine->name() + "'");
@@ -115,6 +135,7 @@ void wrnn_destroy(wrnn_t* h) {
   if (h->d_stage) cudaFree(h->d_stage);
   delete h->engine;
   delete h->fallback;
+  delete h->stream;
   delete h->host_weights;
   delete h;
 }
@@ -202,7 +223,7 @@ int wrnn_generate_host(wrnn_t* h, const wrnn_job* job) {
 const char* wrnn_engine_name(const wrnn_t* h) { return (h && h->last) ? h->last->name() : ""; }
 int wrnn_grid_ctas(const wrnn_t* h) { return (h && h->last) ? h->last->grid_ctas() : 0; }
 int64_t wrnn_launch_count(const wrnn_t* h) {
-  return (h && h->engine) ? h->engine->launches + (h->fallback ? h->fallback->launches : 0) : 0;
+  return (h && h->engine) ? h->engine->launches + (h->fallback ? h->fallback->launches : 0) + (h->stream ? h->stream->launches : 0) : 0;
 }
 
 int wrnn_expand_conditioning(const float* mel_frames, const float* aux_frames, const float* up_taps, int32_t hop, int64_t row_lo,
@@ -213,6 +234,41 @@ int wrnn_expand_conditioning(const float* mel_frames, const float* aux_frames, c
     return WRNN_E_INVALID;
   }
   return expand_conditioning(mel_frames, aux_frames, up_taps, hop, row_lo, n_rows, mels_up, aux, static_cast<cudaStream_t>(stream));
+}
+
+// Test hook (CPU-only, no device needed): the stream engine's packed weight stream and step program for host-resident
+// weights, so the packing and the schedule can be interpreted and checked without a GPU (tests/test_stream_plan.py).
+// Call with blob == NULL to obtain the sizes.  Not part of the reference-facing surface.
+int wrnn_debug_stream_plan(const wrnn_cfg* cfg, const wrnn_weights* w, uint8_t* blob, uint64_t* blob_bytes, uint8_t* prog,
+                           uint64_t* n_chunks, float* vectors /* qk[4096] vq[4096] b1h[1536] b2h[1536] b3[128] */) {
+  if (!cfg || !w || !blob_bytes || !n_chunks) { set_error("null argument"); return WRNN_E_INVALID; }
+  HostWeights hw;
+  hw.n_classes = cfg->n_classes;
+  const size_t W2W = H + AUXD;
+  auto take = [&](std::vector<float>& dst, const float* src, size_t n) { dst.assign(src, src + n); };
+  take(hw.I_w, w->I_weight, (size_t)H * (1 + F1IN)); take(hw.I_b, w->I_bias, H);
+  take(hw.w1i, w->rnn1_weight_ih, (size_t)G3 * H); take(hw.w1h, w->rnn1_weight_hh, (size_t)G3 * H);
+  take(hw.b1i, w->rnn1_bias_ih, G3); take(hw.b1h, w->rnn1_bias_hh, G3);
+  take(hw.w2i, w->rnn2_weight_ih, (size_t)G3 * W2W); take(hw.w2h, w->rnn2_weight_hh, (size_t)G3 * H);
+  take(hw.b2i, w->rnn2_bias_ih, G3); take(hw.b2h, w->rnn2_bias_hh, G3);
+  take(hw.f1w, w->fc1_weight, (size_t)H * W2W); take(hw.f1b, w->fc1_bias, H);
+  take(hw.f2w, w->fc2_weight, (size_t)H * W2W); take(hw.f2b, w->fc2_bias, H);
+  take(hw.f3w, w->fc3_weight, (size_t)cfg->n_classes * H); take(hw.f3b, w->fc3_bias, cfg->n_classes);
+  stream::Plan plan;
+  stream::build_plan(hw, cfg->precision == WRNN_PREC_BF16, plan);
+  if (blob) {
+    if (*blob_bytes < plan.blob.size() || *n_chunks < plan.prog.size()) { set_error("buffers too small"); return WRNN_E_INVALID; }
+    std::memcpy(blob, plan.blob.data(), plan.blob.size());
+    std::memcpy(prog, plan.prog.data(), plan.prog.size() * sizeof(stream::Chunk));
+    float* v = vectors;
+    std::memcpy(v, plan.qk.data(), 8 * H * 4); v += 8 * H;
+    std::memcpy(v, plan.vq.data(), 8 * H * 4); v += 8 * H;
+    std::memcpy(v, plan.b1h.data(), G3 * 4); v += G3;
+    std::memcpy(v, plan.b2h.data(), G3 * 4); v += G3;
+    std::memcpy(v, plan.b3.data(), stream::MROWS * 4);
+  }
+  *blob_bytes = plan.blob.size(); *n_chunks = plan.prog.size();
+  return WRNN_OK;
 }
 
 }  // extern "C"

@@ -33,6 +33,10 @@ constexpr long long kWatchdogCycles = 1ll << 32;
 
 // Grid-wide barrier over a monotonically increasing counter: the k-th barrier of a launch
 // waits for counter >= k * gridDim.x.  Returns false when the launch must be abandoned.
+// The comparison is wrap-safe (signed distance): the 32-bit counter may roll over on very long unbatched jobs
+// (6 barriers x 128 CTAs per step wrap after ~5.6 M steps); CTAs are never more than one barrier apart, so the
+// distance between counter and target is always far below 2^31.
+__device__ __forceinline__ bool counter_behind(unsigned value, unsigned target) { return (int)(value - target) < 0; }
 __device__ __forceinline__ bool grid_barrier(unsigned* counter, unsigned target, int* abort_flag) {
   __shared__ int s_ok;
   __syncthreads();
@@ -41,7 +45,7 @@ __device__ __forceinline__ bool grid_barrier(unsigned* counter, unsigned target,
                                         // thread 0 by the bar.sync above) before the increment
     int ok = 1;
     const long long t0 = clock64();
-    while (ld_acquire_u32(counter) < target) {
+    while (counter_behind(ld_acquire_u32(counter), target)) {
       if (clock64() - t0 > kWatchdogCycles || ld_relaxed_s32(abort_flag) != 0) {
         atomicExch(abort_flag, 1);
         ok = 0;

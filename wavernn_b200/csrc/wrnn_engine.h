@@ -37,6 +37,8 @@ class Engine {
 int make_simt_engine(const wrnn_cfg& cfg, const HostWeights& w, int device, Engine** out);
 // tcgen05 engine: 5th-gen tensor-core contractions with TMEM accumulators (bf16 operands).
 int make_tc_engine(const wrnn_cfg& cfg, const HostWeights& w, int device, Engine** out);
+// stream engine (wrnn_stream.cu): activation-stationary, weights streamed from L2; the throughput form for many folds
+int make_stream_engine(const wrnn_cfg& cfg, const HostWeights& w, int device, Engine** out);
 // conditioning pre-pass (wrnn_tc.cu): rows [row_lo, row_lo + n_rows) of the per-sample stream from frame-rate tensors
 int expand_conditioning(const float* mel_frames, const float* aux_frames, const float* up_taps, int hop, long long row_lo,
                         long long n_rows, float* mels_up, float* aux, cudaStream_t stream);
@@ -46,9 +48,11 @@ int expand_conditioning(const float* mel_frames, const float* aux_frames, const 
 struct wrnn_handle {
   wrnn::Engine* engine = nullptr;          // engine chosen at create time
   wrnn::Engine* fallback = nullptr;        // ENGINE_AUTO only: SIMT engine, created on first job outside `engine`'s envelope
+  wrnn::Engine* stream = nullptr;          // ENGINE_AUTO only: stream engine, created on the first job with many folds
   wrnn::Engine* last = nullptr;            // engine that served the most recent job
   wrnn::HostWeights* host_weights = nullptr;
   bool auto_engine = false;
+  bool stream_failed = false;
   // staging for wrnn_generate_host
   void* d_stage = nullptr;
   size_t stage_bytes = 0;

@@ -25,13 +25,26 @@ inline uint32_t mix(uint32_t a, uint32_t b, uint32_t far) {
 }
 
 // next block of 624 words, in place.  The first loop only reads words that are still old, the second reads words
-// written at least 227 iterations earlier: both vectorise.
-void twist(uint32_t* __restrict__ mt) {
+// written at least 227 iterations earlier: both vectorise (8 words per instruction with AVX2 -- the skipped / foreign
+// part of the draw matrix of a sharded job costs one twist per 624 words, so this loop IS the replay's cost).
+inline __attribute__((always_inline)) void twist_body(uint32_t* __restrict__ mt) {
   int i = 0;
   for (; i < N - M; ++i) mt[i] = mix(mt[i], mt[i + 1], mt[i + M]);
   for (; i < N - 1; ++i) mt[i] = mix(mt[i], mt[i + 1], mt[i + M - N]);
   mt[N - 1] = mix(mt[N - 1], mt[0], mt[M - 1]);
 }
+#if defined(__x86_64__)
+__attribute__((target("avx2"))) void twist_avx2(uint32_t* __restrict__ mt) { twist_body(mt); }
+#endif
+void twist_base(uint32_t* __restrict__ mt) { twist_body(mt); }
+using twist_fn = void (*)(uint32_t*);
+twist_fn pick_twist() {
+#if defined(__x86_64__)
+  if (__builtin_cpu_supports("avx2")) return twist_avx2;
+#endif
+  return twist_base;
+}
+const twist_fn twist = pick_twist();
 
 inline uint32_t temper(uint32_t y) {
   y ^= y >> 11;

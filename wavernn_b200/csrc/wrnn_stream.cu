@@ -1,0 +1,577 @@
+// wrnn_stream.cu -- STREAM engine: the throughput form of the generate() loop (reference models/fatchord_version.py:
+// 201-241 + utils/distribution.py:87-123) for jobs with many folds (BASELINE configs[3], configs[4]).
+//
+// wrnn_tc.cu keeps the weights stationary (row-sharded over 128 SMs) and pays four all-to-all exchanges of the
+// activations per step: right for 19 folds, wrong for 4096 (every exchange broadcasts the whole tile's activations to
+// 128 SMs through L2).  Here the ACTIVATIONS are stationary: one CTA owns NF folds (16 or 32) for the whole sequence,
+// runs every layer for them, and streams the 7.4 MB of fp16 weights from L2 each step through a shared-memory ring of
+// TMA bulk copies -- no inter-SM synchronisation at all, one independent CTA per fold tile, any number of tiles.
+// The step is the static program of wrnn_stream_plan.h (chunk list with accumulator / operand / barrier fields).
+//
+// Swap-AB tcgen05: D[128 weight rows, NF folds] (+)= W[128, 16] * act[NF, 16]^T, kind::f16, fp32 accumulators in
+// TMEM (16 accumulators of NF columns).  TMEM lane == weight row == hidden unit, so the r / z / n pre-activations of a
+// unit are in the same lane of different accumulators and the gate math is thread-local: thread u of the four
+// epilogue warps owns unit 128 b + u of block b for all NF folds.  The fp32 hidden state lives in L2-resident global
+// scratch ([2][512][NF] per tile); the fp16 operand images of h1', h2', y1, y2 live in shared memory.
+//
+// Warp roles (256 threads, no CTA-wide barrier inside the loop):
+//   warp 0     producer : walks the chunk list, one cp.async.bulk per chunk into the ring (full/empty mbarriers)
+//   warp 1     issuer   : waits for operands / accumulators / ring slots, issues the MMAs, commits slot-empty,
+//                         accumulator-full and cond-free barriers with tcgen05.commit
+//   warps 2-3  staging  : conditioning row of step t+1 for the NF folds (stream or frame-rate form) -> fp16 image
+//   warps 4-7  epilogue : TMEM -> registers, gates / relu / MoL sampler (SFU), state, operand images, output
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "wrnn_device.cuh"
+#include "wrnn_engine.h"
+#include "wrnn_stream_plan.h"
+#include "wrnn_tc_common.cuh"
+
+namespace wrnn {
+namespace {
+using namespace tc;
+using namespace stream;
+
+constexpr int NT = 256;
+constexpr int KQ = CDIM / 8;                 // 26 16-byte chunks per conditioning row
+constexpr int SBO_Q = KQ * 128;              // 3328: stride between 8-fold groups of the conditioning image
+constexpr int SBO_H = (H / 8) * 128;         // 8192: same for the K = 512 images
+constexpr int TMEM_COLS = 512;
+constexpr int NBAR = 32;
+
+template <int NF> struct Smem {
+  static constexpr int GROUPS = NF / 8;
+  static constexpr int ACT = GROUPS * SBO_H;                 // one K = 512 activation image
+  static constexpr int COND = GROUPS * SBO_Q;                // one conditioning image
+  static constexpr int OFF_X0 = 0, OFF_X1 = ACT, OFF_H2 = 2 * ACT, OFF_Y2 = 3 * ACT;
+  static constexpr int OFF_COND = 4 * ACT;                   // two conditioning images (double buffer)
+  static constexpr int OFF_RING = (OFF_COND + 2 * COND + 1023) / 1024 * 1024;
+  static constexpr int LOGP = 33;                                            // padded row of the logits transpose (conflict-free both ways)
+  static constexpr int MISC = LOGP * NF * 4 + NF * 4 + NBAR * 8 + 64;        // logits transpose, x, barriers, tmem slot
+  static constexpr int STAGES = (227 * 1024 - OFF_RING - MISC) / CHUNK_BYTES > 8 ? 8 : (227 * 1024 - OFF_RING - MISC) / CHUNK_BYTES;
+  static constexpr int OFF_LOG = OFF_RING + STAGES * CHUNK_BYTES;            // [NF][LOGP] fp32
+  static constexpr int OFF_XS = OFF_LOG + LOGP * NF * 4;                       // [NF] fp32: previous sample per fold
+  static constexpr int OFF_BAR = OFF_XS + NF * 4;
+  static constexpr int BYTES = OFF_BAR + NBAR * 8 + 64;
+  static_assert(STAGES >= 3, "ring too shallow");
+  static_assert(BYTES <= 227 * 1024, "shared memory budget");
+};
+// barrier indices
+constexpr int BAR_FULL = 0, BAR_EMPTY = 8, BAR_ACC_FULL = 16, BAR_ACC_EMPTY = 20, BAR_READY = 24 /* +W_* (1..5), cond uses 24 and 25 */,
+              BAR_COND_FREE = 30;
+// ready barriers: index 24 + {0: cond[0], 1: cond[1], 2: h1new, 3: h2new, 4: y1, 5: y2}
+
+struct StreamParams {
+  const unsigned char* blob; const uint4* prog; int n_chunks;
+  const float* qk; const float* vq; const float* b1h; const float* b2h; const float* b3;
+  const float* mels_up; const float* aux; long long L; long long seg_stride; long long row_base;
+  int n_total, steps, out_pitch, seg_first;
+  const float* uniforms; unsigned long long seed, offset;
+  float* out; const float* x_force; float* logits_out;
+  const long long* fold_row0; const long long* fold_row_end;
+  const float* mel_frames; const float* aux_frames; const float* up_taps; int hop;
+  float* state;                 // [tiles][2][H][NF] fp32 hidden state
+  int* abort_flag;
+  long long* prof;              // optional cycle counters of CTA 0
+};
+
+template <int NF, int FMT, bool FRAMES>
+__global__ void __launch_bounds__(NT, 1) wrnn_stream_kernel(const StreamParams p) {
+  using SM = Smem<NF>;
+  extern __shared__ __align__(1024) unsigned char smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM::OFF_BAR);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM::OFF_BAR + NBAR * 8);
+  volatile int* s_abort = reinterpret_cast<volatile int*>(smem + SM::OFF_BAR + NBAR * 8 + 16);   // CTA-local copy of the abort flag
+  float* x_s = reinterpret_cast<float*>(smem + SM::OFF_XS);
+  float* log_s = reinterpret_cast<float*>(smem + SM::OFF_LOG);
+  auto bar = [&](int i) -> uint32_t { return smem_u32(&bars[i]); };
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tile = blockIdx.x, f0 = tile * NF;
+  const int B = (p.n_total - f0 < NF) ? (p.n_total - f0) : NF;          // real folds of this tile
+  const int S = p.steps;
+
+  // ---- setup ----------------------------------------------------------------------------------------------------
+  {
+    int4* z = reinterpret_cast<int4*>(smem);
+    for (int i = tid; i < SM::OFF_RING / 16; i += NT) z[i] = make_int4(0, 0, 0, 0);       // all operand images start as zeros
+    if (tid < NF) x_s[tid] = 0.f;
+    if (tid == 0) *s_abort = 0;
+  }
+  if (tid == 0) {
+    for (int i = 0; i < SM::STAGES; ++i) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar(BAR_FULL + i)));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar(BAR_EMPTY + i)));
+    }
+    for (int i = 0; i < 4; ++i) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar(BAR_ACC_FULL + i)));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 128;" :: "r"(bar(BAR_ACC_EMPTY + i)));
+    }
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 64;" :: "r"(bar(BAR_READY + 0)));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 64;" :: "r"(bar(BAR_READY + 1)));
+    for (int i = 2; i < 6; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 128;" :: "r"(bar(BAR_READY + i)));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar(BAR_COND_FREE + 0)));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar(BAR_COND_FREE + 1)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "n"(TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  proxy_fence_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  // Bounded wait (a protocol bug must end in WRNN_E_WATCHDOG, never in a hung GPU): once any wait of this CTA has given
+  // up, or another CTA has raised the global flag, every later wait returns at once and the role loops end.
+  auto wait = [&](uint32_t b, uint32_t parity) {
+    if (mbar_try(b, parity)) return;
+    if (*s_abort) return;
+    const long long t0 = clock64();
+    unsigned spins = 0;
+    while (!mbar_try(b, parity)) {
+      if ((++spins & 1023u) == 0) {
+        if (*s_abort) return;
+        if (ld_relaxed_s32(p.abort_flag) != 0) { *s_abort = 1; return; }
+        if (clock64() - t0 > kWatchdogCycles) { atomicExch(p.abort_flag, 2); *s_abort = 1; return; }
+      }
+    }
+  };
+
+  if (warp == 0) {
+    // ===================================================================================================== producer
+    unsigned g = 0;                                           // chunks issued so far (ring position)
+    for (int t = 0; t < S && !*s_abort; ++t) {
+      size_t off = 0;
+      for (int c = 0; c < p.n_chunks; ++c, ++g) {
+        const uint32_t bytes = __ldg(reinterpret_cast<const uint32_t*>(p.prog + c));
+        const int slot = g % SM::STAGES;
+        wait(bar(BAR_EMPTY + slot), ((g / SM::STAGES) & 1) ^ 1);      // slot drained by the MMAs
+        tma_bulk_g2s(smem_u32(smem + SM::OFF_RING + slot * CHUNK_BYTES), p.blob + off, bytes, bar(BAR_FULL + slot));
+        off += bytes;
+      }
+    }
+  } else if (warp == 1) {
+    // ======================================================================================================= issuer
+    const uint32_t idesc = umma_idesc(MROWS, NF, FMT);
+    unsigned g = 0, acc_par = 0, acc_seen = 0;               // per block: parity of / any accumulator-free waits so far
+    const bool profiling = p.prof != nullptr && blockIdx.x == 0;
+    long long t_ring = 0, t_b = 0, t_acc = 0, t_issue = 0;
+    for (int t = 0; t < S && !*s_abort; ++t) {
+      const int cur = t & 1;
+      for (int c = 0; c < p.n_chunks; ++c, ++g) {
+        const uint4 raw = __ldg(p.prog + c);
+        const uint32_t acc = raw.y & 0xff, nk = (raw.y >> 8) & 0xff, b_buf = (raw.y >> 16) & 0xff, b_buf2 = raw.y >> 24;
+        const uint32_t k0 = raw.z & 0xffff, flags = (raw.z >> 16) & 0xff, wait_b = raw.z >> 24;
+        const uint32_t wait_acc = raw.w & 0xff, commit = (raw.w >> 8) & 0xff;
+        long long c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+        if (profiling) c0 = clock64();
+        if (wait_acc) {                                       // the epilogue of the previous phase has drained this block
+          const int blk = wait_acc - 1;                       // wait number k (k >= 1) needs completion k-1 of the barrier
+          if ((acc_seen >> blk) & 1u) wait(bar(BAR_ACC_EMPTY + blk), ((acc_par >> blk) & 1u) ^ 1u);
+          acc_seen |= 1u << blk; acc_par ^= 1u << blk;
+        }
+        if (profiling) c1 = clock64();
+        if (wait_b == W_COND) wait(bar(BAR_READY + cur), (uint32_t)(t >> 1) & 1);
+        else if (wait_b != W_NONE) wait(bar(BAR_READY + wait_b), (uint32_t)t & 1);
+        if (profiling) c2 = clock64();
+        const int slot = g % SM::STAGES;
+        wait(bar(BAR_FULL + slot), (g / SM::STAGES) & 1);
+        tc_fence_after();
+        if (profiling) c3 = clock64();
+        auto b_desc = [&](uint32_t buf) -> uint64_t {
+          // h1 ping-pong: this step's h1 (previous state) is X[cur], the new h1' goes to X[cur^1]; y1 reuses X[cur]
+          uint32_t base, sbo = SBO_H;
+          switch (buf) {
+            case B_COND: base = SM::OFF_COND + cur * SM::COND; sbo = SBO_Q; break;
+            case B_H1PREV: case B_Y1: base = cur ? SM::OFF_X1 : SM::OFF_X0; break;
+            case B_H1NEW: base = cur ? SM::OFF_X0 : SM::OFF_X1; break;
+            case B_H2: base = SM::OFF_H2; break;
+            default: base = SM::OFF_Y2; break;
+          }
+          return umma_desc(smem_u32(smem + base) + k0 * 16, 128, sbo);
+        };
+        const uint64_t dA = umma_desc(smem_u32(smem + SM::OFF_RING + slot * CHUNK_BYTES), 128, nk * 256);
+        const uint64_t dB = b_desc(b_buf);
+        const uint32_t d_col = tmem + acc * NF;
+        for (uint32_t k = 0; k < nk; ++k) umma_f16(d_col, dA + (uint64_t)(k * 16), dB + (uint64_t)(k * 16), idesc, (k > 0 || !(flags & F_FIRST)) ? 1u : 0u);
+        if (b_buf2 != B_NONE) {
+          const uint64_t dB2 = b_desc(b_buf2);
+          for (uint32_t k = 0; k < nk; ++k) umma_f16(d_col, dA + (uint64_t)(k * 16), dB2 + (uint64_t)(k * 16), idesc, 1u);
+        }
+        umma_commit(bar(BAR_EMPTY + slot));
+        if (commit) umma_commit(bar(BAR_ACC_FULL + commit - 1));
+        if (flags & F_COND_RELEASE) umma_commit(bar(BAR_COND_FREE + cur));
+        if (profiling) { const long long c4 = clock64(); t_acc += c1 - c0; t_b += c2 - c1; t_ring += c3 - c2; t_issue += c4 - c3; }
+      }
+    }
+    if (profiling && lane == 0) { p.prof[0] = t_acc; p.prof[1] = t_b; p.prof[2] = t_ring; p.prof[3] = t_issue; }
+  } else if (warp < 4) {
+    // ====================================================================================================== staging
+    // cond_s (fp32 rows of the per-sample conditioning stream, or built from frame-rate tensors) -> fp16 image of step s,
+    // one step ahead of the MMAs.  (fold, 8-column chunk) tasks, 64 threads.
+    const int st = tid - 64;
+    auto row0_of = [&](int f) -> long long {
+      return p.fold_row0 ? __ldg(p.fold_row0 + f0 + f) : (long long)(f0 + f + (FRAMES ? p.seg_first : 0)) * p.seg_stride - p.row_base;
+    };
+    auto end_of = [&](int f) -> long long { return p.fold_row_end ? __ldg(p.fold_row_end + f0 + f) : p.L; };
+    constexpr int TASKS = (NF * KQ + 63) / 64;
+    long long t_row0[TASKS], t_left[TASKS];
+#pragma unroll
+    for (int j = 0; j < TASKS; ++j) {
+      const int task = st + j * 64, f = task / KQ;
+      t_row0[j] = 0; t_left[j] = 0;
+      if (task < NF * KQ && f < B) { t_row0[j] = row0_of(f); t_left[j] = end_of(f) - t_row0[j]; }
+    }
+    for (int s = 0; s < S && !*s_abort; ++s) {
+      const int par = s & 1;
+      if (s >= 2) wait(bar(BAR_COND_FREE + par), (uint32_t)((s >> 1) - 1) & 1);   // step s-2 has consumed this buffer
+      unsigned char* img = smem + SM::OFF_COND + par * SM::COND;
+#pragma unroll
+      for (int j = 0; j < TASKS; ++j) {
+        const int task = st + j * 64;
+        if (task >= NF * KQ) continue;
+        const int f = task / KQ, c8 = task - f * KQ;
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+        if (s < t_left[j]) {
+          const long long row = t_row0[j] + s;
+          if constexpr (!FRAMES) {
+            const float* src = (c8 < FEAT / 8) ? p.mels_up + row * FEAT + c8 * 8 : p.aux + row * (4 * AUXD) + (c8 - FEAT / 8) * 8;
+            a = __ldg(reinterpret_cast<const float4*>(src)); b = __ldg(reinterpret_cast<const float4*>(src) + 1);
+          } else {
+            const unsigned r = (unsigned)row, frame = r / (unsigned)p.hop, phase = r - frame * (unsigned)p.hop;
+            if (c8 >= FEAT / 8) {
+              const float4* src = reinterpret_cast<const float4*>(p.aux_frames + (size_t)frame * (4 * AUXD) + (c8 - FEAT / 8) * 8);
+              a = __ldg(src); b = __ldg(src + 1);
+            } else {                                           // same fmaf order as wrnn_expand_rows_kernel -> identical rows
+              const float* k = p.up_taps + phase * 5;
+#pragma unroll
+              for (int d = 0; d < 5; ++d) {
+                const float wgt = __ldg(k + d);
+                const float4* src = reinterpret_cast<const float4*>(p.mel_frames + (size_t)(frame + d) * FEAT + c8 * 8);
+                const float4 x0 = __ldg(src), x1 = __ldg(src + 1);
+                a.x = fmaf(wgt, x0.x, a.x); a.y = fmaf(wgt, x0.y, a.y); a.z = fmaf(wgt, x0.z, a.z); a.w = fmaf(wgt, x0.w, a.w);
+                b.x = fmaf(wgt, x1.x, b.x); b.y = fmaf(wgt, x1.y, b.y); b.z = fmaf(wgt, x1.z, b.z); b.w = fmaf(wgt, x1.w, b.w);
+              }
+            }
+          }
+        }
+        uint4 v;
+        v.x = pack2<FMT>(a.x, a.y); v.y = pack2<FMT>(a.z, a.w); v.z = pack2<FMT>(b.x, b.y); v.w = pack2<FMT>(b.z, b.w);
+        *reinterpret_cast<uint4*>(img + (f >> 3) * SBO_Q + c8 * 128 + (f & 7) * 16) = v;
+      }
+      proxy_fence_smem();                                      // generic-proxy stores -> async-proxy (MMA) reads
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar(BAR_READY + par)) : "memory");
+    }
+  } else {
+    // ===================================================================================================== epilogue
+    const int row = (warp & 3) * 32 + lane;                   // TMEM lane == weight row within the 128-row tile
+    const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    float* st_h1 = p.state + ((size_t)tile * 2 + 0) * H * NF;
+    float* st_h2 = p.state + ((size_t)tile * 2 + 1) * H * NF;
+    unsigned full_par = 0;                                    // per block: parity of the accumulator-full waits so far
+    const bool profiling = p.prof != nullptr && blockIdx.x == 0 && tid == 128;
+    long long t_wait = 0, t_work = 0;
+    auto wait_full = [&](int blk) {
+      long long c0 = 0;
+      if (profiling) c0 = clock64();
+      wait(bar(BAR_ACC_FULL + blk), (full_par >> blk) & 1u); full_par ^= 1u << blk;
+      tc_fence_after();
+      if (profiling) t_wait += clock64() - c0;
+    };
+    auto release_acc = [&](int blk) {                         // this thread's tcgen05.ld of the block are complete
+      tc_fence_before();
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar(BAR_ACC_EMPTY + blk)) : "memory");
+    };
+    auto publish_ready = [&](int which) {
+      proxy_fence_smem();
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar(BAR_READY + which)) : "memory");
+    };
+    // element (fold f, unit k) of a K = 512 operand image
+    auto img_ptr = [&](int off, int f, int k) -> uint16_t* {
+      return reinterpret_cast<uint16_t*>(smem + off + (f >> 3) * SBO_H + (k >> 3) * 128 + (f & 7) * 16 + (k & 7) * 2);
+    };
+    auto to_bits = [&](float v) -> uint16_t { return (uint16_t)(pack2<FMT>(v, 0.f) & 0xffffu); };
+
+    volatile int* ep_stop = s_abort + 1;                      // the epilogue warps leave the loop together (named barrier inside)
+    if (tid == 128) *ep_stop = 0;
+    named_bar_sync(1, 128);
+    for (int t = 0; t < S; ++t) {
+      const int cur = t & 1;
+      const int off_h1new = cur ? SM::OFF_X0 : SM::OFF_X1, off_y1 = cur ? SM::OFF_X1 : SM::OFF_X0;
+      long long w0 = 0;
+      if (profiling) w0 = clock64();
+      // draws of this step for the fold this thread samples (threads of lane quarter 0, lane < B)
+      float ur[11];
+#pragma unroll
+      for (int i = 0; i < 11; ++i) ur[i] = 0.5f;
+      const bool sampler = (warp & 3) == 0 && lane < B;
+      if (sampler) {
+        const int gf = f0 + lane;
+        if (p.uniforms) {
+          const float* u = p.uniforms + (size_t)t * 11 * p.n_total;
+#pragma unroll
+          for (int i = 0; i < 10; ++i) ur[i] = __ldg(u + gf * 10 + i);
+          ur[10] = __ldg(u + 10 * p.n_total + gf);
+        } else {
+          const unsigned gg = (unsigned)(p.seg_first + gf), k0 = (unsigned)p.seed, k1 = (unsigned)(p.seed >> 32), o0 = (unsigned)p.offset;
+          const Philox4 r0 = philox4x32_10((unsigned)t, gg, 0u, o0, k0, k1), r1 = philox4x32_10((unsigned)t, gg, 1u, o0, k0, k1),
+                        r2 = philox4x32_10((unsigned)t, gg, 2u, o0, k0, k1);
+          ur[0] = u_ref_range(r0.x); ur[1] = u_ref_range(r0.y); ur[2] = u_ref_range(r0.z); ur[3] = u_ref_range(r0.w);
+          ur[4] = u_ref_range(r1.x); ur[5] = u_ref_range(r1.y); ur[6] = u_ref_range(r1.z); ur[7] = u_ref_range(r1.w);
+          ur[8] = u_ref_range(r2.x); ur[9] = u_ref_range(r2.y); ur[10] = u_ref_range(r2.z);
+        }
+      }
+
+      // ---- P1 / P2: the two GRU cells ----------------------------------------------------------------------------
+#pragma unroll 1
+      for (int cell = 0; cell < 2; ++cell) {
+        float* st = cell ? st_h2 : st_h1;
+        const float* bh = cell ? p.b2h : p.b1h;
+        const int qbase = cell * 3 * H;                        // rows of qk / vq: gi1 = 0.., gi2 = 3H..
+        const int off_out = cell ? SM::OFF_H2 : off_h1new;
+#pragma unroll 1
+        for (int b = 0; b < 4; ++b) {
+          const int u = b * MROWS + row;
+          const float qk_r = __ldg(p.qk + qbase + u), qk_z = __ldg(p.qk + qbase + H + u), qk_n = __ldg(p.qk + qbase + 2 * H + u);
+          const float vq_r = __ldg(p.vq + qbase + u), vq_z = __ldg(p.vq + qbase + H + u), vq_n = __ldg(p.vq + qbase + 2 * H + u);
+          const float bh_r = __ldg(bh + u), bh_z = __ldg(bh + H + u), bh_n = __ldg(bh + 2 * H + u);
+          float* hrow = st + (size_t)u * NF;
+          float hp[NF];
+          if (t > 0) {
+#pragma unroll
+            for (int i = 0; i < NF / 4; ++i) {
+              const float4 v = __ldcg(reinterpret_cast<const float4*>(hrow) + i);
+              hp[4 * i] = v.x; hp[4 * i + 1] = v.y; hp[4 * i + 2] = v.z; hp[4 * i + 3] = v.w;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < NF; ++i) hp[i] = 0.f;
+          }
+          wait_full(b);
+#pragma unroll
+          for (int half = 0; half < NF / 16; ++half) {
+            float ar[16], az[16], ai[16], ah[16];
+            tmem_ld16(tlane + (4 * b + 0) * NF + half * 16, ar);
+            tmem_ld16(tlane + (4 * b + 1) * NF + half * 16, az);
+            tmem_ld16(tlane + (4 * b + 2) * NF + half * 16, ai);
+            tmem_ld16(tlane + (4 * b + 3) * NF + half * 16, ah);
+            tmem_ld_wait();
+            if (half == NF / 16 - 1) release_acc(b);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const int f = half * 16 + i;
+              const float x = x_s[f];
+              const float h = gru_unit_fast(ar[i] + qk_r + x * vq_r, az[i] + qk_z + x * vq_z, ai[i] + qk_n + x * vq_n,
+                                            bh_r, bh_z, ah[i] + bh_n, hp[f]);
+              // (the recurrent r / z contributions are already inside ar / az: one accumulator per gate)
+              hp[f] = h;
+              *img_ptr(off_out, f, u) = to_bits(h);
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < NF / 4; ++i)
+            __stcg(reinterpret_cast<float4*>(hrow) + i, make_float4(hp[4 * i], hp[4 * i + 1], hp[4 * i + 2], hp[4 * i + 3]));
+        }
+        publish_ready(cell ? W_H2NEW : W_H1NEW);
+      }
+
+      // ---- P3 / P4: fc1, fc2 ------------------------------------------------------------------------------------
+#pragma unroll 1
+      for (int layer = 0; layer < 2; ++layer) {
+        const int qbase = 6 * H + layer * H;
+        const int off_out = layer ? SM::OFF_Y2 : off_y1;
+#pragma unroll 1
+        for (int b = 0; b < 4; ++b) {
+          const int u = b * MROWS + row;
+          const float qk_u = __ldg(p.qk + qbase + u), vq_u = __ldg(p.vq + qbase + u);
+          wait_full(b);
+#pragma unroll
+          for (int half = 0; half < NF / 16; ++half) {
+            float a[16];
+            tmem_ld16(tlane + (4 * b + layer) * NF + half * 16, a);
+            tmem_ld_wait();
+            if (half == NF / 16 - 1) release_acc(b);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const int f = half * 16 + i;
+              *img_ptr(off_out, f, u) = to_bits(fmaxf(a[i] + qk_u + x_s[f] * vq_u, 0.f));
+            }
+          }
+        }
+        publish_ready(layer ? W_Y2 : W_Y1);
+      }
+
+      // ---- P5: logits -> transpose through shared memory -> one thread per fold samples ----------------------------
+      wait_full(0);
+      if ((warp & 3) == 0) {
+#pragma unroll
+        for (int half = 0; half < NF / 16; ++half) {
+          float a[16];
+          tmem_ld16(tlane + 2 * NF + half * 16, a);
+          tmem_ld_wait();
+          const float b3 = __ldg(p.b3 + row);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) log_s[(half * 16 + i) * SM::LOGP + lane] = a[i] + b3;   // [fold][class], class == lane
+        }
+      }
+      release_acc(0);
+      if ((warp & 3) == 0) {
+        __syncwarp();
+        float xnew = 0.f;
+        if (sampler) {
+          float lgo[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) lgo[i] = log_s[lane * SM::LOGP + i];
+          xnew = mol_sample_fast(lgo, ur);
+          const int gf = f0 + lane;
+          p.out[(size_t)gf * p.out_pitch + t] = xnew;
+          if (p.logits_out) {
+#pragma unroll
+            for (int i = 0; i < 30; ++i) p.logits_out[((size_t)t * p.n_total + gf) * 30 + i] = lgo[i];
+          }
+          if (p.x_force) xnew = __ldg(p.x_force + (size_t)t * p.n_total + gf);               // teacher forcing: step t+1 consumes x_force[t]
+        }
+        __syncwarp();
+        if (lane < NF) x_s[lane] = xnew;
+      }
+      if (tid == 128) *ep_stop = *s_abort;
+      named_bar_sync(1, 128);                                  // x of this step (and the stop decision) visible to all epilogue threads
+      if (profiling) t_work += clock64() - w0;
+      if (*ep_stop) break;
+    }
+    if (profiling) { p.prof[4] = t_wait; p.prof[5] = t_work; }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "n"(TMEM_COLS));
+}
+
+// --------------------------------------------------------------------------------------------------------------------
+// host side
+// --------------------------------------------------------------------------------------------------------------------
+class StreamEngine : public Engine {
+ public:
+  ~StreamEngine() override {
+    cudaSetDevice(device);
+    cudaFree(d_blob_); cudaFree(d_prog_); cudaFree(d_vec_); cudaFree(d_state_); cudaFree(d_sync_);
+  }
+  const char* name() const override { return cfg.precision == WRNN_PREC_BF16 ? "tcgen05-stream-bf16" : "tcgen05-stream-fp16"; }
+  int grid_ctas() const override { return last_grid_; }
+
+  template <int NF> const void* kernel_nf(bool frames) const {
+    if (cfg.precision == WRNN_PREC_BF16) return frames ? (const void*)wrnn_stream_kernel<NF, 1, true> : (const void*)wrnn_stream_kernel<NF, 1, false>;
+    return frames ? (const void*)wrnn_stream_kernel<NF, 0, true> : (const void*)wrnn_stream_kernel<NF, 0, false>;
+  }
+
+  int init(const HostWeights& w) {
+    Plan plan;
+    build_plan(w, cfg.precision == WRNN_PREC_BF16, plan);
+    n_chunks_ = (int)plan.prog.size(); n_mma_ = plan.n_mma;
+    WRNN_CUDA_OK(cudaMalloc(&d_blob_, plan.blob.size()));
+    WRNN_CUDA_OK(cudaMemcpy(d_blob_, plan.blob.data(), plan.blob.size(), cudaMemcpyHostToDevice));
+    WRNN_CUDA_OK(cudaMalloc(&d_prog_, plan.prog.size() * sizeof(Chunk)));
+    WRNN_CUDA_OK(cudaMemcpy(d_prog_, plan.prog.data(), plan.prog.size() * sizeof(Chunk), cudaMemcpyHostToDevice));
+    std::vector<float> vec;
+    off_qk_ = 0; vec.insert(vec.end(), plan.qk.begin(), plan.qk.end());
+    off_vq_ = vec.size(); vec.insert(vec.end(), plan.vq.begin(), plan.vq.end());
+    off_b1h_ = vec.size(); vec.insert(vec.end(), plan.b1h.begin(), plan.b1h.end());
+    off_b2h_ = vec.size(); vec.insert(vec.end(), plan.b2h.begin(), plan.b2h.end());
+    off_b3_ = vec.size(); vec.insert(vec.end(), plan.b3.begin(), plan.b3.end());
+    WRNN_CUDA_OK(cudaMalloc(&d_vec_, vec.size() * sizeof(float)));
+    WRNN_CUDA_OK(cudaMemcpy(d_vec_, vec.data(), vec.size() * sizeof(float), cudaMemcpyHostToDevice));
+    WRNN_CUDA_OK(cudaMalloc(&d_sync_, 256));
+    WRNN_CUDA_OK(cudaMemset(d_sync_, 0, 256));
+    for (int fr = 0; fr < 2; ++fr) {
+      WRNN_CUDA_OK(cudaFuncSetAttribute(kernel_nf<16>(fr != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<16>::BYTES));
+      WRNN_CUDA_OK(cudaFuncSetAttribute(kernel_nf<32>(fr != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<32>::BYTES));
+    }
+    WRNN_CUDA_OK(cudaDeviceGetAttribute(&n_sm_, cudaDevAttrMultiProcessorCount, device));
+    return WRNN_OK;
+  }
+
+  static bool supports_cfg(const wrnn_cfg& c) {
+    return c.precision != WRNN_PREC_FP32 && c.mode == WRNN_MODE_MOL && c.n_classes == 30;
+  }
+  bool supports(const wrnn_job& job) const override { return job.expo == nullptr && !(job.mel_frames && job.cond_mode == WRNN_COND_EXPAND && job.fold_row0); }
+
+  int generate(const wrnn_job& job, cudaStream_t stream) override {
+    WRNN_CUDA_OK(cudaSetDevice(device));
+    // folds per CTA: 16 while that still gives every tile its own SM, else 32 (twice the folds per streamed byte)
+    const int nf = ((job.n_seg + 15) / 16 <= n_sm_) ? 16 : 32;
+    const int tiles = (job.n_seg + nf - 1) / nf;
+    const size_t need = (size_t)tiles * 2 * H * nf * sizeof(float);
+    if (need > state_bytes_) {
+      cudaFree(d_state_); d_state_ = nullptr; state_bytes_ = 0;
+      WRNN_CUDA_OK(cudaMalloc(&d_state_, need));
+      state_bytes_ = need;
+    }
+    StreamParams p{};
+    const float* v = static_cast<const float*>(d_vec_);
+    p.blob = static_cast<const unsigned char*>(d_blob_); p.prog = static_cast<const uint4*>(d_prog_); p.n_chunks = n_chunks_;
+    p.qk = v + off_qk_; p.vq = v + off_vq_; p.b1h = v + off_b1h_; p.b2h = v + off_b2h_; p.b3 = v + off_b3_;
+    p.mels_up = job.mels_up; p.aux = job.aux; p.L = job.L; p.seg_stride = job.seg_stride; p.row_base = 0;
+    p.n_total = job.n_seg; p.steps = job.steps > 0 ? job.steps : job.seg_len; p.out_pitch = p.steps; p.seg_first = job.seg_first;
+    p.uniforms = job.uniforms; p.seed = job.philox_seed; p.offset = job.philox_offset;
+    p.out = job.out; p.x_force = job.x_force; p.logits_out = job.logits_out;
+    p.fold_row0 = reinterpret_cast<const long long*>(job.fold_row0); p.fold_row_end = reinterpret_cast<const long long*>(job.fold_row_end);
+    p.mel_frames = job.mel_frames; p.aux_frames = job.aux_frames; p.up_taps = job.up_taps; p.hop = job.hop;
+    p.state = static_cast<float*>(d_state_);
+    p.abort_flag = reinterpret_cast<int*>(static_cast<unsigned*>(d_sync_) + 8);
+    p.prof = getenv("WRNN_STREAM_PROF") ? reinterpret_cast<long long*>(static_cast<unsigned char*>(d_sync_) + 64) : nullptr;
+    const bool frames = job.mel_frames != nullptr;             // rows are formed by the staging warps (no scratch of size L)
+    const void* fn = nf == 16 ? kernel_nf<16>(frames) : kernel_nf<32>(frames);
+    const int smem = nf == 16 ? Smem<16>::BYTES : Smem<32>::BYTES;
+    void* args[] = {&p};
+    WRNN_CUDA_OK(cudaLaunchKernel(fn, dim3(tiles), dim3(NT), args, smem, stream));
+    ++launches;
+    last_grid_ = tiles; last_steps_ = p.steps; last_nf_ = nf;
+    return WRNN_OK;
+  }
+
+  int check() override {
+    unsigned char buf[256];
+    WRNN_CUDA_OK(cudaSetDevice(device));
+    WRNN_CUDA_OK(cudaMemcpy(buf, d_sync_, 256, cudaMemcpyDeviceToHost));
+    const int flag = reinterpret_cast<int*>(buf)[8];
+    if (getenv("WRNN_STREAM_PROF") && last_steps_ > 0) {
+      long long prof[8]; std::memcpy(prof, buf + 64, sizeof(prof));
+      const long long n = last_steps_;
+      fprintf(stderr, "[wrnn_stream prof] NF=%d tiles=%d steps=%d mma/step=%d chunks/step=%d | issuer: acc-wait=%lld operand-wait=%lld ring-wait=%lld "
+              "issue=%lld | epilogue thread: mma-wait=%lld step=%lld (cycles per step)\n", last_nf_, last_grid_, last_steps_, n_mma_, n_chunks_,
+              prof[0] / n, prof[1] / n, prof[2] / n, prof[3] / n, prof[4] / n, prof[5] / n);
+    }
+    if (flag != 0) { set_error("stream kernel aborted: an mbarrier wait (TMA / MMA / operand hand-off) timed out"); return WRNN_E_WATCHDOG; }
+    return WRNN_OK;
+  }
+
+ private:
+  void *d_blob_ = nullptr, *d_prog_ = nullptr, *d_vec_ = nullptr, *d_state_ = nullptr, *d_sync_ = nullptr;
+  size_t state_bytes_ = 0, off_qk_ = 0, off_vq_ = 0, off_b1h_ = 0, off_b2h_ = 0, off_b3_ = 0;
+  int n_chunks_ = 0, n_mma_ = 0, n_sm_ = 0, last_grid_ = 0, last_steps_ = 0, last_nf_ = 0;
+};
+
+}  // namespace
+
+int make_stream_engine(const wrnn_cfg& cfg, const HostWeights& w, int device, Engine** out) {
+  if (!StreamEngine::supports_cfg(cfg)) {
+    set_error("stream engine serves the MoL head (30 classes) with fp16/bf16 operands");
+    return WRNN_E_INVALID;
+  }
+  StreamEngine* e = new StreamEngine();
+  e->cfg = cfg; e->device = device;
+  const int rc = e->init(w);
+  if (rc != WRNN_OK) { delete e; return rc; }
+  *out = e;
+  return WRNN_OK;
+}
+
+}  // namespace wrnn

@@ -1,0 +1,169 @@
+// wrnn_stream_plan.h -- host side of the STREAM engine (wrnn_stream.cu): the packed weight stream and the static
+// per-step MMA program one CTA interprets.  Pure C++ (no CUDA), so the packing and the schedule can be checked on a
+// CPU-only box (wrnn_debug_stream_plan + tests/test_stream_plan.py interpret the program with numpy and compare it
+// with the engine-arithmetic emulation oracle/contract.py).
+//
+// Decomposition ("activation-stationary"; the opposite of wrnn_tc.cu).  A CTA owns NF folds for the whole sequence
+// and runs EVERY layer for them; nothing is exchanged between SMs.  The weights (7.4 MB as fp16) do not fit one SM,
+// so they are streamed from L2 every step, in the order the step consumes them, through a shared-memory ring (TMA
+// bulk copies; every CTA of the grid reads the same stream, which the 126 MB L2 serves at ~100 B/cycle/SM --
+// profiles/r02_probes.md).  Contractions are "swap-AB": the weight rows are the MMA M dimension (tiles of 128 rows =
+// 128 TMEM lanes), the CTA's folds are N (NF = 16 or 32), D[rows, folds] += W[rows, k0:k0+16] * act[folds, k0:k0+16]^T.
+// A GRU unit's r / z / n pre-activations sit in the SAME TMEM lane of different accumulators, so the gate math is
+// thread-local (one thread per unit row, NF folds each).
+//
+// Per step (folded algebra of wrnn_fold.h; reference models/fatchord_version.py:208-223), unit blocks b = 0..3 of 128:
+//   P1 GRU1 :  acc r,z = Q1[g,b] cond + W1h[g,b] h1   | acc in = Q1[n,b] cond          | acc hn = W1h[n,b] h1
+//   P2 GRU2 :  acc r,z = Q2[g,b] cond + W2h[g,b] h2 + W2x[g,b] h1' | acc in = Q2[n,b] cond + W2x[n,b] h1' | acc hn = W2h[n,b] h2
+//   P3 fc1  :  acc = Q3[b] cond + F1x[b] h1' + F1x[b] h2'      (one streamed F1x chunk feeds two MMAs)
+//   P4 fc2  :  acc = Q4[b] cond + F2x[b] y1
+//   P5 fc3  :  acc = F3 y2        (MoL: 30 rows in one 128-row tile)
+// The program lists the weight chunks in exactly this order; within P2 every chunk that does not depend on h1' is
+// issued first, so those MMAs (and the epilogue-free h2 reads) overlap the P1 gate math.
+#pragma once
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "wrnn_fold.h"
+
+namespace wrnn {
+namespace stream {
+
+constexpr int MROWS = 128;          // weight rows per MMA tile (UMMA M)
+constexpr int KCH = 64;             // K elements per streamed chunk (4 MMAs of K = 16)
+constexpr int CHUNK_BYTES = MROWS * KCH * 2;   // 16 KB ring slot
+
+// B operand (activation image) selectors
+enum : uint8_t { B_COND = 0, B_H1PREV = 1, B_H1NEW = 2, B_H2 = 3, B_Y1 = 4, B_Y2 = 5, B_NONE = 0xff };
+// readiness barriers the issuer may have to wait for before a chunk
+enum : uint8_t { W_NONE = 0, W_COND = 1, W_H1NEW = 2, W_H2NEW = 3, W_Y1 = 4, W_Y2 = 5 };
+enum : uint8_t { F_FIRST = 1, F_COND_RELEASE = 2 };
+
+struct Chunk {            // 16 bytes, read as one uint4 by the producer and the issuer warp
+  uint32_t bytes;         // size of this chunk in the weight stream (chunks are consecutive): 128 rows x (16*nk) x 2 B
+  uint8_t acc;            // accumulator index: TMEM column = acc * NF
+  uint8_t nk;             // K = 16 steps in this chunk
+  uint8_t b_buf;          // B operand image (B_*)
+  uint8_t b_buf2;         // second B operand for the same weight chunk (fc1: h2'), B_NONE otherwise
+  uint16_t k0;            // K offset of the chunk inside the B image (elements)
+  uint8_t flags;          // F_FIRST: first MMA of the accumulator in this phase overwrites; F_COND_RELEASE: last reader of cond
+  uint8_t wait_b;         // W_*: readiness barrier to wait for before issuing
+  uint8_t wait_acc;       // 0, or block + 1: wait until the epilogue of the previous phase has drained this block's accumulators
+  uint8_t commit;         // 0, or block + 1: after this chunk, signal "accumulators of block full" to the epilogue warps
+  uint16_t pad;
+};
+static_assert(sizeof(Chunk) == 16, "Chunk must stay one uint4");
+
+struct Plan {
+  std::vector<uint8_t> blob;      // the weight stream: chunk images back to back (fp16 / bf16 bits)
+  std::vector<Chunk> prog;        // one step of the program
+  std::vector<float> qk, vq;      // [4096] conditioning-row constants, row order gi1 | gi2 | fc1 | fc2 (gate-major inside the GRUs)
+  std::vector<float> b1h, b2h;    // [1536] gate-major
+  std::vector<float> b3;          // [n_classes padded to 128]
+  int n_classes = 0;
+  int n_mma = 0;                  // MMA instructions per step (for the roofline bookkeeping)
+};
+
+// K-major no-swizzle operand image of a [128 x kc] tile: element (r, k) at (r/8)*(kc/8)*64 + (k/8)*64 + (r%8)*8 + k%8
+inline size_t tile_index(int r, int k, int kc) { return (size_t)(r / 8) * (kc / 8) * 64 + (size_t)(k / 8) * 64 + (r % 8) * 8 + (k % 8); }
+
+// Builds the plan.  `bf` selects bf16 instead of fp16 operand bits.  n_classes <= 128 (MoL: 30).
+inline void build_plan(const HostWeights& w, bool bf, Plan& p) {
+  Folded f; fold(w, f);
+  CtaSlice s; slice_for_cta(w, f, 0, H, s);          // P = 1: the dense matrices in the row order documented in wrnn_fold.h
+  auto cvt = [&](double v) -> uint16_t { return bf ? f2bf((float)v) : f2h((float)v); };
+  p.blob.clear(); p.prog.clear(); p.n_mma = 0;
+  p.n_classes = w.n_classes;
+  p.qk = s.qk; p.vq = s.vq; p.b1h = s.b1h; p.b2h = s.b2h;
+  p.b3.assign(MROWS, 0.f);
+  for (int r = 0; r < w.n_classes && r < MROWS; ++r) p.b3[r] = w.f3b[r];
+
+  // appends the chunks of rows [row0, row0 + 128) x columns [0, K) of a dense row-major [rows][K] matrix
+  auto emit = [&](const double* M, int K, int n_rows_valid, int row0, uint8_t acc, uint8_t b_buf, uint8_t b_buf2, bool& first,
+                  uint8_t wait_b, uint8_t& wait_acc) {
+    for (int k0 = 0; k0 < K; k0 += KCH) {
+      const int kc = (K - k0 < KCH) ? (K - k0) : KCH;              // 64, or the 16-wide tail of K = 208
+      const size_t base = p.blob.size();
+      p.blob.resize(base + (size_t)MROWS * kc * 2, 0);
+      uint16_t* img = reinterpret_cast<uint16_t*>(p.blob.data() + base);
+      for (int r = 0; r < MROWS; ++r) {
+        if (row0 + r >= n_rows_valid) continue;                    // rows beyond the matrix stay zero (fc3: 30 of 128)
+        for (int k = 0; k < kc; ++k) img[tile_index(r, k, kc)] = cvt(M[(size_t)(row0 + r) * K + k0 + k]);
+      }
+      Chunk c{};
+      c.bytes = (uint32_t)(MROWS * kc * 2); c.acc = acc; c.nk = (uint8_t)(kc / 16); c.b_buf = b_buf; c.b_buf2 = b_buf2;
+      c.k0 = (uint16_t)k0; c.flags = first ? F_FIRST : 0; c.wait_b = wait_b; c.wait_acc = wait_acc; c.commit = 0;
+      first = false; wait_acc = 0;
+      p.prog.push_back(c);
+      p.n_mma += c.nk * (b_buf2 == B_NONE ? 1 : 2);
+    }
+  };
+  const double* Q = s.Q.data();         // [8H][CDIM]: gi1 (g*H+u) | gi2 (3H + g*H+u) | fc1 (6H+u) | fc2 (7H+u)
+  const double* S1 = s.S1.data();       // [7H][H]: W2x (g*H+u) | W1h (3H + g*H+u) | F1x (6H+u)
+  const double* S2 = s.S2.data();       // [4H][H]: F1x (u) | W2h (H + g*H+u)
+  const double* S3 = s.S3.data();       // [H][H] : F2x
+  const double* W2x = S1; const double* W1h = S1 + (size_t)3 * H * H; const double* F1x = S1 + (size_t)6 * H * H;
+  const double* W2h = S2 + (size_t)H * H; const double* F2x = S3;
+  const int NB = H / MROWS;             // 4 unit blocks
+  std::vector<double> F3((size_t)MROWS * H, 0.0);
+  for (int r = 0; r < w.n_classes && r < MROWS; ++r) for (int k = 0; k < H; ++k) F3[(size_t)r * H + k] = w.f3w[(size_t)r * H + k];
+
+  // ---- P1: GRU1.  Accumulators of block b: 4b + {0: r, 1: z, 2: in, 3: hn}
+  for (int b = 0; b < NB; ++b) {
+    uint8_t wacc = (uint8_t)(b + 1);                               // previous phase = P5 (block 0) / P4 of the step before
+    for (int g = 0; g < 2; ++g) {                                  // r, z: conditioning + recurrent part in one accumulator
+      bool first = true;
+      emit(Q, CDIM, 8 * H, g * H + b * MROWS, (uint8_t)(4 * b + g), B_COND, B_NONE, first, W_COND, wacc);
+      emit(W1h, H, 3 * H, g * H + b * MROWS, (uint8_t)(4 * b + g), B_H1PREV, B_NONE, first, W_NONE, wacc);
+    }
+    { bool first = true; emit(Q, CDIM, 8 * H, 2 * H + b * MROWS, (uint8_t)(4 * b + 2), B_COND, B_NONE, first, W_COND, wacc); }
+    { bool first = true; emit(W1h, H, 3 * H, 2 * H + b * MROWS, (uint8_t)(4 * b + 3), B_H1PREV, B_NONE, first, W_NONE, wacc); }
+    p.prog.back().commit = (uint8_t)(b + 1);
+  }
+  // ---- P2: GRU2.  First everything that does not need h1' (overlaps the P1 gate math), then W2x h1'.
+  for (int b = 0; b < NB; ++b) {
+    uint8_t wacc = (uint8_t)(b + 1);
+    for (int g = 0; g < 3; ++g) {
+      bool first = true;
+      emit(Q, CDIM, 8 * H, 3 * H + g * H + b * MROWS, (uint8_t)(4 * b + g), B_COND, B_NONE, first, W_COND, wacc);
+      if (g < 2) emit(W2h, H, 3 * H, g * H + b * MROWS, (uint8_t)(4 * b + g), B_H2, B_NONE, first, W_NONE, wacc);
+    }
+    { bool first = true; emit(W2h, H, 3 * H, 2 * H + b * MROWS, (uint8_t)(4 * b + 3), B_H2, B_NONE, first, W_NONE, wacc); }
+  }
+  for (int b = 0; b < NB; ++b) {
+    uint8_t wacc = 0;
+    for (int g = 0; g < 3; ++g) { bool first = false; emit(W2x, H, 3 * H, g * H + b * MROWS, (uint8_t)(4 * b + g), B_H1NEW, B_NONE, first, W_H1NEW, wacc); }
+    p.prog.back().commit = (uint8_t)(b + 1);
+  }
+  // ---- P3: fc1 (accumulator 4b).  Conditioning rows of all blocks first, then F1x with both operands.
+  for (int b = 0; b < NB; ++b) {
+    uint8_t wacc = (uint8_t)(b + 1); bool first = true;
+    emit(Q, CDIM, 8 * H, 6 * H + b * MROWS, (uint8_t)(4 * b), B_COND, B_NONE, first, W_COND, wacc);
+  }
+  for (int b = 0; b < NB; ++b) {
+    uint8_t wacc = 0; bool first = false;
+    emit(F1x, H, H, b * MROWS, (uint8_t)(4 * b), B_H1NEW, B_H2, first, W_H2NEW, wacc);
+    p.prog.back().commit = (uint8_t)(b + 1);
+  }
+  // ---- P4: fc2 (accumulator 4b + 1)
+  for (int b = 0; b < NB; ++b) {
+    uint8_t wacc = (uint8_t)(b + 1); bool first = true;
+    emit(Q, CDIM, 8 * H, 7 * H + b * MROWS, (uint8_t)(4 * b + 1), B_COND, B_NONE, first, W_COND, wacc);
+    if (b == NB - 1) p.prog.back().flags |= F_COND_RELEASE;       // last reader of this step's conditioning image
+  }
+  for (int b = 0; b < NB; ++b) {
+    uint8_t wacc = 0; bool first = false;
+    emit(F2x, H, H, b * MROWS, (uint8_t)(4 * b + 1), B_Y1, B_NONE, first, W_Y1, wacc);
+    p.prog.back().commit = (uint8_t)(b + 1);
+  }
+  // ---- P5: fc3 (accumulator 2, block 0's barriers)
+  {
+    uint8_t wacc = 1; bool first = true;
+    emit(F3.data(), H, MROWS, 0, 2, B_Y2, B_NONE, first, W_Y2, wacc);
+    p.prog.back().commit = 1;
+  }
+}
+
+}  // namespace stream
+}  // namespace wrnn

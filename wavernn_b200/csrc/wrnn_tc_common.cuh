@@ -118,9 +118,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* ab
   }
 }
 __device__ __forceinline__ void counter_wait(const unsigned* ctr, unsigned target, int* abort_flag) {
-  if (ld_acquire_u32(ctr) >= target) return;
+  if (!counter_behind(ld_acquire_u32(ctr), target)) return;          // wrap-safe, see grid_barrier
   const long long t0 = clock64();
-  while (ld_acquire_u32(ctr) < target) {
+  while (counter_behind(ld_acquire_u32(ctr), target)) {
     if (clock64() - t0 > kWatchdogCycles || ld_relaxed_s32(abort_flag) != 0) { atomicExch(abort_flag, 1); return; }
   }
 }

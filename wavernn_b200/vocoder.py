@@ -147,9 +147,10 @@ class WaveRNN(nn.Module):
         # ---- knobs of the B200 engine (not part of the reference surface) ----
         self.gen_rng = 'torch'          # 'torch' (reference-compatible CPU draws) | 'philox' (in-kernel)
         self.gen_precision = 'fp16'     # 'fp16' | 'bf16' tensor-core operands | 'fp32' strict SIMT mode
-        self.gen_engine = 'auto'        # 'auto' | 'simt' | 'tcgen05'
+        self.gen_engine = 'auto'        # 'auto' | 'simt' | 'tcgen05' (weights stationary, lowest latency) | 'stream' (many folds)
         self.gen_philox_seed = 0
         self.gen_native_rng = True      # replay torch's CPU generator natively (self-checked; False = torch operators)
+        self.gen_max_draw_bytes = 16 << 30   # bound on the host tensor of reference-compatible RAW draws (see _reference_draws)
         self._draw_buf = None
         self.gen_upsample_chunk = 2048  # mel frames per UpsampleNetwork call (bounds HBM intermediates)
         self.gen_epilogue = 'device'      # 'device': wrnn_epilogue (xfade / overlap-add / fade-out in one pass) | 'host': numpy
@@ -256,12 +257,25 @@ class WaveRNN(nn.Module):
             keep = (d >= 0) & (d < 5)
             taps = torch.zeros(hop, 5, device=device)
             taps[(n % hop)[keep], d[keep]] = y[keep]
+            # the 5-tap form is exact only if the whole impulse response falls inside the table (it does for the
+            # reference's (5, 5, 11); a first factor of 1 widens the support beyond +-2 frames)
+            self._taps_exact = bool((y[~keep] == 0).all().item())
             self._taps, self._taps_key = taps.contiguous(), key
         return self._taps
 
     def _kernel_conditioning_ok(self) -> bool:
-        return (self.gen_conditioning == 'kernel' and self.gen_precision != 'fp32'
-                and self.gen_engine in ('auto', 'tcgen05') and (self.mode == 'MOL' or self.n_classes == 512))
+        """Frame-rate conditioning (rows formed by the library from 5 taps per phase) is served when the engine is the
+        tcgen05 one AND the module's geometry is the one the tap table encodes: pad == 2 (the kernels read mel frames
+        n//hop .. n//hop + 4 of the (T + 2*pad)-row tensor, i.e. a centre offset of pad = 2) and an interpolation
+        cascade whose impulse response fits 5 frames.  Any other `pad` / `upsample_factors` (the reference accepts
+        them, fatchord_version.py:64-89) takes the materialised torch path, like the reference."""
+        if not (self.gen_conditioning == 'kernel' and self.gen_precision != 'fp32'
+                and self.gen_engine in ('auto', 'tcgen05', 'stream') and (self.mode == 'MOL' or self.n_classes == 512)):
+            return False
+        if self.pad != 2 or self.upsample.total_scale != self.hop_length:
+            return False
+        self.upsample_taps(next(self.parameters()).device)
+        return bool(self._taps_exact)
 
     # ------------------------------------------------------------------ randomness
     def _reference_draws(self, geo: FoldGeometry, steps: int, reuse_buffer: bool = False, shard=None):
@@ -300,10 +314,20 @@ class WaveRNN(nn.Module):
         if self.mode == 'MOL':
             u = torch.empty(steps, 11 * B).uniform_(1e-5, 1.0 - 1e-5)   # distribution.py:106,118
             return u, None
-        # RAW: Categorical.sample() -> torch.multinomial -> one exponential_() per step (:233-235)
-        e = torch.empty(steps, B, self.n_classes)
+        # RAW: Categorical.sample() -> torch.multinomial -> one exponential_() of shape (B, n_classes) per step
+        # (:233-235).  Only this rank's folds are kept (the whole (B, n_classes) row is still drawn: the stream is
+        # the reference's).  512 draws per fold-step is what parity with the reference costs: 25 MB per fold of
+        # 12,100 steps -- long RAW jobs should use gen_rng='philox' (in-kernel draws, no host tensor at all).
+        f0, nl = (shard.seg_first, shard.n_seg) if shard is not None else (0, B)
+        need = steps * nl * self.n_classes * 4
+        if need > self.gen_max_draw_bytes:
+            raise RuntimeError(f"wavernn_b200: gen_rng='torch' on the RAW head needs {need / 2**30:.1f} GiB of Exp(1) draws for "
+                               f"{nl} folds x {steps} steps; set model.gen_rng = 'philox' (or raise model.gen_max_draw_bytes)")
+        e = torch.empty(steps, nl, self.n_classes, pin_memory=torch.cuda.is_available())
+        row = torch.empty(B, self.n_classes)
         for t in range(steps):
-            e[t].exponential_()
+            row.exponential_()
+            e[t] = row[f0:f0 + nl]
         return None, e
 
     # ------------------------------------------------------------------ the hot path
@@ -372,7 +396,8 @@ class WaveRNN(nn.Module):
                     torch.cat([u_all[:, 10 * f0:10 * (f0 + n)], u_all[:, 10 * B + f0:10 * B + f0 + n]], dim=1)
                 uniforms = u_loc.contiguous().to(device, non_blocking=True)
             if e_all is not None:
-                expo = e_all[:, f0:f0 + n].contiguous().to(device, non_blocking=True)
+                e_loc = e_all if e_all.shape[1] == n else e_all[:, f0:f0 + n].contiguous()
+                expo = e_loc.to(device, non_blocking=True)
         elif self.gen_rng != 'philox':
             raise ValueError(f"gen_rng must be 'torch' or 'philox', got {self.gen_rng!r}")
         if shard.n_seg == 0:
@@ -483,9 +508,11 @@ class WaveRNN(nn.Module):
         dist_on = torch.distributed.is_available() and torch.distributed.is_initialized()
         rank = torch.distributed.get_rank() if dist_on else 0
         world = torch.distributed.get_world_size() if dist_on else 1
-        if self.mode != 'MOL' or len(mels_list) == 0:
-            # the RAW head is served fold-strided by the SIMT engine: one call per utterance
-            return [self.generate(m, p, True, target, overlap, mu_law) for m, p in zip(mels_list, save_paths)]
+        if self.mode not in ('MOL', 'RAW'):
+            raise RuntimeError("Unknown model mode value - ", self.mode)
+        if len(mels_list) == 0:
+            return []
+        mu_law = mu_law if self.mode == 'RAW' else False                        # :174
         t_start = time.time()
         self.eval()
         hop = self.hop_length
@@ -505,7 +532,7 @@ class WaveRNN(nn.Module):
                     m_up, aux = self.conditioning(mp, 0, T)
                     streams_m.append(m_up); streams_a.append(aux)
                 if self.gen_rng == 'torch':
-                    draws.append(self._reference_draws(geo, geo.seg_len)[0])     # same order as sequential generate() calls
+                    draws.append(self._reference_draws(geo, geo.seg_len))        # same order as sequential generate() calls
             S, stride = geos[0].seg_len, geos[0].seg_stride
             B = sum(g.n_seg for g in geos)
             row0, row_end, base = [], [], 0
@@ -532,12 +559,14 @@ class WaveRNN(nn.Module):
             job = FoldGeometry(base, target, overlap, B, S, stride, base)
             shard = shard_folds(job, rank, world, hop)
             f_lo, n_loc = shard.seg_first, shard.n_seg
-            uniforms = None
-            if self.gen_rng == 'torch':
-                mix = torch.cat([u[:, :10 * g.n_seg] for u, g in zip(draws, geos)], 1)
-                logi = torch.cat([u[:, 10 * g.n_seg:] for u, g in zip(draws, geos)], 1)
+            uniforms = expo = None
+            if self.gen_rng == 'torch' and self.mode == 'MOL':
+                mix = torch.cat([u[:, :10 * g.n_seg] for (u, _), g in zip(draws, geos)], 1)
+                logi = torch.cat([u[:, 10 * g.n_seg:] for (u, _), g in zip(draws, geos)], 1)
                 uniforms = torch.cat([mix[:, 10 * f_lo:10 * (f_lo + n_loc)], logi[:, f_lo:f_lo + n_loc]], 1) \
                     .contiguous().to(device, non_blocking=True)
+            elif self.gen_rng == 'torch':         # RAW: per-utterance Exp(1) streams, folds side by side
+                expo = torch.cat([e for _, e in draws], 1)[:, f_lo:f_lo + n_loc].contiguous().to(device, non_blocking=True)
             elif self.gen_rng != 'philox':
                 raise ValueError(f"gen_rng must be 'torch' or 'philox', got {self.gen_rng!r}")
             engine = self._get_engine(device)
@@ -546,6 +575,7 @@ class WaveRNN(nn.Module):
                 cond = dict(mels_up=m_all.data_ptr(), aux=a_all.data_ptr())
                 engine.generate(L=m_all.shape[0], n_seg=n_loc, seg_len=S, seg_stride=stride, out=out.data_ptr(), seg_first=f_lo,
                                 uniforms=uniforms.data_ptr() if uniforms is not None else 0,
+                                expo=expo.data_ptr() if expo is not None else 0,
                                 philox_seed=int(self.gen_philox_seed), fold_row0=t_row0[f_lo:].data_ptr(),
                                 fold_row_end=t_end[f_lo:].data_ptr(),
                                 stream=torch.cuda.current_stream(device).cuda_stream, **cond)
@@ -555,7 +585,7 @@ class WaveRNN(nn.Module):
                 out = gather_segments(out, shard, job)
         wavs, f0 = [], 0
         for g, wl, path in zip(geos, wave_lens, save_paths):
-            wav = self._finish(out[f0:f0 + g.n_seg], g, True, wl, False)
+            wav = self._finish(out[f0:f0 + g.n_seg], g, True, wl, mu_law)
             f0 += g.n_seg
             if path is not None and rank == 0:
                 save_wav(wav, path, self.sample_rate)
