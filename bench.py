@@ -51,6 +51,20 @@ def frames_for(n_gpus: int) -> int:
     return L // HOP
 
 
+def workload_config(world: int, workload: str = "cfg2") -> dict:
+    """The `config` object BOTH arms print (identical for the same --gpus / --workload, so the driver's same_config
+    check compares like with like)."""
+    if workload == "cfg5":
+        return {"workload": "cfg5: mel T=172034 frames (35.8 min) -> 4096 folds x 12100 steps, target=11000 overlap=550, MoL head, "
+                            "rnn_dims=512, random-init weights (seed 0), torch.rand mel (seed 0)", "folds": 4096, "steps_per_fold": 12100}
+    T = frames_for(world)
+    head = {"cfg2": "MoL head", "cfg3": "RAW head (bits=9, mu-law)"}[workload]
+    return {"workload": f"{workload} x{world}: mel T={T} frames ({T * HOP / 22050:.1f} s) -> {FOLDS_PER_GPU * world} folds x 12100 steps "
+                        f"({FOLDS_PER_GPU} folds per GPU), target={TARGET} overlap={OVERLAP}, {head}, rnn_dims=512, random-init weights "
+                        f"(seed 0), torch.rand mel (seed 0), sampler seed 1234",
+            "folds": FOLDS_PER_GPU * world, "steps_per_fold": 12100}
+
+
 def build_model(device, mode="MOL"):
     from wavernn_b200 import WaveRNN
     torch.manual_seed(0)
@@ -140,58 +154,93 @@ def cpu_conditioning(model_cpu, mel):
     return mels_f, aux_f
 
 
-def time_cpu_port(sample_steps: int, repeats: int = 1, warmup: int = 0):
+def time_cpu_port(sample_steps: int):
+    """cpu_baseline leg of the GPU arm: the port of the reference loop on a bounded sample (first `sample_steps` steps of
+    all 19 folds), best thread count of a sweep."""
+    from oracle import torch_port
+    threads, sweep, (sd, mels_f, aux_f) = best_cpu_threads(FOLDS_PER_GPU)
+    torch.set_num_threads(threads)
+    torch.manual_seed(1234)
+    _, dt = torch_port.generate_segments_torch(sd, mels_f, aux_f, steps=sample_steps)
+    return dict(B=mels_f.shape[0], steps=sample_steps, seconds=[dt], cores=threads, threads=threads,
+                host_cores=os.cpu_count() or 1, sweep=sweep)
+
+
+def best_cpu_threads(folds: int):
+    """The loop is small-batch GEMVs: torch's default (all cores) oversubscribes badly on a many-core host (128 threads:
+    ~40x slower than 8).  Both the port and the unmodified reference get the best thread count of a short sweep."""
     from oracle import torch_port
     cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
     model = build_model("cpu")
     torch.manual_seed(0)
-    mel = torch.rand(1, 80, frames_for(1))
+    mel = torch.rand(1, 80, frames_for(max(1, folds // FOLDS_PER_GPU)))
     mels_f, aux_f = cpu_conditioning(model, mel)
     sd = {k: v.detach() for k, v in model.state_dict().items()}
-    B = mels_f.shape[0]
-    # The loop is 19-row GEMVs: on a many-core host torch's default (all cores) oversubscribes badly
-    # (128 threads: ~40x slower than 8).  Give the CPU arm its best thread count from a short sweep.
     trials = {}
-    for n in sorted({min(cores, c) for c in (4, 8, 16, 32, cores)}):
+    for n in sorted({min(cores, c) for c in (4, 8, 16, 32, 64, cores)}):
         torch.set_num_threads(n)
         torch.manual_seed(1234)
         _, dt = torch_port.generate_segments_torch(sd, mels_f, aux_f, steps=40)
         trials[n] = dt
-    # the 40-step sweep is noisy on a shared host: time the full sample on the two best counts, keep the faster
-    finals = {}
-    for n in sorted(trials, key=trials.get)[:2]:
-        torch.set_num_threads(n)
-        ts = []
-        for i in range(warmup + repeats):
-            torch.manual_seed(1234)
-            _, dt = torch_port.generate_segments_torch(sd, mels_f, aux_f, steps=sample_steps)
-            if i >= warmup:
-                ts.append(dt)
-        finals[n] = ts
-    best = min(finals, key=lambda n: float(np.mean(finals[n])))
-    torch.set_num_threads(best)
-    cores, times = best, finals[best]
-    return dict(B=B, steps=sample_steps, seconds=times, cores=cores, threads=torch.get_num_threads(),
-                host_cores=os.cpu_count() or 1, sweep={str(k): round(40 * B / v, 1) for k, v in trials.items()})
+    best = min(trials, key=trials.get)
+    return best, {str(k): round(40 * mels_f.shape[0] / v, 1) for k, v in trials.items()}, (sd, mels_f, aux_f)
 
 
 def run_reference_arm(args):
+    """bench.py --impl reference: the reference's own CPU implementation of the path on this box's host cores.
+    With oracle/_ref (oracle/make_ref.py: the unmodified reference files) it is the reference's `WaveRNN.generate()`
+    itself, end to end, all 12,100 steps of all folds (`kind: "reference"`); otherwise the torch-operator port of its loop
+    (`kind: "port"`, bit-identical samples, tests/test_oracle_vs_reference.py).  Under torchrun only rank 0 works."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample_steps = 1210                          # 10% of the 12,100 steps of every fold, all 19 folds
-    r = time_cpu_port(sample_steps, repeats=args.steps, warmup=args.warmup)
-    per_step = float(np.mean(r["seconds"]))
-    value = r["B"] * sample_steps / per_step
-    sample = f"{r['B']} folds x {sample_steps} of 12100 steps per bench step (torch CPU operators, best of thread sweep = {r['threads']} threads on {r['host_cores']} host cores; samples/s by threads: {r['sweep']})"
+    world = args.gpus
+    cfg = workload_config(world, "cfg2")
+    folds, S = cfg["folds"], cfg["steps_per_fold"]
+    threads, sweep, (sd, mels_f, aux_f) = best_cpu_threads(folds)
+    torch.set_num_threads(threads)
+    sys.path.insert(0, str(ROOT / "oracle"))
+    import make_ref
+    use_ref = make_ref.verify()
+    # one bench step = one pass over the workload; at N > 1 the CPU pass is bounded to 12100 // N steps of every fold
+    # (the same number of fold-steps as at N = 1) so that a --steps K run still ends within minutes
+    sample_steps = S if world == 1 else max(1210, S // world)
+    times = []
+    if use_ref and world == 1:
+        os.environ["WAVERNN_REFERENCE"] = str(ROOT / "oracle" / "_ref")
+        from oracle import ref_shim
+        ref_shim.REF_ROOT = str(ROOT / "oracle" / "_ref")
+        model = ref_shim.build_reference_model(seed=0, mode="MOL")
+        torch.manual_seed(0)
+        mel = torch.rand(1, 80, frames_for(world))
+        for i in range(args.warmup + args.steps):
+            torch.manual_seed(1234)
+            t0 = time.perf_counter()
+            wav = model.generate(mel, "/dev/null.wav", True, TARGET, OVERLAP, False)
+            dt = time.perf_counter() - t0
+            if i >= args.warmup:
+                times.append(dt)
+        assert len(wav) == (frames_for(world) - 1) * HOP
+        kind = "reference"
+        how = "UNMODIFIED reference WaveRNN.generate() (oracle/_ref, CPU, fp32), whole call: upsample network + fold + 12100-step loop + xfade"
+    else:
+        from oracle import torch_port
+        for i in range(args.warmup + args.steps):
+            torch.manual_seed(1234)
+            _, dt = torch_port.generate_segments_torch(sd, mels_f, aux_f, steps=sample_steps)
+            if i >= args.warmup:
+                times.append(dt)
+        kind = "port"
+        how = "torch-operator port of the reference loop (oracle/torch_port.py; bit-identical samples), loop only"
+    per_step = float(np.mean(times))
+    value = folds * sample_steps / per_step
+    sample = (f"{folds} folds x {sample_steps} of {S} steps per bench step; {how}; {threads} torch threads (best of sweep, samples/s by "
+              f"threads: {sweep}) on {os.cpu_count()} host cores")
     line = {"impl": "reference", "metric": "audio samples/sec (22.05 kHz) batched MoL generate", "value": value,
             "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": per_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "cfg2: 10 s mel (T=800) -> 19 folds x 12100 steps, target=11000 overlap=550, "
-                                   "MoL head, rnn_dims=512, random-init", "sample": sample},
-            "cpu_baseline": {"value": value, "unit": "samples/s", "cores": r["cores"], "kind": "port", "sample": sample},
+            "dtype": "f32", "data": "synthetic", "config": cfg,
+            "cpu_baseline": {"value": value, "unit": "samples/s", "cores": threads, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "x_realtime": value / 22050.0}
     emit(line)
@@ -232,14 +281,14 @@ def run_ours(args):
     shard = shard_folds(geo, rank, world, HOP)
     B_total, S = geo.n_seg, geo.seg_len
 
-    # ---- resident inputs for the device-timed region ------------------------------------
+    # ---- resident inputs for the device-timed region: exactly what WaveRNN.generate() hands to the library by default
+    # (frame-rate conditioning: padded mel, MelResNet frames, 5-tap table; the library forms the x275 rows itself) ------
     model.eval()
     with torch.no_grad():
         mp = torch.nn.functional.pad(mel_host.to(device), (2, 2))
-        m_up, aux = model.conditioning(mp, shard.frame_lo, shard.frame_hi)
-        off = shard.row_lo - shard.frame_lo * HOP
-        m_up = m_up[off:off + shard.row_hi - shard.row_lo].contiguous()
-        aux = aux[off:off + shard.row_hi - shard.row_lo].contiguous()
+        mel_fr = mp[0].transpose(0, 1).contiguous().float()
+        aux_fr = model.upsample.resnet(mp)[0].transpose(0, 1).contiguous().float()
+        taps = model.upsample_taps(device)
     f0, n = shard.seg_first, shard.n_seg
     if cfg5 or cfg3:
         u_all, uni_ptr, h2d_rng = None, 0, 0
@@ -253,9 +302,9 @@ def run_ours(args):
     stream = torch.cuda.current_stream(device)
 
     def device_step():
-        engine.generate(mels_up=m_up.data_ptr(), aux=aux.data_ptr(), L=m_up.shape[0], n_seg=n, seg_len=S,
-                        seg_stride=geo.seg_stride, out=out.data_ptr(), seg_first=f0, uniforms=uni_ptr,
-                        steps=args.seg_steps, stream=stream.cuda_stream)
+        engine.generate(mels_up=0, aux=0, L=T * HOP, n_seg=n, seg_len=S, seg_stride=geo.seg_stride, out=out.data_ptr(),
+                        seg_first=f0, uniforms=uni_ptr, steps=args.seg_steps, mel_frames=mel_fr.data_ptr(),
+                        aux_frames=aux_fr.data_ptr(), up_taps=taps.data_ptr(), hop=HOP, cond_mode=0, stream=stream.cuda_stream)
         if world > 1:
             return gather_segments(out, shard, geo)
         return out
@@ -325,14 +374,12 @@ def run_ours(args):
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_dev / args.steps * 1e3,
             "higher_is_better": True, "scaling": "strong" if cfg5 else "weak", "vs_baseline": None,
             "dtype": {"fp16": "f16", "bf16": "bf16", "fp32": "f32"}[args.precision], "data": "synthetic",
-            "config": {"workload": (f"cfg5: mel T={T} frames (35.8 min) -> {B_total} folds x {S} steps sharded over {world} GPU(s), "
-                                    if cfg5 else
-                                    f"cfg2 x{world}: mel T={T} frames -> {B_total} folds x {S} steps ({FOLDS_PER_GPU} folds per GPU), ")
-                                   + f"target={TARGET} overlap={OVERLAP}, " + ("RAW head (bits=9, mu-law)" if cfg3 else "MoL head") + ", rnn_dims=512, random-init weights, torch.rand mel",
-                       "engine": model.gen_stats.get("engine", engine.name), "grid_ctas": engine.grid_ctas,
-                       "parallelism": f"folds sharded x{world}" if world > 1 else "single GPU",
-                       "l2_policy": "no flush: the per-step conditioning stream (183 MB per 19 folds) exceeds the 126 MB L2",
-                       "rng": "in-kernel Philox4x32-10" if (cfg5 or cfg3) else "reference-compatible torch CPU draws, resident in HBM for `value`"},
+            "config": workload_config(world, args.workload),
+            "impl_details": {"engine": engine.name, "grid_ctas": engine.grid_ctas,
+                             "parallelism": f"folds sharded x{world}, one NCCL all-gather of the sample blocks" if world > 1 else "single GPU",
+                             "conditioning": "frame-rate tensors resident in HBM; the library forms the x275 rows (pre-pass per tile / staging warps)",
+                             "l2_policy": "no flush: every step streams fresh conditioning rows and draws; the weights are SUPPOSED to stay on chip",
+                             "rng": "in-kernel Philox4x32-10" if (cfg5 or cfg3) else "reference-compatible torch CPU draws, resident in HBM for `value`"},
             "clocks": clocks, "gpu_launches": int(gpu_launches),
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(mel_host.numel() * 4 + h2d_rng),
                     "d2h_bytes_per_step": int(B_total * S * 4), "ms_per_step": t_e2e / args.steps * 1e3},
@@ -354,17 +401,25 @@ def run_ours(args):
 
 
 def run_cfg4(args, device, rank, world, local):
-    """BASELINE configs[3] without the text front-end ('16 synthetic mels of 150-800 frames'): the folds of
-    16 utterances vocoded as ONE job through WaveRNN.generate_many (sharded over the ranks, one all-gather).  Tacotron
-    itself is out of scope and stays torch.  The whole call is host-facing, so `value` and `e2e` are the same
-    end-to-end measurement (host mels in, float64 waveforms out), stated in `config`."""
+    """BASELINE configs[3] (gen_tacotron.py wavernn, 16 sentences): the reference Tacotron's mels of 16 sentences
+    (committed fixture) vocoded with the reference's shipped LJSpeech checkpoint as ONE job through
+    WaveRNN.generate_many (all folds of all sentences in one launch, sharded over the ranks, one all-gather).  Tacotron
+    itself is out of scope (torch, run once in the build container to make the fixture).  The whole call is host-facing,
+    so `value` and `e2e` are the same end-to-end measurement (host mels in, float64 waveforms out), stated in `config`."""
+    import io as _io
+    import zipfile
     import torch.distributed as dist
     model = build_model(device)
+    with zipfile.ZipFile(ROOT / "tests" / "golden" / "pretrained" / "ljspeech.wavernn.mol.800k.zip") as z:
+        model.load_state_dict(torch.load(_io.BytesIO(z.read("latest_weights.pyt")), map_location=device), strict=False)
     model.gen_precision, model.gen_engine, model.gen_rng = args.precision, args.engine, "philox"
-    rs = np.random.RandomState(0)
-    frames = [int(t) for t in rs.randint(150, 801, size=16)]
-    torch.manual_seed(0)
-    mels = [torch.rand(1, 80, T).pin_memory() for T in frames]
+    # the 16 mel spectrograms the reference's own Tacotron (shipped checkpoint, CPU) produced for 16 sentences -- the 6 of
+    # sentences.txt plus 10 more -- prepared exactly as gen_tacotron.py:139-143 hands them to voc_model.generate
+    # (fixture tests/golden/tacotron_mels.npz, generator tests/golden/make_tacotron_mels.py; uint16-quantised [0, 1])
+    g = np.load(ROOT / "tests" / "golden" / "tacotron_mels.npz", allow_pickle=False)
+    mels_np = [g[f"mel_{i:02d}"].astype(np.float32) / np.float32(65535.0) for i in range(16)]
+    frames = [int(m.shape[1]) for m in mels_np]
+    mels = [torch.from_numpy(m).unsqueeze(0).pin_memory() for m in mels_np]
     from wavernn_b200.sharding import fold_geometry
     S = TARGET + 2 * OVERLAP
     folds = [fold_geometry(T * HOP, TARGET, OVERLAP).n_seg for T in frames]
@@ -401,9 +456,9 @@ def run_cfg4(args, device, rank, world, local):
         emit({"metric": "audio samples/sec (22.05 kHz) batched MoL generate", "value": value, "unit": "samples/s",
               "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t / args.steps * 1e3,
               "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
-              "config": {"workload": f"cfg4: 16 synthetic utterances of {min(frames)}-{max(frames)} mel frames ({sum(frames)} frames, "
-                                     f"{sum(frames) * HOP / 22050:.1f} s of audio) -> {sum(folds)} folds x {S} steps in ONE generate_many job, "
-                                     f"sharded over {world} GPU(s); Tacotron not included (torch, out of scope)",
+              "config": {"workload": f"cfg4: the reference Tacotron's mels of 16 sentences ({min(frames)}-{max(frames)} frames each, {sum(frames)} frames, "
+                                     f"{sum(frames) * HOP / 22050:.1f} s of audio; fixture tests/golden/tacotron_mels.npz) -> {sum(folds)} folds x {S} steps in ONE "
+                                     f"generate_many job, sharded over {world} GPU(s), WaveRNN weights = the reference's shipped LJSpeech checkpoint; Tacotron itself is not timed (torch, out of scope)",
                          "engine": model.gen_stats.get("engine"), "rng": "in-kernel Philox4x32-10",
                          "note": "value == e2e: the job is timed end to end through the public call (host mels in, float64 waveforms out)"},
               "clocks": clk.summary(), "gpu_launches": int(engine.launch_count - launches0),

@@ -146,6 +146,12 @@ typedef struct {
   const float *up_taps;
   int32_t hop;
   int32_t cond_mode;
+  /* Optional (MoL parity mode, tensor-core engines): `uniforms` may still be in flight when the job is enqueued.
+   * *uniforms_ready (device, uint32) = number of leading rows of `uniforms` that are valid; the kernel consumes row t at
+   * step t and waits (bounded by the watchdog) while t >= *uniforms_ready.  The caller uploads the draws in step
+   * chunks on another stream and bumps the counter after each chunk (a 4-byte copy on that same stream), so the
+   * host-side replay of torch's generator overlaps the kernel instead of preceding it.  NULL: all rows are valid.  */
+  const uint32_t *uniforms_ready;
 } wrnn_job;
 
 int wrnn_abi_version(void);

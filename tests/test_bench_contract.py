@@ -17,7 +17,15 @@ def _check(stdout: str, n_gpus: int):
     assert KEYS <= set(d), KEYS - set(d)
     assert d["impl"] == "reference" and d["n_gpus"] == n_gpus and d["steps"] == 1 and d["warmup"] == 0
     assert d["unit"] == "samples/s" and d["higher_is_better"] is True and d["vs_baseline"] is None
-    assert d["value"] > 0 and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    # N = 1 with oracle/_ref present (oracle/make_ref.py): the unmodified reference generate(); otherwise its torch-operator port
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_ref", ROOT / "oracle" / "make_ref.py")
+    make_ref = importlib.util.module_from_spec(spec); spec.loader.exec_module(make_ref)
+    want_kind = "reference" if (n_gpus == 1 and make_ref.verify()) else "port"
+    assert d["value"] > 0 and d["cpu_baseline"]["kind"] == want_kind and d["cpu_baseline"]["cores"] >= 1
+    spec = importlib.util.spec_from_file_location("bench", ROOT / "bench.py")
+    bench = importlib.util.module_from_spec(spec); spec.loader.exec_module(bench)
+    assert d["config"] == bench.workload_config(n_gpus, "cfg2")          # the SAME config object the GPU arm prints
     assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert "workload" in d["config"] and "sample" in d["cpu_baseline"]
 

@@ -33,7 +33,7 @@ def test_header_symbols_are_exported(lib):
 def test_struct_layouts_match_header():
     assert ctypes.sizeof(cabi.WrnnCfg) == 8 * 4
     assert ctypes.sizeof(cabi.WrnnWeights) == 16 * ctypes.sizeof(ctypes.c_void_p)
-    assert ctypes.sizeof(cabi.WrnnJob) == 8 * 4 + 4 * 4 + 2 * 8 + 2 * 8 + 3 * 8 + 2 * 8 + 3 * 8 + 2 * 4
+    assert ctypes.sizeof(cabi.WrnnJob) == 8 * 4 + 4 * 4 + 2 * 8 + 2 * 8 + 3 * 8 + 2 * 8 + 3 * 8 + 2 * 4 + 8      # + uniforms_ready (ABI v5)
     assert cabi.WrnnJob.seg_first.offset == 40 and cabi.WrnnJob.uniforms.offset == 48 and cabi.WrnnJob.out.offset == 80
 
 

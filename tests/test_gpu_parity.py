@@ -314,3 +314,26 @@ def test_device_epilogue_is_bit_identical_to_the_host_epilogue(mode, batched, mu
         wavs[where] = model.generate(mel, None, batched, 2750, 275, mu_law)
     assert wavs["device"].dtype == np.float64 and wavs["device"].shape == wavs["host"].shape == ((33 - 1) * 275,)
     assert np.array_equal(wavs["device"], wavs["host"])
+
+
+def test_streamed_draws_equal_resident_draws_and_leave_the_generator_where_the_reference_does(mol):
+    """wrnn_job::uniforms_ready: the reference-compatible draws replayed and uploaded in step chunks WHILE the kernel
+    runs (default) give the same waveform as uploading them all first, and torch's CPU generator ends in the state the
+    reference's generate() leaves it in (so the next call / the next torch.rand of the caller is unaffected)."""
+    model, g = mol["model"], mol["g"]
+    mel = helpers.make_mel(30, 0)
+    wavs, tails = {}, {}
+    try:
+        for streamed in (True, False):
+            model.gen_stream_draws, model.gen_draw_chunk = streamed, 256          # 3300 steps -> 13 chunks
+            torch.manual_seed(1234)
+            wavs[streamed] = model.generate(mel, None, True, 2750, 275, False)
+            tails[streamed] = torch.rand(4)
+    finally:
+        model.gen_stream_draws, model.gen_draw_chunk = True, 1024
+    assert np.array_equal(wavs[True], wavs[False]) and torch.equal(tails[True], tails[False])
+    assert np.abs(wavs[True] - g["wav"]).max() <= 2e-2
+    torch.manual_seed(1234)
+    torch.nn.GRUCell(512, 512); torch.nn.GRUCell(544, 512)
+    torch.empty(3300, 33).uniform_(1e-5, 1 - 1e-5)
+    assert torch.equal(torch.rand(4), tails[True])                              # == the reference's consumption

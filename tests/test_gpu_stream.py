@@ -140,3 +140,52 @@ def test_stream_engine_trained_checkpoint_teacher_forced():
     e = np.abs(lg - g["logits"])
     print(f"{name} trained teacher-forced logits: max {e.max():.3e} p99.9 {np.quantile(e, 0.999):.3e} median {np.median(e):.3e}")
     assert e.max() <= 1e-1 and np.quantile(e, 0.999) <= 3e-2 and np.median(e) <= 1e-3
+
+
+def test_stream_engine_cfg5_4096_folds_shard_invariance_and_agreement_with_the_persistent_engine():
+    """BASELINE configs[4] at its full fold count (T = 172,034 frames -> 4096 folds; first 48 steps): frame-rate
+    conditioning formed by the staging warps, 128 CTAs of 32 folds.  Size-independent properties: any shard / tile of
+    the job generated on its own (other tile size, other seg_first) reproduces its rows bit for bit (fold-keyed Philox,
+    fold-independent arithmetic), with or without fold tables; and the persistent tcgen05 engine -- different
+    decomposition, same rounding contract -- agrees to accumulation-order noise."""
+    from wavernn_b200 import cabi
+    from wavernn_b200.sharding import fold_geometry
+    model = helpers.make_model(0, "MOL", "cuda")
+    dev = torch.device("cuda")
+    T, hop, steps = 172_034, 275, 48
+    geo = fold_geometry(T * hop, 11_000, 550)
+    assert geo.n_seg == 4096
+    torch.manual_seed(0)
+    mel = torch.rand(1, 80, T, device=dev)
+    with torch.no_grad():
+        mp = torch.nn.functional.pad(mel, (2, 2))
+        mel_fr = mp[0].transpose(0, 1).contiguous()
+        aux_fr = model.eval().upsample.resnet(mp)[0].transpose(0, 1).contiguous()
+        taps = model.upsample_taps(dev)
+
+    def run(eng, f0, n, tables=False):
+        row0 = (torch.arange(f0, f0 + n, device=dev, dtype=torch.int64) * geo.seg_stride).contiguous()
+        end = torch.full_like(row0, T * hop)
+        out = torch.full((n, steps), float("nan"), device=dev)
+        eng.generate(mels_up=0, aux=0, L=T * hop, n_seg=n, seg_len=geo.seg_len, seg_stride=geo.seg_stride, out=out.data_ptr(),
+                     seg_first=f0, steps=steps, philox_seed=11, fold_row0=row0.data_ptr() if tables else 0,
+                     fold_row_end=end.data_ptr() if tables else 0, mel_frames=mel_fr.data_ptr(), aux_frames=aux_fr.data_ptr(),
+                     up_taps=taps.data_ptr(), hop=hop, stream=torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        eng.check()
+        return out.cpu().numpy()
+
+    eng = cabi.Engine(model.hot_state(), n_classes=30, mode="MOL", precision="fp16", engine="stream", device=0)
+    big = run(eng, 0, 4096)
+    assert eng.name.startswith("tcgen05-stream") and eng.grid_ctas == 128 and eng.launch_count == 1
+    assert np.isfinite(big).all() and np.abs(big).max() <= 1.0 and big.std() > 0.05
+    for f0, n in ((0, 64), (64 * 37, 64), (4096 - 64, 64), (512 * 5, 512), (4000, 96)):
+        assert np.array_equal(run(eng, f0, n), big[f0:f0 + n]), (f0, n)
+    assert np.array_equal(run(eng, 512 * 3, 512, tables=True), big[512 * 3:512 * 4])
+    eng.close()
+    tc = cabi.Engine(model.hot_state(), n_classes=30, mode="MOL", precision="fp16", engine="tcgen05", device=0)
+    ref = run(tc, 64 * 37, 64)
+    tc.close()
+    d = np.abs(ref - big[64 * 37:64 * 38]).max()
+    print("cfg5 fold tile 37: stream engine vs persistent engine:", d)
+    assert d <= 1e-3

@@ -20,13 +20,13 @@ B_COND, B_H1PREV, B_H1NEW, B_H2, B_Y1, B_Y2, B_NONE = 0, 1, 2, 3, 4, 5, 0xFF
 W_NONE, W_COND, W_H1NEW, W_H2NEW, W_Y1, W_Y2 = range(6)
 
 CHUNK = np.dtype([("bytes", "<u4"), ("acc", "u1"), ("nk", "u1"), ("b_buf", "u1"), ("b_buf2", "u1"), ("k0", "<u2"),
-                  ("flags", "u1"), ("wait_b", "u1"), ("wait_acc", "u1"), ("commit", "u1"), ("pad", "<u2")])
+                  ("flags", "u1"), ("wait_b", "u1"), ("wait_acc", "u1"), ("commit", "u1"), ("owner", "u1"), ("phase", "u1")])
 
 
 def get_plan(sd, precision="fp16"):
     lib = cabi.load()
     lib.wrnn_debug_stream_plan.restype = C.c_int
-    lib.wrnn_debug_stream_plan.argtypes = [C.c_void_p] * 7
+    lib.wrnn_debug_stream_plan.argtypes = [C.c_void_p] * 8
     cfg = cabi.WrnnCfg(512, 512, 80, 32, 30, cabi.MODE_MOL, {"fp16": cabi.PREC_F16, "bf16": cabi.PREC_BF16}[precision], 3)
     w = cabi.WrnnWeights()
     keep = []
@@ -35,12 +35,18 @@ def get_plan(sd, precision="fp16"):
         keep.append(a)
         setattr(w, field, a.ctypes.data)
     nb, nc = C.c_uint64(0), C.c_uint64(0)
-    assert lib.wrnn_debug_stream_plan(C.byref(cfg), C.byref(w), None, C.byref(nb), None, C.byref(nc), None) == 0
+    assert lib.wrnn_debug_stream_plan(C.byref(cfg), C.byref(w), None, C.byref(nb), None, C.byref(nc), None, None) == 0
     blob = np.zeros(nb.value, np.uint8)
     prog = np.zeros(nc.value, CHUNK)
     vec = np.zeros(4096 * 2 + 1536 * 2 + 128, np.float32)
+    mine = np.zeros((4, nc.value), np.uint16)
     assert lib.wrnn_debug_stream_plan(C.byref(cfg), C.byref(w), blob.ctypes.data, C.byref(nb), prog.ctypes.data, C.byref(nc),
-                                      vec.ctypes.data) == 0
+                                      vec.ctypes.data, mine.ctypes.data) == 0
+    # the four issuing warps' lists partition the program, ascending, and agree with the owner field
+    lists = [m[m != 0xFFFF].astype(int) for m in mine]
+    assert sorted(np.concatenate(lists).tolist()) == list(range(nc.value))
+    for o, l in enumerate(lists):
+        assert np.all(np.diff(l) > 0) and np.all(prog["owner"][l] == o)
     v = dict(qk=vec[:4096], vq=vec[4096:8192], b1h=vec[8192:9728], b2h=vec[9728:11264], b3=vec[11264:])
     return blob, prog, v
 
@@ -67,8 +73,9 @@ def interpret(blob, prog, v, m_up, aux, U, *, n_seg, seg_len, seg_stride, steps,
     L = m_up.shape[0]
     cond_z = np.concatenate([np.concatenate([m_up, aux], 1).astype(np.float32), np.zeros((1, CDIM), np.float32)])
     base = np.arange(NF) * seg_stride
-    X = [np.zeros((NF, H), np.float32), np.zeros((NF, H), np.float32)]       # h1 ping-pong (+ y1)
-    H2 = np.zeros((NF, H), np.float32); Y2 = np.zeros((NF, H), np.float32)
+    X = [np.zeros((NF, H), np.float32), np.zeros((NF, H), np.float32)]       # h1 ping-pong (+ y1, then y2, in X[cur])
+    H2 = np.zeros((NF, H), np.float32)
+    y2_pending = {}                                                           # fc2 results held back until all fc2 MMAs are done
     h1 = np.zeros((H, NF), np.float32); h2 = np.zeros((H, NF), np.float32)   # fp32 state, [unit][fold] like the kernel's scratch
     x = np.zeros(NF, np.float32)
     acc = np.zeros((16, 128, NF), np.float32)
@@ -82,19 +89,27 @@ def interpret(blob, prog, v, m_up, aux, U, *, n_seg, seg_len, seg_stride, steps,
         ready = {W_COND}                      # staging runs ahead of the step
         waited = set()
         n_commit = [0] * NB                   # phase of each block within the step
+        n_arrive = [0] * NB                   # commits of the current (phase, block): the epilogue runs after all four issuers'
+        seen_owner = set()                    # (owner, phase, block) that already issued a chunk this step
         acc_drained = [True] * NB
         h2_touched = False
         xs = x.copy()
         for i, c in enumerate(prog):
             def image(buf):
                 if buf == B_COND: return cond
-                if buf in (B_H1PREV, B_Y1): return X[cur]
+                if buf in (B_H1PREV, B_Y1, B_Y2): return X[cur]
                 if buf == B_H1NEW: return X[cur ^ 1]
-                return H2 if buf == B_H2 else Y2
-            if c["wait_acc"]:
-                blk = int(c["wait_acc"]) - 1
-                assert acc_drained[blk], f"chunk {i}: accumulators of block {blk} not drained"
+                assert buf == B_H2
+                return H2
             blk_of_acc = int(c["acc"]) // 4
+            key = (int(c["owner"]), int(c["phase"]), blk_of_acc)
+            assert int(c["phase"]) == n_commit[blk_of_acc], f"chunk {i}: phase field {c['phase']} but block {blk_of_acc} is in phase {n_commit[blk_of_acc]}"
+            if key not in seen_owner:         # an issuer's first chunk of a (phase, block) must carry the accumulator-free wait
+                assert int(c["wait_acc"]) == blk_of_acc + 1, f"chunk {i}: first chunk of {key} lacks wait_acc"
+                assert acc_drained[blk_of_acc] or any(k[1:] == key[1:] for k in seen_owner), f"chunk {i}: block {blk_of_acc} not drained"
+                seen_owner.add(key)
+            else:
+                assert c["wait_acc"] == 0
             if c["wait_b"]:
                 assert int(c["wait_b"]) in ready, f"chunk {i} waits for operand {c['wait_b']} that no epilogue of this step produces before it"
                 waited.add(int(c["wait_b"]))
@@ -112,7 +127,11 @@ def interpret(blob, prog, v, m_up, aux, U, *, n_seg, seg_len, seg_stride, steps,
             if c["b_buf2"] != B_NONE:
                 acc[a] += tiles[i] @ image(int(c["b_buf2"]))[:, k0:k0 + kc].T
             if c["commit"]:
+                assert int(c["commit"]) - 1 == blk_of_acc
+                n_arrive[blk_of_acc] += 1
+            if c["commit"] and n_arrive[blk_of_acc] == 4:
                 b = int(c["commit"]) - 1
+                n_arrive[b] = 0
                 ph = n_commit[b]; n_commit[b] += 1
                 u = slice(b * 128, b * 128 + 128)
                 if ph in (0, 1):                       # GRU1 / GRU2
@@ -131,13 +150,21 @@ def interpret(blob, prog, v, m_up, aux, U, *, n_seg, seg_len, seg_stride, steps,
                     if n_commit == [ph + 1] * NB: ready.add(W_H2NEW if ph else W_H1NEW)
                 elif ph in (2, 3):                     # fc1 / fc2
                     q0 = 6 * H + (ph - 2) * H
-                    y = np.maximum(acc[4 * b + (ph - 2)] + v["qk"][q0 + b * 128: q0 + b * 128 + 128][:, None]
+                    y = np.maximum(((acc[4 * b] + acc[4 * b + 1]) + (acc[4 * b + 2] + acc[4 * b + 3])) + v["qk"][q0 + b * 128: q0 + b * 128 + 128][:, None]
                                    + xs[None, :] * v["vq"][q0 + b * 128: q0 + b * 128 + 128][:, None], 0).astype(np.float32)
-                    (Y2 if ph == 3 else X[cur])[:, u] = rnd(y).T
-                    if n_commit == [ph + 1] * NB: ready.add(W_Y2 if ph == 3 else W_Y1)
+                    if ph == 2:
+                        X[cur][:, u] = rnd(y).T
+                        if n_commit == [3] * NB: ready.add(W_Y1)
+                    else:                              # y2 replaces y1 only after the LAST block's fc2 MMAs (kernel: registers)
+                        y2_pending[b] = rnd(y).T
+                        if n_commit == [4] * NB:
+                            for bb, val in y2_pending.items():
+                                X[cur][:, bb * 128: bb * 128 + 128] = val
+                            y2_pending.clear()
+                            ready.add(W_Y2)
                 else:                                  # fc3 + sampler
                     assert b == 0 and ph == 4
-                    lg = (acc[2][:30] + v["b3"][:30, None]).T.astype(np.float32)
+                    lg = (((acc[0] + acc[1]) + (acc[2] + acc[3]))[:30] + v["b3"][:30, None]).T.astype(np.float32)
                     logits[t] = lg
                     u_t = U[t]
                     x = O.mol_sample(lg, u_t[:10 * NF].reshape(NF, 10), u_t[10 * NF:11 * NF]).astype(np.float32)

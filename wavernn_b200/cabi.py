@@ -54,7 +54,7 @@ class WrnnJob(C.Structure):
                 ("out", C.c_void_p), ("x_force", C.c_void_p), ("logits_out", C.c_void_p),
                 ("fold_row0", C.c_void_p), ("fold_row_end", C.c_void_p),
                 ("mel_frames", C.c_void_p), ("aux_frames", C.c_void_p), ("up_taps", C.c_void_p),
-                ("hop", C.c_int32), ("cond_mode", C.c_int32)]
+                ("hop", C.c_int32), ("cond_mode", C.c_int32), ("uniforms_ready", C.c_void_p)]
 
 
 _lib = None
@@ -165,12 +165,12 @@ class Engine:
                  seg_first: int = 0, steps: int = 0, uniforms: int = 0, expo: int = 0, philox_seed: int = 0,
                  philox_offset: int = 0, x_force: int = 0, logits_out: int = 0, fold_row0: int = 0, fold_row_end: int = 0,
                  mel_frames: int = 0, aux_frames: int = 0, up_taps: int = 0, hop: int = 0, cond_mode: int = 0,
-                 stream: int = 0):
+                 uniforms_ready: int = 0, stream: int = 0):
         """All buffer arguments are raw device addresses (ints).  Asynchronous."""
         job = WrnnJob(mels_up, aux, L, seg_stride, n_seg, seg_len, seg_first, steps, uniforms or None,
                       expo or None, philox_seed, philox_offset, out, x_force or None, logits_out or None,
                       fold_row0 or None, fold_row_end or None, mel_frames or None, aux_frames or None, up_taps or None,
-                      hop, cond_mode)
+                      hop, cond_mode, uniforms_ready or None)
         _check(self.lib, self.lib.wrnn_generate(self._h, C.byref(job), C.c_void_p(stream or None)))
 
     def generate_host(self, *, mels_up, aux, n_seg: int, seg_len: int, seg_stride: int, seg_first: int = 0, steps: int = 0,
@@ -187,7 +187,7 @@ class Engine:
         ptr = lambda a: None if a is None else a.ctypes.data
         job = WrnnJob(ptr(mels_up), ptr(aux), mels_up.shape[0], seg_stride, n_seg, seg_len, seg_first, steps, ptr(uniforms),
                       ptr(expo), philox_seed, philox_offset, ptr(out), ptr(x_force), ptr(logits), None, None, None, None,
-                      None, 0, 0)
+                      None, 0, 0, None)
         _check(self.lib, self.lib.wrnn_generate_host(self._h, C.byref(job)))
         return (out, logits) if want_logits else out
 

@@ -155,6 +155,7 @@ static int validate(const wrnn_t* h, const wrnn_job* job, bool host) {
   }
   if (job->steps < 0 || job->steps > job->seg_len) { set_error("steps must be in [0, seg_len]"); return WRNN_E_INVALID; }
   if ((job->fold_row0 == nullptr) != (job->fold_row_end == nullptr)) { set_error("fold_row0 and fold_row_end go together"); return WRNN_E_INVALID; }
+  if (job->uniforms_ready && (!job->uniforms || host)) { set_error("uniforms_ready needs device `uniforms` (wrnn_generate)"); return WRNN_E_INVALID; }
   (void)host;
   return WRNN_OK;
 }
@@ -240,7 +241,8 @@ int wrnn_expand_conditioning(const float* mel_frames, const float* aux_frames, c
 // weights, so the packing and the schedule can be interpreted and checked without a GPU (tests/test_stream_plan.py).
 // Call with blob == NULL to obtain the sizes.  Not part of the reference-facing surface.
 int wrnn_debug_stream_plan(const wrnn_cfg* cfg, const wrnn_weights* w, uint8_t* blob, uint64_t* blob_bytes, uint8_t* prog,
-                           uint64_t* n_chunks, float* vectors /* qk[4096] vq[4096] b1h[1536] b2h[1536] b3[128] */) {
+                           uint64_t* n_chunks, float* vectors /* qk[4096] vq[4096] b1h[1536] b2h[1536] b3[128] */,
+                           uint16_t* mine /* [4][n_chunks]: per issuing warp, its chunk indices; unused tail = 0xffff */) {
   if (!cfg || !w || !blob_bytes || !n_chunks) { set_error("null argument"); return WRNN_E_INVALID; }
   HostWeights hw;
   hw.n_classes = cfg->n_classes;
@@ -266,6 +268,10 @@ int wrnn_debug_stream_plan(const wrnn_cfg* cfg, const wrnn_weights* w, uint8_t* 
     std::memcpy(v, plan.b1h.data(), G3 * 4); v += G3;
     std::memcpy(v, plan.b2h.data(), G3 * 4); v += G3;
     std::memcpy(v, plan.b3.data(), stream::MROWS * 4);
+    if (mine) {
+      std::memset(mine, 0xff, sizeof(uint16_t) * stream::N_ISSUERS * plan.prog.size());
+      for (int o = 0; o < stream::N_ISSUERS; ++o) std::memcpy(mine + (size_t)o * plan.prog.size(), plan.mine[o].data(), plan.mine[o].size() * sizeof(uint16_t));
+    }
   }
   *blob_bytes = plan.blob.size(); *n_chunks = plan.prog.size();
   return WRNN_OK;

@@ -443,6 +443,7 @@ class SimtEngine : public Engine {
 
   int generate(const wrnn_job& job, cudaStream_t stream) override {
     if (job.mel_frames) { set_error("the SIMT engine takes the upsampled conditioning streams (mels_up / aux)"); return WRNN_E_INVALID; }
+    if (job.uniforms_ready) { set_error("the SIMT engine needs all draws resident (no uniforms_ready)"); return WRNN_E_INVALID; }
     WRNN_CUDA_OK(cudaSetDevice(device));
     const int Bp = (job.n_seg + FT - 1) / FT * FT;
     const size_t need = ((size_t)4 * H * Bp + Bp + (size_t)P * NSTATE * Bp + (size_t)cfg.n_classes * Bp) * sizeof(float);

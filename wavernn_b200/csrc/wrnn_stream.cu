@@ -14,12 +14,15 @@
 // epilogue warps owns unit 128 b + u of block b for all NF folds.  The fp32 hidden state lives in L2-resident global
 // scratch ([2][512][NF] per tile); the fp16 operand images of h1', h2', y1, y2 live in shared memory.
 //
-// Warp roles (256 threads, no CTA-wide barrier inside the loop):
+// Warp roles (320 threads, no CTA-wide barrier inside the loop):
 //   warp 0     producer : walks the chunk list, one cp.async.bulk per chunk into the ring (full/empty mbarriers)
-//   warp 1     issuer   : waits for operands / accumulators / ring slots, issues the MMAs, commits slot-empty,
-//                         accumulator-full and cond-free barriers with tcgen05.commit
-//   warps 2-3  staging  : conditioning row of step t+1 for the NF folds (stream or frame-rate form) -> fp16 image
-//   warps 4-7  epilogue : TMEM -> registers, gates / relu / MoL sampler (SFU), state, operand images, output
+//   warps 1-4  issuers  : every accumulator chain belongs to one of them (GRU phases: r / z / in / hn; fc phases: a K
+//                         quarter into a partial accumulator).  Each walks its own chunk list: waits for operands /
+//                         accumulators / its ring slots, issues the MMAs, commits slot-empty, block-full and cond-free
+//                         with tcgen05.commit.  One warp alone sustains ~1 MMA per 100 cycles (measured, r02 first
+//                         version: 214 us per step); the tensor pipe wants one per ~40.
+//   warp 5     staging  : conditioning row of step t+1 for the NF folds (stream or frame-rate form) -> fp16 image
+//   warps 6-9  epilogue : TMEM -> registers, gates / relu / MoL sampler (SFU), state, operand images, output
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
@@ -38,23 +41,27 @@ namespace {
 using namespace tc;
 using namespace stream;
 
-constexpr int NT = 256;
+constexpr int NT = 320;
+constexpr int EPI_WARP0 = 6, EPI_TID0 = EPI_WARP0 * 32;     // first epilogue warp / thread
 constexpr int KQ = CDIM / 8;                 // 26 16-byte chunks per conditioning row
 constexpr int SBO_Q = KQ * 128;              // 3328: stride between 8-fold groups of the conditioning image
 constexpr int SBO_H = (H / 8) * 128;         // 8192: same for the K = 512 images
 constexpr int TMEM_COLS = 512;
-constexpr int NBAR = 32;
+constexpr int NBAR = 40;
+constexpr int MAX_STAGES = 12;
 
 template <int NF> struct Smem {
   static constexpr int GROUPS = NF / 8;
   static constexpr int ACT = GROUPS * SBO_H;                 // one K = 512 activation image
   static constexpr int COND = GROUPS * SBO_Q;                // one conditioning image
-  static constexpr int OFF_X0 = 0, OFF_X1 = ACT, OFF_H2 = 2 * ACT, OFF_Y2 = 3 * ACT;
-  static constexpr int OFF_COND = 4 * ACT;                   // two conditioning images (double buffer)
+  // Three K = 512 operand images: X0 / X1 = h1 ping-pong (this step's h1 is X[cur], h1' goes to X[cur^1]); y1 and then y2
+  // reuse X[cur] once its readers are done (y2 is written only after ALL fc2 MMAs have completed); h2 is updated in place.
+  static constexpr int OFF_X0 = 0, OFF_X1 = ACT, OFF_H2 = 2 * ACT;
+  static constexpr int OFF_COND = 3 * ACT;                   // two conditioning images (double buffer)
   static constexpr int OFF_RING = (OFF_COND + 2 * COND + 1023) / 1024 * 1024;
   static constexpr int LOGP = 33;                                            // padded row of the logits transpose (conflict-free both ways)
   static constexpr int MISC = LOGP * NF * 4 + NF * 4 + NBAR * 8 + 64;        // logits transpose, x, barriers, tmem slot
-  static constexpr int STAGES = (227 * 1024 - OFF_RING - MISC) / CHUNK_BYTES > 8 ? 8 : (227 * 1024 - OFF_RING - MISC) / CHUNK_BYTES;
+  static constexpr int STAGES = (227 * 1024 - OFF_RING - MISC) / CHUNK_BYTES > MAX_STAGES ? MAX_STAGES : (227 * 1024 - OFF_RING - MISC) / CHUNK_BYTES;
   static constexpr int OFF_LOG = OFF_RING + STAGES * CHUNK_BYTES;            // [NF][LOGP] fp32
   static constexpr int OFF_XS = OFF_LOG + LOGP * NF * 4;                       // [NF] fp32: previous sample per fold
   static constexpr int OFF_BAR = OFF_XS + NF * 4;
@@ -63,16 +70,17 @@ template <int NF> struct Smem {
   static_assert(BYTES <= 227 * 1024, "shared memory budget");
 };
 // barrier indices
-constexpr int BAR_FULL = 0, BAR_EMPTY = 8, BAR_ACC_FULL = 16, BAR_ACC_EMPTY = 20, BAR_READY = 24 /* +W_* (1..5), cond uses 24 and 25 */,
-              BAR_COND_FREE = 30;
-// ready barriers: index 24 + {0: cond[0], 1: cond[1], 2: h1new, 3: h2new, 4: y1, 5: y2}
+constexpr int BAR_FULL = 0, BAR_EMPTY = MAX_STAGES, BAR_ACC_FULL = 2 * MAX_STAGES, BAR_ACC_EMPTY = BAR_ACC_FULL + 4,
+              BAR_READY = BAR_ACC_EMPTY + 4 /* + {0: cond[0], 1: cond[1], 2: h1new, 3: h2new, 4: y1, 5: y2} */, BAR_COND_FREE = BAR_READY + 6;
+static_assert(BAR_COND_FREE + 2 <= NBAR, "barrier table");
 
 struct StreamParams {
   const unsigned char* blob; const uint4* prog; int n_chunks;
+  const unsigned short* mine[N_ISSUERS]; int n_mine[N_ISSUERS];     // per issuing warp: its chunk indices, ascending
   const float* qk; const float* vq; const float* b1h; const float* b2h; const float* b3;
   const float* mels_up; const float* aux; long long L; long long seg_stride; long long row_base;
   int n_total, steps, out_pitch, seg_first;
-  const float* uniforms; unsigned long long seed, offset;
+  const float* uniforms; const unsigned* uniforms_ready; unsigned long long seed, offset;
   float* out; const float* x_force; float* logits_out;
   const long long* fold_row0; const long long* fold_row_end;
   const float* mel_frames; const float* aux_frames; const float* up_taps; int hop;
@@ -88,6 +96,7 @@ __global__ void __launch_bounds__(NT, 1) wrnn_stream_kernel(const StreamParams p
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM::OFF_BAR);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM::OFF_BAR + NBAR * 8);
   volatile int* s_abort = reinterpret_cast<volatile int*>(smem + SM::OFF_BAR + NBAR * 8 + 16);   // CTA-local copy of the abort flag
+  volatile unsigned* issued_s = reinterpret_cast<volatile unsigned*>(smem + SM::OFF_BAR + NBAR * 8 + 32);   // chunks the producer has issued
   float* x_s = reinterpret_cast<float*>(smem + SM::OFF_XS);
   float* log_s = reinterpret_cast<float*>(smem + SM::OFF_LOG);
   auto bar = [&](int i) -> uint32_t { return smem_u32(&bars[i]); };
@@ -102,7 +111,7 @@ __global__ void __launch_bounds__(NT, 1) wrnn_stream_kernel(const StreamParams p
     int4* z = reinterpret_cast<int4*>(smem);
     for (int i = tid; i < SM::OFF_RING / 16; i += NT) z[i] = make_int4(0, 0, 0, 0);       // all operand images start as zeros
     if (tid < NF) x_s[tid] = 0.f;
-    if (tid == 0) *s_abort = 0;
+    if (tid == 0) { *s_abort = 0; *issued_s = 0; }
   }
   if (tid == 0) {
     for (int i = 0; i < SM::STAGES; ++i) {
@@ -110,14 +119,14 @@ __global__ void __launch_bounds__(NT, 1) wrnn_stream_kernel(const StreamParams p
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar(BAR_EMPTY + i)));
     }
     for (int i = 0; i < 4; ++i) {
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar(BAR_ACC_FULL + i)));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar(BAR_ACC_FULL + i)), "n"(N_ISSUERS));   // one commit per issuing warp
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 128;" :: "r"(bar(BAR_ACC_EMPTY + i)));
     }
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 64;" :: "r"(bar(BAR_READY + 0)));
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 64;" :: "r"(bar(BAR_READY + 1)));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 32;" :: "r"(bar(BAR_READY + 0)));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 32;" :: "r"(bar(BAR_READY + 1)));
     for (int i = 2; i < 6; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 128;" :: "r"(bar(BAR_READY + i)));
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar(BAR_COND_FREE + 0)));
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar(BAR_COND_FREE + 1)));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar(BAR_COND_FREE + 0)), "n"(N_ISSUERS));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar(BAR_COND_FREE + 1)), "n"(N_ISSUERS));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -155,34 +164,62 @@ __global__ void __launch_bounds__(NT, 1) wrnn_stream_kernel(const StreamParams p
         const int slot = g % SM::STAGES;
         wait(bar(BAR_EMPTY + slot), ((g / SM::STAGES) & 1) ^ 1);      // slot drained by the MMAs
         tma_bulk_g2s(smem_u32(smem + SM::OFF_RING + slot * CHUNK_BYTES), p.blob + off, bytes, bar(BAR_FULL + slot));
+        __syncwarp();
+        if (lane == 0) *issued_s = g + 1;                      // see the issuers: parity waits need "this phase is armed"
         off += bytes;
       }
     }
-  } else if (warp == 1) {
-    // ======================================================================================================= issuer
+  } else if (warp <= N_ISSUERS) {
+    // ====================================================================================================== issuers
+    const int q = warp - 1;
     const uint32_t idesc = umma_idesc(MROWS, NF, FMT);
-    unsigned g = 0, acc_par = 0, acc_seen = 0;               // per block: parity of / any accumulator-free waits so far
-    const bool profiling = p.prof != nullptr && blockIdx.x == 0;
+    const unsigned short* my = p.mine[q];
+    const int n_my = p.n_mine[q];
+    const bool profiling = p.prof != nullptr && blockIdx.x == 0 && q == 0;
     long long t_ring = 0, t_b = 0, t_acc = 0, t_issue = 0;
+    const uint32_t ring0 = smem_u32(smem + SM::OFF_RING), s0 = smem_u32(smem);
+    unsigned issued_seen = 0;
     for (int t = 0; t < S && !*s_abort; ++t) {
       const int cur = t & 1;
-      for (int c = 0; c < p.n_chunks; ++c, ++g) {
-        const uint4 raw = __ldg(p.prog + c);
-        const uint32_t acc = raw.y & 0xff, nk = (raw.y >> 8) & 0xff, b_buf = (raw.y >> 16) & 0xff, b_buf2 = raw.y >> 24;
-        const uint32_t k0 = raw.z & 0xffff, flags = (raw.z >> 16) & 0xff, wait_b = raw.z >> 24;
-        const uint32_t wait_acc = raw.w & 0xff, commit = (raw.w >> 8) & 0xff;
+      const unsigned gbase = (unsigned)t * (unsigned)p.n_chunks;       // ring position of this step's chunk 0
+      uint4 raw = __ldg(p.prog + __ldg(my));
+      for (int i = 0; i < n_my; ++i) {
+        const unsigned c = __ldg(my + i);
+        const uint4 cur_raw = raw;
+        if (i + 1 < n_my) raw = __ldg(p.prog + __ldg(my + i + 1));     // next record: its latency hides under this chunk
+        const uint32_t acc = cur_raw.y & 0xff, nk = (cur_raw.y >> 8) & 0xff, b_buf = (cur_raw.y >> 16) & 0xff, b_buf2 = cur_raw.y >> 24;
+        const uint32_t k0 = cur_raw.z & 0xffff, flags = (cur_raw.z >> 16) & 0xff, wait_b = cur_raw.z >> 24;
+        const uint32_t wait_acc = cur_raw.w & 0xff, commit = (cur_raw.w >> 8) & 0xff, phase = cur_raw.w >> 24;
         long long c0 = 0, c1 = 0, c2 = 0, c3 = 0;
         if (profiling) c0 = clock64();
-        if (wait_acc) {                                       // the epilogue of the previous phase has drained this block
-          const int blk = wait_acc - 1;                       // wait number k (k >= 1) needs completion k-1 of the barrier
-          if ((acc_seen >> blk) & 1u) wait(bar(BAR_ACC_EMPTY + blk), ((acc_par >> blk) & 1u) ^ 1u);
-          acc_seen |= 1u << blk; acc_par ^= 1u << blk;
+        if (wait_acc) {
+          // the epilogue of the previous (phase, block) use must have drained the block: its arrivals on acc_empty[blk] are
+          // numbered A*t + phase (A = 5 for block 0, which also serves fc3; 4 otherwise); we need number A*t + phase - 1
+          const int blk = wait_acc - 1;
+          const int idx = (blk == 0 ? N_PHASES : N_PHASES - 1) * t + (int)phase - 1;
+          if (idx >= 0) wait(bar(BAR_ACC_EMPTY + blk), (uint32_t)idx & 1u);
         }
         if (profiling) c1 = clock64();
         if (wait_b == W_COND) wait(bar(BAR_READY + cur), (uint32_t)(t >> 1) & 1);
         else if (wait_b != W_NONE) wait(bar(BAR_READY + wait_b), (uint32_t)t & 1);
         if (profiling) c2 = clock64();
+        const unsigned g = gbase + c;
         const int slot = g % SM::STAGES;
+        // The ring is filled in stream order but drained by four warps: this warp may get here while the slot still holds
+        // (or waits for) the chunk STAGES positions earlier, owned by another warp -- a parity wait would then alias
+        // "previous phase" with "this phase".  The producer publishes how many chunks it has issued; once ours is issued
+        // the slot's barrier is in OUR phase and the parity wait is exact.
+        if (issued_seen <= g) {
+          const long long tw = clock64();
+          unsigned spins = 0;
+          while ((issued_seen = *issued_s) <= g) {
+            if ((++spins & 255u) == 0) {
+              if (*s_abort) break;
+              if (ld_relaxed_s32(p.abort_flag) != 0) { *s_abort = 1; break; }
+              if (clock64() - tw > kWatchdogCycles) { atomicExch(p.abort_flag, 2); *s_abort = 1; break; }
+            }
+          }
+        }
         wait(bar(BAR_FULL + slot), (g / SM::STAGES) & 1);
         tc_fence_after();
         if (profiling) c3 = clock64();
@@ -191,20 +228,25 @@ __global__ void __launch_bounds__(NT, 1) wrnn_stream_kernel(const StreamParams p
           uint32_t base, sbo = SBO_H;
           switch (buf) {
             case B_COND: base = SM::OFF_COND + cur * SM::COND; sbo = SBO_Q; break;
-            case B_H1PREV: case B_Y1: base = cur ? SM::OFF_X1 : SM::OFF_X0; break;
             case B_H1NEW: base = cur ? SM::OFF_X0 : SM::OFF_X1; break;
             case B_H2: base = SM::OFF_H2; break;
-            default: base = SM::OFF_Y2; break;
+            default: base = cur ? SM::OFF_X1 : SM::OFF_X0; break;      // B_H1PREV, B_Y1, B_Y2
           }
-          return umma_desc(smem_u32(smem + base) + k0 * 16, 128, sbo);
+          return umma_desc(s0 + base + k0 * 16, 128, sbo);
         };
-        const uint64_t dA = umma_desc(smem_u32(smem + SM::OFF_RING + slot * CHUNK_BYTES), 128, nk * 256);
+        const uint64_t dA = umma_desc(ring0 + slot * CHUNK_BYTES, 128, nk * 256);
         const uint64_t dB = b_desc(b_buf);
         const uint32_t d_col = tmem + acc * NF;
-        for (uint32_t k = 0; k < nk; ++k) umma_f16(d_col, dA + (uint64_t)(k * 16), dB + (uint64_t)(k * 16), idesc, (k > 0 || !(flags & F_FIRST)) ? 1u : 0u);
+        if (nk == 4) {
+#pragma unroll
+          for (uint32_t k = 0; k < 4; ++k) umma_f16(d_col, dA + (uint64_t)(k * 16), dB + (uint64_t)(k * 16), idesc, (k > 0 || !(flags & F_FIRST)) ? 1u : 0u);
+        } else {
+          for (uint32_t k = 0; k < nk; ++k) umma_f16(d_col, dA + (uint64_t)(k * 16), dB + (uint64_t)(k * 16), idesc, (k > 0 || !(flags & F_FIRST)) ? 1u : 0u);
+        }
         if (b_buf2 != B_NONE) {
           const uint64_t dB2 = b_desc(b_buf2);
-          for (uint32_t k = 0; k < nk; ++k) umma_f16(d_col, dA + (uint64_t)(k * 16), dB2 + (uint64_t)(k * 16), idesc, 1u);
+#pragma unroll
+          for (uint32_t k = 0; k < 4; ++k) umma_f16(d_col, dA + (uint64_t)(k * 16), dB2 + (uint64_t)(k * 16), idesc, 1u);
         }
         umma_commit(bar(BAR_EMPTY + slot));
         if (commit) umma_commit(bar(BAR_ACC_FULL + commit - 1));
@@ -213,20 +255,20 @@ __global__ void __launch_bounds__(NT, 1) wrnn_stream_kernel(const StreamParams p
       }
     }
     if (profiling && lane == 0) { p.prof[0] = t_acc; p.prof[1] = t_b; p.prof[2] = t_ring; p.prof[3] = t_issue; }
-  } else if (warp < 4) {
+  } else if (warp == N_ISSUERS + 1) {
     // ====================================================================================================== staging
     // cond_s (fp32 rows of the per-sample conditioning stream, or built from frame-rate tensors) -> fp16 image of step s,
-    // one step ahead of the MMAs.  (fold, 8-column chunk) tasks, 64 threads.
-    const int st = tid - 64;
+    // one step ahead of the MMAs.  (fold, 8-column chunk) tasks, 32 threads.
+    const int st = lane;
     auto row0_of = [&](int f) -> long long {
       return p.fold_row0 ? __ldg(p.fold_row0 + f0 + f) : (long long)(f0 + f + (FRAMES ? p.seg_first : 0)) * p.seg_stride - p.row_base;
     };
     auto end_of = [&](int f) -> long long { return p.fold_row_end ? __ldg(p.fold_row_end + f0 + f) : p.L; };
-    constexpr int TASKS = (NF * KQ + 63) / 64;
+    constexpr int TASKS = (NF * KQ + 31) / 32;
     long long t_row0[TASKS], t_left[TASKS];
 #pragma unroll
     for (int j = 0; j < TASKS; ++j) {
-      const int task = st + j * 64, f = task / KQ;
+      const int task = st + j * 32, f = task / KQ;
       t_row0[j] = 0; t_left[j] = 0;
       if (task < NF * KQ && f < B) { t_row0[j] = row0_of(f); t_left[j] = end_of(f) - t_row0[j]; }
     }
@@ -236,7 +278,7 @@ __global__ void __launch_bounds__(NT, 1) wrnn_stream_kernel(const StreamParams p
       unsigned char* img = smem + SM::OFF_COND + par * SM::COND;
 #pragma unroll
       for (int j = 0; j < TASKS; ++j) {
-        const int task = st + j * 64;
+        const int task = st + j * 32;
         if (task >= NF * KQ) continue;
         const int f = task / KQ, c8 = task - f * KQ;
         float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
@@ -277,7 +319,8 @@ __global__ void __launch_bounds__(NT, 1) wrnn_stream_kernel(const StreamParams p
     float* st_h1 = p.state + ((size_t)tile * 2 + 0) * H * NF;
     float* st_h2 = p.state + ((size_t)tile * 2 + 1) * H * NF;
     unsigned full_par = 0;                                    // per block: parity of the accumulator-full waits so far
-    const bool profiling = p.prof != nullptr && blockIdx.x == 0 && tid == 128;
+    unsigned rows_known = p.uniforms_ready ? 0u : 0xffffffffu;   // rows of p.uniforms known to have landed (streamed draws)
+    const bool profiling = p.prof != nullptr && blockIdx.x == 0 && tid == EPI_TID0;
     long long t_wait = 0, t_work = 0;
     auto wait_full = [&](int blk) {
       long long c0 = 0;
@@ -301,7 +344,7 @@ __global__ void __launch_bounds__(NT, 1) wrnn_stream_kernel(const StreamParams p
     auto to_bits = [&](float v) -> uint16_t { return (uint16_t)(pack2<FMT>(v, 0.f) & 0xffffu); };
 
     volatile int* ep_stop = s_abort + 1;                      // the epilogue warps leave the loop together (named barrier inside)
-    if (tid == 128) *ep_stop = 0;
+    if (tid == EPI_TID0) *ep_stop = 0;
     named_bar_sync(1, 128);
     for (int t = 0; t < S; ++t) {
       const int cur = t & 1;
@@ -313,13 +356,14 @@ __global__ void __launch_bounds__(NT, 1) wrnn_stream_kernel(const StreamParams p
 #pragma unroll
       for (int i = 0; i < 11; ++i) ur[i] = 0.5f;
       const bool sampler = (warp & 3) == 0 && lane < B;
+      if (p.uniforms && (warp & 3) == 0 && (unsigned)t >= rows_known) rows_known = rows_wait(p.uniforms_ready, (unsigned)t + 1u, p.abort_flag);
       if (sampler) {
         const int gf = f0 + lane;
         if (p.uniforms) {
           const float* u = p.uniforms + (size_t)t * 11 * p.n_total;
 #pragma unroll
-          for (int i = 0; i < 10; ++i) ur[i] = __ldg(u + gf * 10 + i);
-          ur[10] = __ldg(u + 10 * p.n_total + gf);
+          for (int i = 0; i < 10; ++i) ur[i] = __ldcg(u + gf * 10 + i);
+          ur[10] = __ldcg(u + 10 * p.n_total + gf);
         } else {
           const unsigned gg = (unsigned)(p.seg_first + gf), k0 = (unsigned)p.seed, k1 = (unsigned)(p.seed >> 32), o0 = (unsigned)p.offset;
           const Philox4 r0 = philox4x32_10((unsigned)t, gg, 0u, o0, k0, k1), r1 = philox4x32_10((unsigned)t, gg, 1u, o0, k0, k1),
@@ -383,11 +427,9 @@ __global__ void __launch_bounds__(NT, 1) wrnn_stream_kernel(const StreamParams p
         publish_ready(cell ? W_H2NEW : W_H1NEW);
       }
 
-      // ---- P3 / P4: fc1, fc2 ------------------------------------------------------------------------------------
-#pragma unroll 1
-      for (int layer = 0; layer < 2; ++layer) {
-        const int qbase = 6 * H + layer * H;
-        const int off_out = layer ? SM::OFF_Y2 : off_y1;
+      // ---- P3: fc1 -> y1 into X[cur] (its readers, this step's W1h h1 MMAs, completed before P1's block-full) ------
+      {
+        const int qbase = 6 * H;
 #pragma unroll 1
         for (int b = 0; b < 4; ++b) {
           const int u = b * MROWS + row;
@@ -395,18 +437,59 @@ __global__ void __launch_bounds__(NT, 1) wrnn_stream_kernel(const StreamParams p
           wait_full(b);
 #pragma unroll
           for (int half = 0; half < NF / 16; ++half) {
-            float a[16];
-            tmem_ld16(tlane + (4 * b + layer) * NF + half * 16, a);
+            float a[16], a1[16], a2[16], a3[16];                // the four K-quarter partials (one per issuing warp)
+            tmem_ld16(tlane + (4 * b + 0) * NF + half * 16, a);
+            tmem_ld16(tlane + (4 * b + 1) * NF + half * 16, a1);
+            tmem_ld16(tlane + (4 * b + 2) * NF + half * 16, a2);
+            tmem_ld16(tlane + (4 * b + 3) * NF + half * 16, a3);
             tmem_ld_wait();
             if (half == NF / 16 - 1) release_acc(b);
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
               const int f = half * 16 + i;
-              *img_ptr(off_out, f, u) = to_bits(fmaxf(a[i] + qk_u + x_s[f] * vq_u, 0.f));
+              *img_ptr(off_y1, f, u) = to_bits(fmaxf(((a[i] + a1[i]) + (a2[i] + a3[i])) + qk_u + x_s[f] * vq_u, 0.f));
             }
           }
         }
-        publish_ready(layer ? W_Y2 : W_Y1);
+        publish_ready(W_Y1);
+      }
+      // ---- P4: fc2 -> y2.  y2 REPLACES y1 in X[cur], which the fc2 MMAs of the later blocks still read: the values are
+      // held in registers (packed pairs) until block 3's block-full, i.e. until every fc2 MMA of every issuing warp has
+      // completed (each warp's block-3 commit follows its chunks of blocks 0-2), and written then.  One image saved =
+      // two more ring slots for the weight stream.
+      {
+        const int qbase = 7 * H;
+        uint32_t ypk[4][NF / 2];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const float qk_u = __ldg(p.qk + qbase + b * MROWS + row);
+          wait_full(b);
+#pragma unroll
+          for (int half = 0; half < NF / 16; ++half) {
+            float a[16], a1[16], a2[16], a3[16];
+            tmem_ld16(tlane + (4 * b + 0) * NF + half * 16, a);
+            tmem_ld16(tlane + (4 * b + 1) * NF + half * 16, a1);
+            tmem_ld16(tlane + (4 * b + 2) * NF + half * 16, a2);
+            tmem_ld16(tlane + (4 * b + 3) * NF + half * 16, a3);
+            tmem_ld_wait();
+            if (half == NF / 16 - 1) release_acc(b);
+#pragma unroll
+            for (int i = 0; i < 16; i += 2) {
+              const float y0 = fmaxf(((a[i] + a1[i]) + (a2[i] + a3[i])) + qk_u, 0.f);
+              const float y1v = fmaxf(((a[i + 1] + a1[i + 1]) + (a2[i + 1] + a3[i + 1])) + qk_u, 0.f);
+              ypk[b][half * 8 + i / 2] = pack2<FMT>(y0, y1v);
+            }
+          }
+        }
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+#pragma unroll
+          for (int i = 0; i < NF / 2; ++i) {
+            *img_ptr(off_y1, 2 * i, b * MROWS + row) = (uint16_t)(ypk[b][i] & 0xffffu);
+            *img_ptr(off_y1, 2 * i + 1, b * MROWS + row) = (uint16_t)(ypk[b][i] >> 16);
+          }
+        }
+        publish_ready(W_Y2);
       }
 
       // ---- P5: logits -> transpose through shared memory -> one thread per fold samples ----------------------------
@@ -414,9 +497,14 @@ __global__ void __launch_bounds__(NT, 1) wrnn_stream_kernel(const StreamParams p
       if ((warp & 3) == 0) {
 #pragma unroll
         for (int half = 0; half < NF / 16; ++half) {
-          float a[16];
-          tmem_ld16(tlane + 2 * NF + half * 16, a);
+          float a[16], a1[16], a2[16], a3[16];
+          tmem_ld16(tlane + 0 * NF + half * 16, a);
+          tmem_ld16(tlane + 1 * NF + half * 16, a1);
+          tmem_ld16(tlane + 2 * NF + half * 16, a2);
+          tmem_ld16(tlane + 3 * NF + half * 16, a3);
           tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) a[i] = (a[i] + a1[i]) + (a2[i] + a3[i]);
           const float b3 = __ldg(p.b3 + row);
 #pragma unroll
           for (int i = 0; i < 16; ++i) log_s[(half * 16 + i) * SM::LOGP + lane] = a[i] + b3;   // [fold][class], class == lane
@@ -442,7 +530,7 @@ __global__ void __launch_bounds__(NT, 1) wrnn_stream_kernel(const StreamParams p
         __syncwarp();
         if (lane < NF) x_s[lane] = xnew;
       }
-      if (tid == 128) *ep_stop = *s_abort;
+      if (tid == EPI_TID0) *ep_stop = *s_abort;
       named_bar_sync(1, 128);                                  // x of this step (and the stop decision) visible to all epilogue threads
       if (profiling) t_work += clock64() - w0;
       if (*ep_stop) break;
@@ -462,7 +550,7 @@ class StreamEngine : public Engine {
  public:
   ~StreamEngine() override {
     cudaSetDevice(device);
-    cudaFree(d_blob_); cudaFree(d_prog_); cudaFree(d_vec_); cudaFree(d_state_); cudaFree(d_sync_);
+    cudaFree(d_blob_); cudaFree(d_prog_); cudaFree(d_mine_); cudaFree(d_vec_); cudaFree(d_state_); cudaFree(d_sync_);
   }
   const char* name() const override { return cfg.precision == WRNN_PREC_BF16 ? "tcgen05-stream-bf16" : "tcgen05-stream-fp16"; }
   int grid_ctas() const override { return last_grid_; }
@@ -480,6 +568,12 @@ class StreamEngine : public Engine {
     WRNN_CUDA_OK(cudaMemcpy(d_blob_, plan.blob.data(), plan.blob.size(), cudaMemcpyHostToDevice));
     WRNN_CUDA_OK(cudaMalloc(&d_prog_, plan.prog.size() * sizeof(Chunk)));
     WRNN_CUDA_OK(cudaMemcpy(d_prog_, plan.prog.data(), plan.prog.size() * sizeof(Chunk), cudaMemcpyHostToDevice));
+    {
+      std::vector<uint16_t> lists;
+      for (int o = 0; o < N_ISSUERS; ++o) { off_mine_[o] = lists.size(); n_mine_[o] = (int)plan.mine[o].size(); lists.insert(lists.end(), plan.mine[o].begin(), plan.mine[o].end()); }
+      WRNN_CUDA_OK(cudaMalloc(&d_mine_, lists.size() * sizeof(uint16_t)));
+      WRNN_CUDA_OK(cudaMemcpy(d_mine_, lists.data(), lists.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    }
     std::vector<float> vec;
     off_qk_ = 0; vec.insert(vec.end(), plan.qk.begin(), plan.qk.end());
     off_vq_ = vec.size(); vec.insert(vec.end(), plan.vq.begin(), plan.vq.end());
@@ -506,7 +600,8 @@ class StreamEngine : public Engine {
   int generate(const wrnn_job& job, cudaStream_t stream) override {
     WRNN_CUDA_OK(cudaSetDevice(device));
     // folds per CTA: 16 while that still gives every tile its own SM, else 32 (twice the folds per streamed byte)
-    const int nf = ((job.n_seg + 15) / 16 <= n_sm_) ? 16 : 32;
+    int nf = ((job.n_seg + 15) / 16 <= n_sm_) ? 16 : 32;
+    if (const char* e = getenv("WRNN_STREAM_NF")) { const int v = atoi(e); if (v == 16 || v == 32) nf = v; }   // experiments
     const int tiles = (job.n_seg + nf - 1) / nf;
     const size_t need = (size_t)tiles * 2 * H * nf * sizeof(float);
     if (need > state_bytes_) {
@@ -517,10 +612,11 @@ class StreamEngine : public Engine {
     StreamParams p{};
     const float* v = static_cast<const float*>(d_vec_);
     p.blob = static_cast<const unsigned char*>(d_blob_); p.prog = static_cast<const uint4*>(d_prog_); p.n_chunks = n_chunks_;
+    for (int o = 0; o < N_ISSUERS; ++o) { p.mine[o] = static_cast<const unsigned short*>(d_mine_) + off_mine_[o]; p.n_mine[o] = n_mine_[o]; }
     p.qk = v + off_qk_; p.vq = v + off_vq_; p.b1h = v + off_b1h_; p.b2h = v + off_b2h_; p.b3 = v + off_b3_;
     p.mels_up = job.mels_up; p.aux = job.aux; p.L = job.L; p.seg_stride = job.seg_stride; p.row_base = 0;
     p.n_total = job.n_seg; p.steps = job.steps > 0 ? job.steps : job.seg_len; p.out_pitch = p.steps; p.seg_first = job.seg_first;
-    p.uniforms = job.uniforms; p.seed = job.philox_seed; p.offset = job.philox_offset;
+    p.uniforms = job.uniforms; p.uniforms_ready = job.uniforms_ready; p.seed = job.philox_seed; p.offset = job.philox_offset;
     p.out = job.out; p.x_force = job.x_force; p.logits_out = job.logits_out;
     p.fold_row0 = reinterpret_cast<const long long*>(job.fold_row0); p.fold_row_end = reinterpret_cast<const long long*>(job.fold_row_end);
     p.mel_frames = job.mel_frames; p.aux_frames = job.aux_frames; p.up_taps = job.up_taps; p.hop = job.hop;
@@ -545,7 +641,7 @@ class StreamEngine : public Engine {
     if (getenv("WRNN_STREAM_PROF") && last_steps_ > 0) {
       long long prof[8]; std::memcpy(prof, buf + 64, sizeof(prof));
       const long long n = last_steps_;
-      fprintf(stderr, "[wrnn_stream prof] NF=%d tiles=%d steps=%d mma/step=%d chunks/step=%d | issuer: acc-wait=%lld operand-wait=%lld ring-wait=%lld "
+      fprintf(stderr, "[wrnn_stream prof] NF=%d tiles=%d steps=%d mma/step=%d chunks/step=%d | issuer 0: acc-wait=%lld operand-wait=%lld ring-wait=%lld "
               "issue=%lld | epilogue thread: mma-wait=%lld step=%lld (cycles per step)\n", last_nf_, last_grid_, last_steps_, n_mma_, n_chunks_,
               prof[0] / n, prof[1] / n, prof[2] / n, prof[3] / n, prof[4] / n, prof[5] / n);
     }
@@ -554,7 +650,8 @@ class StreamEngine : public Engine {
   }
 
  private:
-  void *d_blob_ = nullptr, *d_prog_ = nullptr, *d_vec_ = nullptr, *d_state_ = nullptr, *d_sync_ = nullptr;
+  void *d_blob_ = nullptr, *d_prog_ = nullptr, *d_mine_ = nullptr, *d_vec_ = nullptr, *d_state_ = nullptr, *d_sync_ = nullptr;
+  size_t off_mine_[N_ISSUERS] = {0, 0, 0, 0}; int n_mine_[N_ISSUERS] = {0, 0, 0, 0};
   size_t state_bytes_ = 0, off_qk_ = 0, off_vq_ = 0, off_b1h_ = 0, off_b2h_ = 0, off_b3_ = 0;
   int n_chunks_ = 0, n_mma_ = 0, n_sm_ = 0, last_grid_ = 0, last_steps_ = 0, last_nf_ = 0;
 };

@@ -36,28 +36,32 @@ constexpr int CHUNK_BYTES = MROWS * KCH * 2;   // 16 KB ring slot
 
 // B operand (activation image) selectors
 enum : uint8_t { B_COND = 0, B_H1PREV = 1, B_H1NEW = 2, B_H2 = 3, B_Y1 = 4, B_Y2 = 5, B_NONE = 0xff };
-// readiness barriers the issuer may have to wait for before a chunk
+// readiness barriers an issuer may have to wait for before a chunk
 enum : uint8_t { W_NONE = 0, W_COND = 1, W_H1NEW = 2, W_H2NEW = 3, W_Y1 = 4, W_Y2 = 5 };
 enum : uint8_t { F_FIRST = 1, F_COND_RELEASE = 2 };
+constexpr int N_ISSUERS = 4;        // issuing warps; every accumulator chain belongs to exactly one of them
+constexpr int N_PHASES = 5;
 
-struct Chunk {            // 16 bytes, read as one uint4 by the producer and the issuer warp
+struct Chunk {            // 16 bytes, read as one uint4
   uint32_t bytes;         // size of this chunk in the weight stream (chunks are consecutive): 128 rows x (16*nk) x 2 B
   uint8_t acc;            // accumulator index: TMEM column = acc * NF
   uint8_t nk;             // K = 16 steps in this chunk
   uint8_t b_buf;          // B operand image (B_*)
   uint8_t b_buf2;         // second B operand for the same weight chunk (fc1: h2'), B_NONE otherwise
   uint16_t k0;            // K offset of the chunk inside the B image (elements)
-  uint8_t flags;          // F_FIRST: first MMA of the accumulator in this phase overwrites; F_COND_RELEASE: last reader of cond
+  uint8_t flags;          // F_FIRST: first MMA of the accumulator in this phase overwrites; F_COND_RELEASE: this issuer's last cond read
   uint8_t wait_b;         // W_*: readiness barrier to wait for before issuing
-  uint8_t wait_acc;       // 0, or block + 1: wait until the epilogue of the previous phase has drained this block's accumulators
-  uint8_t commit;         // 0, or block + 1: after this chunk, signal "accumulators of block full" to the epilogue warps
-  uint16_t pad;
+  uint8_t wait_acc;       // 0, or block + 1: first chunk of this issuer in (phase, block): the previous phase's epilogue must have drained the block
+  uint8_t commit;         // 0, or block + 1: last chunk of this issuer in (phase, block): signal "my accumulators of the block are full"
+  uint8_t owner;          // issuing warp 0..3
+  uint8_t phase;          // 0..4 (P1..P5)
 };
 static_assert(sizeof(Chunk) == 16, "Chunk must stay one uint4");
 
 struct Plan {
-  std::vector<uint8_t> blob;      // the weight stream: chunk images back to back (fp16 / bf16 bits)
-  std::vector<Chunk> prog;        // one step of the program
+  std::vector<uint8_t> blob;      // the weight stream: chunk images back to back (fp16 / bf16 bits), in program order
+  std::vector<Chunk> prog;        // one step of the program, in stream order (what the producer walks)
+  std::vector<uint16_t> mine[N_ISSUERS];   // per issuing warp: indices into prog, ascending
   std::vector<float> qk, vq;      // [4096] conditioning-row constants, row order gi1 | gi2 | fc1 | fc2 (gate-major inside the GRUs)
   std::vector<float> b1h, b2h;    // [1536] gate-major
   std::vector<float> b3;          // [n_classes padded to 128]
@@ -69,36 +73,71 @@ struct Plan {
 inline size_t tile_index(int r, int k, int kc) { return (size_t)(r / 8) * (kc / 8) * 64 + (size_t)(k / 8) * 64 + (r % 8) * 8 + (k % 8); }
 
 // Builds the plan.  `bf` selects bf16 instead of fp16 operand bits.  n_classes <= 128 (MoL: 30).
+//
+// Ownership (one issuing warp per accumulator chain, four chains per unit block in every phase, so that the four warps
+// issue concurrently and "block full" always takes exactly four commits):
+//   GRU phases : warp 0 = r, 1 = z, 2 = in (input-side n), 3 = hn (hidden-side n)            accumulators 4b + q
+//   fc phases  : the K dimension is split in four: warp q owns conditioning K-chunk q and K = [128q, 128q + 128) of the
+//                recurrent operand, into its own partial accumulator 4b + q (the epilogue adds the four partials)
+// Stream order: the chains of one (phase, block) are interleaved round-robin, so consecutive ring slots go to different
+// warps; within P2 everything that does not depend on h1' is issued (for all blocks) before the W2x h1' chunks.
 inline void build_plan(const HostWeights& w, bool bf, Plan& p) {
   Folded f; fold(w, f);
   CtaSlice s; slice_for_cta(w, f, 0, H, s);          // P = 1: the dense matrices in the row order documented in wrnn_fold.h
   auto cvt = [&](double v) -> uint16_t { return bf ? f2bf((float)v) : f2h((float)v); };
   p.blob.clear(); p.prog.clear(); p.n_mma = 0;
+  for (auto& m : p.mine) m.clear();
   p.n_classes = w.n_classes;
   p.qk = s.qk; p.vq = s.vq; p.b1h = s.b1h; p.b2h = s.b2h;
   p.b3.assign(MROWS, 0.f);
   for (int r = 0; r < w.n_classes && r < MROWS; ++r) p.b3[r] = w.f3b[r];
 
-  // appends the chunks of rows [row0, row0 + 128) x columns [0, K) of a dense row-major [rows][K] matrix
-  auto emit = [&](const double* M, int K, int n_rows_valid, int row0, uint8_t acc, uint8_t b_buf, uint8_t b_buf2, bool& first,
-                  uint8_t wait_b, uint8_t& wait_acc) {
-    for (int k0 = 0; k0 < K; k0 += KCH) {
-      const int kc = (K - k0 < KCH) ? (K - k0) : KCH;              // 64, or the 16-wide tail of K = 208
-      const size_t base = p.blob.size();
-      p.blob.resize(base + (size_t)MROWS * kc * 2, 0);
-      uint16_t* img = reinterpret_cast<uint16_t*>(p.blob.data() + base);
+  struct Pending { Chunk c; std::vector<uint16_t> img; };
+  std::vector<Pending> q[N_ISSUERS];
+  bool fresh[N_ISSUERS] = {true, true, true, true};       // no chunk of this issuer yet in the current (phase, block)
+
+  // queues the chunks of rows [row0, row0 + 128) x columns [kbeg, kend) of a dense row-major [rows][K] matrix for `owner`
+  auto emit = [&](int owner, int phase, int blk, const double* M, int K, int n_rows_valid, int row0, int kbeg, int kend, uint8_t acc,
+                  uint8_t b_buf, uint8_t b_buf2, bool& first, uint8_t wait_b) {
+    for (int k0 = kbeg; k0 < kend; k0 += KCH) {
+      const int kc = (kend - k0 < KCH) ? (kend - k0) : KCH;        // 64, or the 16-wide tail of K = 208
+      Pending pd;
+      pd.img.assign((size_t)MROWS * kc, 0);
       for (int r = 0; r < MROWS; ++r) {
         if (row0 + r >= n_rows_valid) continue;                    // rows beyond the matrix stay zero (fc3: 30 of 128)
-        for (int k = 0; k < kc; ++k) img[tile_index(r, k, kc)] = cvt(M[(size_t)(row0 + r) * K + k0 + k]);
+        for (int k = 0; k < kc; ++k) pd.img[tile_index(r, k, kc)] = cvt(M[(size_t)(row0 + r) * K + k0 + k]);
       }
       Chunk c{};
       c.bytes = (uint32_t)(MROWS * kc * 2); c.acc = acc; c.nk = (uint8_t)(kc / 16); c.b_buf = b_buf; c.b_buf2 = b_buf2;
-      c.k0 = (uint16_t)k0; c.flags = first ? F_FIRST : 0; c.wait_b = wait_b; c.wait_acc = wait_acc; c.commit = 0;
-      first = false; wait_acc = 0;
-      p.prog.push_back(c);
+      c.k0 = (uint16_t)k0; c.flags = first ? F_FIRST : 0; c.wait_b = wait_b; c.wait_acc = fresh[owner] ? (uint8_t)(blk + 1) : 0;
+      c.commit = 0; c.owner = (uint8_t)owner; c.phase = (uint8_t)phase;
+      first = false; fresh[owner] = false;
+      pd.c = c;
+      q[owner].push_back(std::move(pd));
       p.n_mma += c.nk * (b_buf2 == B_NONE ? 1 : 2);
     }
   };
+  auto mark_commit = [&](int owner, int blk) { q[owner].back().c.commit = (uint8_t)(blk + 1); };
+  // appends the queued chunks to the stream, round-robin over the issuers
+  auto flush = [&]() {
+    size_t pos[N_ISSUERS] = {0, 0, 0, 0};
+    for (bool any = true; any;) {
+      any = false;
+      for (int o = 0; o < N_ISSUERS; ++o) {
+        if (pos[o] >= q[o].size()) continue;
+        any = true;
+        Pending& pd = q[o][pos[o]++];
+        p.mine[o].push_back((uint16_t)p.prog.size());
+        p.prog.push_back(pd.c);
+        const size_t base = p.blob.size();
+        p.blob.resize(base + pd.img.size() * 2);
+        std::memcpy(p.blob.data() + base, pd.img.data(), pd.img.size() * 2);
+      }
+    }
+    for (auto& v : q) v.clear();
+  };
+  auto new_block = [&]() { for (bool& b : fresh) b = true; };
+
   const double* Q = s.Q.data();         // [8H][CDIM]: gi1 (g*H+u) | gi2 (3H + g*H+u) | fc1 (6H+u) | fc2 (7H+u)
   const double* S1 = s.S1.data();       // [7H][H]: W2x (g*H+u) | W1h (3H + g*H+u) | F1x (6H+u)
   const double* S2 = s.S2.data();       // [4H][H]: F1x (u) | W2h (H + g*H+u)
@@ -108,61 +147,65 @@ inline void build_plan(const HostWeights& w, bool bf, Plan& p) {
   const int NB = H / MROWS;             // 4 unit blocks
   std::vector<double> F3((size_t)MROWS * H, 0.0);
   for (int r = 0; r < w.n_classes && r < MROWS; ++r) for (int k = 0; k < H; ++k) F3[(size_t)r * H + k] = w.f3w[(size_t)r * H + k];
+  const int QK[5] = {0, 64, 128, 192, CDIM};              // the four K-chunks of a conditioning row (64, 64, 64, 16)
 
-  // ---- P1: GRU1.  Accumulators of block b: 4b + {0: r, 1: z, 2: in, 3: hn}
+  // ---- P1: GRU1 (phase 0).  Accumulators of block b: 4b + {0: r, 1: z, 2: in, 3: hn}
   for (int b = 0; b < NB; ++b) {
-    uint8_t wacc = (uint8_t)(b + 1);                               // previous phase = P5 (block 0) / P4 of the step before
+    new_block();
     for (int g = 0; g < 2; ++g) {                                  // r, z: conditioning + recurrent part in one accumulator
       bool first = true;
-      emit(Q, CDIM, 8 * H, g * H + b * MROWS, (uint8_t)(4 * b + g), B_COND, B_NONE, first, W_COND, wacc);
-      emit(W1h, H, 3 * H, g * H + b * MROWS, (uint8_t)(4 * b + g), B_H1PREV, B_NONE, first, W_NONE, wacc);
+      emit(g, 0, b, Q, CDIM, 8 * H, g * H + b * MROWS, 0, CDIM, (uint8_t)(4 * b + g), B_COND, B_NONE, first, W_COND);
+      emit(g, 0, b, W1h, H, 3 * H, g * H + b * MROWS, 0, H, (uint8_t)(4 * b + g), B_H1PREV, B_NONE, first, W_NONE);
+      mark_commit(g, b);
     }
-    { bool first = true; emit(Q, CDIM, 8 * H, 2 * H + b * MROWS, (uint8_t)(4 * b + 2), B_COND, B_NONE, first, W_COND, wacc); }
-    { bool first = true; emit(W1h, H, 3 * H, 2 * H + b * MROWS, (uint8_t)(4 * b + 3), B_H1PREV, B_NONE, first, W_NONE, wacc); }
-    p.prog.back().commit = (uint8_t)(b + 1);
+    { bool first = true; emit(2, 0, b, Q, CDIM, 8 * H, 2 * H + b * MROWS, 0, CDIM, (uint8_t)(4 * b + 2), B_COND, B_NONE, first, W_COND); mark_commit(2, b); }
+    { bool first = true; emit(3, 0, b, W1h, H, 3 * H, 2 * H + b * MROWS, 0, H, (uint8_t)(4 * b + 3), B_H1PREV, B_NONE, first, W_NONE); mark_commit(3, b); }
+    flush();
   }
-  // ---- P2: GRU2.  First everything that does not need h1' (overlaps the P1 gate math), then W2x h1'.
+  // ---- P2: GRU2 (phase 1).  First everything that does not need h1' (overlaps the P1 gate math), then W2x h1'.
   for (int b = 0; b < NB; ++b) {
-    uint8_t wacc = (uint8_t)(b + 1);
+    new_block();
     for (int g = 0; g < 3; ++g) {
       bool first = true;
-      emit(Q, CDIM, 8 * H, 3 * H + g * H + b * MROWS, (uint8_t)(4 * b + g), B_COND, B_NONE, first, W_COND, wacc);
-      if (g < 2) emit(W2h, H, 3 * H, g * H + b * MROWS, (uint8_t)(4 * b + g), B_H2, B_NONE, first, W_NONE, wacc);
+      emit(g, 1, b, Q, CDIM, 8 * H, 3 * H + g * H + b * MROWS, 0, CDIM, (uint8_t)(4 * b + g), B_COND, B_NONE, first, W_COND);
+      if (g < 2) emit(g, 1, b, W2h, H, 3 * H, g * H + b * MROWS, 0, H, (uint8_t)(4 * b + g), B_H2, B_NONE, first, W_NONE);
     }
-    { bool first = true; emit(W2h, H, 3 * H, 2 * H + b * MROWS, (uint8_t)(4 * b + 3), B_H2, B_NONE, first, W_NONE, wacc); }
+    { bool first = true; emit(3, 1, b, W2h, H, 3 * H, 2 * H + b * MROWS, 0, H, (uint8_t)(4 * b + 3), B_H2, B_NONE, first, W_NONE); mark_commit(3, b); }
+    flush();
   }
   for (int b = 0; b < NB; ++b) {
-    uint8_t wacc = 0;
-    for (int g = 0; g < 3; ++g) { bool first = false; emit(W2x, H, 3 * H, g * H + b * MROWS, (uint8_t)(4 * b + g), B_H1NEW, B_NONE, first, W_H1NEW, wacc); }
-    p.prog.back().commit = (uint8_t)(b + 1);
+    for (bool& fr : fresh) fr = false;                             // the accumulators were opened by the independent part
+    for (int g = 0; g < 3; ++g) {
+      bool first = false;
+      emit(g, 1, b, W2x, H, 3 * H, g * H + b * MROWS, 0, H, (uint8_t)(4 * b + g), B_H1NEW, B_NONE, first, W_H1NEW);
+      mark_commit(g, b);
+    }
+    flush();
   }
-  // ---- P3: fc1 (accumulator 4b).  Conditioning rows of all blocks first, then F1x with both operands.
-  for (int b = 0; b < NB; ++b) {
-    uint8_t wacc = (uint8_t)(b + 1); bool first = true;
-    emit(Q, CDIM, 8 * H, 6 * H + b * MROWS, (uint8_t)(4 * b), B_COND, B_NONE, first, W_COND, wacc);
+  // ---- P3 / P4: fc1 (phase 2), fc2 (phase 3): K split over the four issuers, partial accumulators 4b + q
+  for (int layer = 0; layer < 2; ++layer) {
+    const double* F = layer ? F2x : F1x;
+    for (int b = 0; b < NB; ++b) {
+      new_block();
+      for (int o = 0; o < N_ISSUERS; ++o) {
+        bool first = true;
+        emit(o, 2 + layer, b, Q, CDIM, 8 * H, (6 + layer) * H + b * MROWS, QK[o], QK[o + 1], (uint8_t)(4 * b + o), B_COND, B_NONE, first, W_COND);
+        if (layer == 1 && b == NB - 1) q[o].back().c.flags |= F_COND_RELEASE;      // this issuer's last read of the step's conditioning
+        if (layer == 0) emit(o, 2, b, F, H, H, b * MROWS, 128 * o, 128 * o + 128, (uint8_t)(4 * b + o), B_H1NEW, B_H2, first, W_H2NEW);
+        else emit(o, 3, b, F, H, H, b * MROWS, 128 * o, 128 * o + 128, (uint8_t)(4 * b + o), B_Y1, B_NONE, first, W_Y1);
+        mark_commit(o, b);
+      }
+      flush();
+    }
   }
-  for (int b = 0; b < NB; ++b) {
-    uint8_t wacc = 0; bool first = false;
-    emit(F1x, H, H, b * MROWS, (uint8_t)(4 * b), B_H1NEW, B_H2, first, W_H2NEW, wacc);
-    p.prog.back().commit = (uint8_t)(b + 1);
+  // ---- P5: fc3 (phase 4): partial accumulators 0..3 of block 0
+  new_block();
+  for (int o = 0; o < N_ISSUERS; ++o) {
+    bool first = true;
+    emit(o, 4, 0, F3.data(), H, MROWS, 0, 128 * o, 128 * o + 128, (uint8_t)o, B_Y2, B_NONE, first, W_Y2);
+    mark_commit(o, 0);
   }
-  // ---- P4: fc2 (accumulator 4b + 1)
-  for (int b = 0; b < NB; ++b) {
-    uint8_t wacc = (uint8_t)(b + 1); bool first = true;
-    emit(Q, CDIM, 8 * H, 7 * H + b * MROWS, (uint8_t)(4 * b + 1), B_COND, B_NONE, first, W_COND, wacc);
-    if (b == NB - 1) p.prog.back().flags |= F_COND_RELEASE;       // last reader of this step's conditioning image
-  }
-  for (int b = 0; b < NB; ++b) {
-    uint8_t wacc = 0; bool first = false;
-    emit(F2x, H, H, b * MROWS, (uint8_t)(4 * b + 1), B_Y1, B_NONE, first, W_Y1, wacc);
-    p.prog.back().commit = (uint8_t)(b + 1);
-  }
-  // ---- P5: fc3 (accumulator 2, block 0's barriers)
-  {
-    uint8_t wacc = 1; bool first = true;
-    emit(F3.data(), H, MROWS, 0, 2, B_Y2, B_NONE, first, W_Y2, wacc);
-    p.prog.back().commit = 1;
-  }
+  flush();
 }
 
 }  // namespace stream

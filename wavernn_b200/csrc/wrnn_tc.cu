@@ -91,6 +91,7 @@ struct TcParams {
   int n_seg, steps, out_pitch, seg_first;   // n_seg = folds of THIS launch's tile (<= 64)
   int f0, n_total;                         // first fold of the tile / folds of the whole job (indexing of the job-wide arrays)
   const float* uniforms; const float* expo; unsigned long long seed, offset;   // expo: RAW head, [steps, n_total, 512]
+  const unsigned* uniforms_ready;   // optional: rows of `uniforms` uploaded so far (draws streamed in while the kernel runs)
   float* out; const float* x_force; float* logits_out;
   const long long* fold_row0; const long long* fold_row_end;   // optional per-fold conditioning windows (job-wide, [n_total])
   const float* mel_frames; const float* aux_frames; const float* up_taps; int hop;   // optional frame-rate conditioning
@@ -204,6 +205,7 @@ __global__ void __launch_bounds__(NT, 1) wrnn_tc_kernel(const TcParams p) {
     float h1[U] = {0.f, 0.f, 0.f, 0.f}, h2[U] = {0.f, 0.f, 0.f, 0.f};
     float x = 0.f;
     unsigned n_mma = 0;                                   // completed phases of bar_mma
+    unsigned rows_known = p.uniforms_ready ? 0u : 0xffffffffu;   // rows of p.uniforms known to have landed
 
     for (int t = 0; t < S; ++t) {
       const int par = t & 1;
@@ -231,13 +233,16 @@ __global__ void __launch_bounds__(NT, 1) wrnn_tc_kernel(const TcParams p) {
             ex[0] = -logf(u01(r.x)); ex[1] = -logf(u01(r.y)); ex[2] = -logf(u01(r.z)); ex[3] = -logf(u01(r.w));
           }
         }
-      } else if (owns_fold) {
-        if (p.uniforms) {
+      } else if (p.uniforms) {
+        if ((unsigned)t >= rows_known) rows_known = rows_wait(p.uniforms_ready, (unsigned)t + 1u, p.abort_flag);   // streamed draws
+        if (owns_fold) {                                   // L2 loads (.cg): rows may land while the kernel runs
           const float* u = p.uniforms + (size_t)t * 11 * p.n_total;
 #pragma unroll
-          for (int i = 0; i < 10; ++i) ur[i] = __ldg(u + (p.f0 + fold) * 10 + i);
-          ur[10] = __ldg(u + 10 * p.n_total + p.f0 + fold);
-        } else {
+          for (int i = 0; i < 10; ++i) ur[i] = __ldcg(u + (p.f0 + fold) * 10 + i);
+          ur[10] = __ldcg(u + 10 * p.n_total + p.f0 + fold);
+        }
+      } else if (owns_fold) {
+        {
           const unsigned g = (unsigned)(p.seg_first + p.f0 + fold), k0 = (unsigned)p.seed, k1 = (unsigned)(p.seed >> 32), o0 = (unsigned)p.offset;
           const Philox4 r0 = philox4x32_10((unsigned)t, g, 0u, o0, k0, k1), r1 = philox4x32_10((unsigned)t, g, 1u, o0, k0, k1),
                         r2 = philox4x32_10((unsigned)t, g, 2u, o0, k0, k1);
@@ -681,6 +686,7 @@ class TcEngine : public Engine {
     p.n_seg = job.n_seg; p.steps = job.steps > 0 ? job.steps : job.seg_len; p.out_pitch = p.steps;
     p.seg_first = job.seg_first;
     p.uniforms = job.uniforms; p.expo = job.expo; p.seed = job.philox_seed; p.offset = job.philox_offset;
+    p.uniforms_ready = job.uniforms_ready;
     p.out = job.out; p.x_force = job.x_force; p.logits_out = job.logits_out;
     p.fold_row0 = reinterpret_cast<const long long*>(job.fold_row0); p.fold_row_end = reinterpret_cast<const long long*>(job.fold_row_end);
     p.mel_frames = job.mel_frames; p.aux_frames = job.aux_frames; p.up_taps = job.up_taps; p.hop = job.hop;

@@ -125,6 +125,20 @@ __device__ __forceinline__ void counter_wait(const unsigned* ctr, unsigned targe
   }
 }
 
+// Streamed draws (wrnn_job::uniforms_ready): returns the number of valid rows once it exceeds `need - 1`
+// (0xffffffff if the job is being abandoned, so the caller stops asking).
+__device__ __forceinline__ unsigned rows_wait(const unsigned* ready, unsigned need, int* abort_flag) {
+  unsigned v = ld_acquire_u32(ready);
+  if (v >= need) return v;
+  const long long t0 = clock64();
+  while ((v = ld_acquire_u32(ready)) < need) {
+    if (ld_relaxed_s32(abort_flag) != 0) return 0xffffffffu;
+    if (clock64() - t0 > kWatchdogCycles) { atomicExch(abort_flag, 1); return 0xffffffffu; }
+    __nanosleep(200);
+  }
+  return v;
+}
+
 template <int FMT> __device__ __forceinline__ uint32_t pack2(float a, float b);
 template <> __device__ __forceinline__ uint32_t pack2<0>(float a, float b) {      // fp16, RNE, saturating
   uint32_t r;

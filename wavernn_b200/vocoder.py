@@ -151,6 +151,9 @@ class WaveRNN(nn.Module):
         self.gen_philox_seed = 0
         self.gen_native_rng = True      # replay torch's CPU generator natively (self-checked; False = torch operators)
         self.gen_max_draw_bytes = 16 << 30   # bound on the host tensor of reference-compatible RAW draws (see _reference_draws)
+        self.gen_stream_draws = True    # MoL parity mode: replay + upload the draws in step chunks WHILE the kernel runs
+        self.gen_draw_chunk = 1024      # steps per chunk
+        self._copy_stream = None
         self._draw_buf = None
         self.gen_upsample_chunk = 2048  # mel frames per UpsampleNetwork call (bounds HBM intermediates)
         self.gen_epilogue = 'device'      # 'device': wrnn_epilogue (xfade / overlap-add / fade-out in one pass) | 'host': numpy
@@ -330,6 +333,49 @@ class WaveRNN(nn.Module):
             e[t] = row[f0:f0 + nl]
         return None, e
 
+    def _can_stream_draws(self, steps: int, x_force, draws) -> bool:
+        """MoL parity draws can be replayed and uploaded while the kernel runs (wrnn_job::uniforms_ready) when they come
+        from the native replay and a tensor-core engine consumes them."""
+        return (bool(self.gen_stream_draws) and self.gen_rng == 'torch' and draws is None and x_force is None and self.mode == 'MOL'
+                and self.gen_precision != 'fp32' and self.gen_engine != 'simt' and steps > 2 * int(self.gen_draw_chunk)
+                and bool(self.gen_native_rng) and cabi.is_built() and cabi.torch_rng_replay_ok())
+
+    def _streamed_draws(self, geo: FoldGeometry, steps: int, shard, device, launch):
+        """The reference's draws (two discarded nn.GRUCell initialisations, then `steps` rows of 11*B uniforms; same
+        generator consumption as _reference_draws) replayed natively in chunks of `gen_draw_chunk` steps.  Chunk 0 is
+        uploaded, then `launch(uniforms_ptr, ready_ptr)` enqueues the kernel, then the remaining chunks are replayed and
+        uploaded on a side stream while it runs; after every chunk a 4-byte copy on that stream bumps the device counter
+        the kernel checks before it reads a row.  Host replay time (9 ms on an 8-rank job) leaves the critical path."""
+        B, f0, nl = geo.n_seg, shard.seg_first, shard.n_seg
+        skip = sum(3 * g.hidden_size * (g.input_size + g.hidden_size + 2) for g in (self.rnn1, self.rnn2))
+        cols = ((10 * f0, 10 * (f0 + nl)), (10 * B + f0, 10 * B + f0 + nl)) if nl < B else None
+        width = 11 * nl
+        chunk = int(self.gen_draw_chunk)
+        bounds = list(range(0, steps, chunk)) + [steps]
+        n_keep = steps * width
+        if self._draw_buf is None or self._draw_buf.numel() < n_keep:
+            self._draw_buf = torch.empty(n_keep, dtype=torch.float32, pin_memory=True)
+        host = self._draw_buf
+        marks = torch.tensor(bounds[1:], dtype=torch.int32).pin_memory()
+        main = torch.cuda.current_stream(device)
+        if self._copy_stream is None or self._copy_stream.device != device:
+            self._copy_stream = torch.cuda.Stream(device)
+        side = self._copy_stream
+        dev = torch.empty(n_keep, dtype=torch.float32, device=device)
+        ready = torch.zeros(1, dtype=torch.int32, device=device)
+        dev.record_stream(side); ready.record_stream(side)
+        side.wait_stream(main)                                   # the counter is zero before the first bump
+        for i in range(len(bounds) - 1):
+            r0, r1 = bounds[i], bounds[i + 1]
+            piece = host[r0 * width:r1 * width]
+            cabi.torch_rng_uniform(skip if i == 0 else 0, (r1 - r0) * 11 * B, 1e-5, 1.0 - 1e-5, out=piece, row_len=11 * B, cols=cols)
+            with torch.cuda.stream(side):
+                dev[r0 * width:r1 * width].copy_(piece, non_blocking=True)
+                ready.copy_(marks[i:i + 1], non_blocking=True)
+            if i == 0:
+                launch(dev.data_ptr(), ready.data_ptr())
+        return dev, ready, side
+
     # ------------------------------------------------------------------ the hot path
     def generate(self, mels, save_path: Union[str, Path, None], batched, target, overlap, mu_law):
         """Same contract as reference :169-264: returns the float64 waveform of length
@@ -387,7 +433,10 @@ class WaveRNN(nn.Module):
             mel_fr = mels_padded[0].transpose(0, 1).contiguous().float()                  # (T + 2 pad, feat)
             aux_fr = self.upsample.resnet(mels_padded)[0].transpose(0, 1).contiguous().float()   # (T, 4*aux)
             taps = self.upsample_taps(device)
-        if self.gen_rng == 'torch' or draws is not None:
+        stream_draws = frames and self._can_stream_draws(S, x_force, draws)
+        if stream_draws:
+            pass                                   # drawn, uploaded and consumed concurrently: see _streamed_draws below
+        elif self.gen_rng == 'torch' or draws is not None:
             u_all, e_all = draws if draws is not None else self._reference_draws(geo, S, reuse_buffer=True, shard=shard)
             f0, n = shard.seg_first, shard.n_seg
             B = geo.n_seg
@@ -408,13 +457,19 @@ class WaveRNN(nn.Module):
             # frame-rate conditioning: the library forms every (T*hop, 208) row itself from the padded mel, the
             # MelResNet frames and the 5-tap interpolation table (an HBM-rate pre-pass per 64-fold tile, or inside the
             # persistent kernel -- cabi.COND_*); torch never materialises anything of size T*hop
-            engine.generate(mels_up=0, aux=0, L=T * self.hop_length, n_seg=shard.n_seg, seg_len=geo.seg_len,
-                            seg_stride=geo.seg_stride, out=out.data_ptr(), seg_first=shard.seg_first, steps=steps,
-                            uniforms=uniforms.data_ptr() if uniforms is not None else 0,
-                            expo=expo.data_ptr() if expo is not None else 0,
-                            philox_seed=int(self.gen_philox_seed), mel_frames=mel_fr.data_ptr(),
-                            aux_frames=aux_fr.data_ptr(), up_taps=taps.data_ptr(), hop=self.hop_length,
-                            cond_mode=int(self.gen_cond_mode), stream=torch.cuda.current_stream(device).cuda_stream)
+            def launch(uni_ptr, ready_ptr):
+                engine.generate(mels_up=0, aux=0, L=T * self.hop_length, n_seg=shard.n_seg, seg_len=geo.seg_len,
+                                seg_stride=geo.seg_stride, out=out.data_ptr(), seg_first=shard.seg_first, steps=steps,
+                                uniforms=uni_ptr, expo=expo.data_ptr() if expo is not None else 0,
+                                philox_seed=int(self.gen_philox_seed), mel_frames=mel_fr.data_ptr(),
+                                aux_frames=aux_fr.data_ptr(), up_taps=taps.data_ptr(), hop=self.hop_length,
+                                cond_mode=int(self.gen_cond_mode), uniforms_ready=ready_ptr,
+                                stream=torch.cuda.current_stream(device).cuda_stream)
+            if stream_draws:
+                keep = self._streamed_draws(geo, S, shard, device, launch)
+                keep[2].synchronize()
+            else:
+                launch(uniforms.data_ptr() if uniforms is not None else 0, 0)
             torch.cuda.current_stream(device).synchronize()
             engine.check()
             self.gen_stats.update(engine=engine.name, grid_ctas=engine.grid_ctas, launches=engine.launch_count,
