@@ -19,7 +19,7 @@ H, CDIM, NB = 512, 208, 4
 B_COND, B_H1PREV, B_H1NEW, B_H2, B_Y1, B_Y2, B_NONE = 0, 1, 2, 3, 4, 5, 0xFF
 W_NONE, W_COND, W_H1NEW, W_H2NEW, W_Y1, W_Y2 = range(6)
 
-CHUNK = np.dtype([("bytes", "<u4"), ("acc", "u1"), ("nk", "u1"), ("b_buf", "u1"), ("b_buf2", "u1"), ("k0", "<u2"),
+CHUNK = np.dtype([("size16", "<u2"), ("a_off16", "<u2"), ("acc", "u1"), ("nk", "u1"), ("b_buf", "u1"), ("b_buf2", "u1"), ("k0", "<u2"),
                   ("flags", "u1"), ("wait_b", "u1"), ("wait_acc", "u1"), ("commit", "u1"), ("owner", "u1"), ("phase", "u1")])
 
 
@@ -47,6 +47,7 @@ def get_plan(sd, precision="fp16"):
     assert sorted(np.concatenate(lists).tolist()) == list(range(nc.value))
     for o, l in enumerate(lists):
         assert np.all(np.diff(l) > 0) and np.all(prog["owner"][l] == o)
+    assert nc.value % 2 == 0 and np.all(prog["owner"][0::2] == prog["owner"][1::2])     # a pair travels to ONE issuing warp
     v = dict(qk=vec[:4096], vq=vec[4096:8192], b1h=vec[8192:9728], b2h=vec[9728:11264], b3=vec[11264:])
     return blob, prog, v
 
@@ -80,7 +81,10 @@ def interpret(blob, prog, v, m_up, aux, U, *, n_seg, seg_len, seg_stride, steps,
     x = np.zeros(NF, np.float32)
     acc = np.zeros((16, 128, NF), np.float32)
     out = np.zeros((NF, steps), np.float32); logits = np.zeros((steps, NF, 30), np.float32)
-    offs = np.concatenate([[0], np.cumsum(prog["bytes"].astype(np.int64))])
+    nbytes = prog["size16"].astype(np.int64) * 16
+    offs = np.concatenate([[0], np.cumsum(nbytes)])
+    # chunks travel in pairs: the second one lands right behind the first inside the 32 KB ring slot
+    assert len(prog) % 2 == 0 and np.all(prog["a_off16"][0::2] == 0) and np.all(prog["a_off16"][1::2] == prog["size16"][0::2])
     assert offs[-1] == blob.size
     tiles = [decode_tile(blob[offs[i]:offs[i + 1]], int(c["nk"]) * 16, precision) for i, c in enumerate(prog)]
     for t in range(steps):
@@ -186,7 +190,7 @@ def test_stream_plan_interpreted_on_the_cpu_equals_the_engine_contract(precision
     # structure: the whole weight set once per step, one 16-byte record per chunk
     assert blob.size == 2 * (4096 * 208 + (3 * 1536 + 2 * 512 + 128) * 512)
     assert int((prog["nk"].astype(int) * np.where(prog["b_buf2"] == B_NONE, 1, 2)).sum()) == 32 * 13 + 36 * 32 + 4 * 64 + 4 * 32 + 32
-    assert set(np.unique(prog["bytes"])) == {4096, 16384} and prog["acc"].max() <= 15
+    assert set(np.unique(prog["size16"])) == {256, 1024} and prog["acc"].max() <= 15
     rs = np.random.RandomState(1)
     n_seg, seg_len, stride = 16, 40, 25
     L = (n_seg - 1) * stride + 30                                  # the last folds run past the end of the stream

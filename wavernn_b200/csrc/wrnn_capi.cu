@@ -99,10 +99,10 @@ int wrnn_create(wrnn_t** out, const wrnn_cfg* cfg, const wrnn_weights* w, int de
 }
 
 // Folds from which ENGINE_AUTO hands a job to the stream engine: the persistent engine serves tiles of 64 folds one
-// after the other at ~15.5 us per step each, the stream engine serves all folds at once at ~one weight pass per step
-// (profiles/r02_stream.md), so it wins from a few tiles on.  WRNN_STREAM_MIN_FOLDS overrides (experiments).
+// after the other at 15.5 us per step each, the stream engine serves up to 148 tiles of 16 folds at once at ~66 us per step
+// (profiles/r02_stream.md): break-even at 4.3 tiles = 272 folds.  WRNN_STREAM_MIN_FOLDS overrides (experiments).
 static int stream_min_folds() {
-  static const int v = [] { const char* e = getenv("WRNN_STREAM_MIN_FOLDS"); return e ? atoi(e) : 192; }();
+  static const int v = [] { const char* e = getenv("WRNN_STREAM_MIN_FOLDS"); return e ? atoi(e) : 288; }();
   return v;
 }
 

@@ -48,7 +48,7 @@ constexpr int SBO_Q = KQ * 128;              // 3328: stride between 8-fold grou
 constexpr int SBO_H = (H / 8) * 128;         // 8192: same for the K = 512 images
 constexpr int TMEM_COLS = 512;
 constexpr int NBAR = 40;
-constexpr int MAX_STAGES = 12;
+constexpr int MAX_STAGES = 6;               // ring slots of PAIR_BYTES (two chunks each)
 
 template <int NF> struct Smem {
   static constexpr int GROUPS = NF / 8;
@@ -61,8 +61,8 @@ template <int NF> struct Smem {
   static constexpr int OFF_RING = (OFF_COND + 2 * COND + 1023) / 1024 * 1024;
   static constexpr int LOGP = 33;                                            // padded row of the logits transpose (conflict-free both ways)
   static constexpr int MISC = LOGP * NF * 4 + NF * 4 + NBAR * 8 + 64;        // logits transpose, x, barriers, tmem slot
-  static constexpr int STAGES = (227 * 1024 - OFF_RING - MISC) / CHUNK_BYTES > MAX_STAGES ? MAX_STAGES : (227 * 1024 - OFF_RING - MISC) / CHUNK_BYTES;
-  static constexpr int OFF_LOG = OFF_RING + STAGES * CHUNK_BYTES;            // [NF][LOGP] fp32
+  static constexpr int STAGES = (227 * 1024 - OFF_RING - MISC) / PAIR_BYTES > MAX_STAGES ? MAX_STAGES : (227 * 1024 - OFF_RING - MISC) / PAIR_BYTES;
+  static constexpr int OFF_LOG = OFF_RING + STAGES * PAIR_BYTES;             // [NF][LOGP] fp32
   static constexpr int OFF_XS = OFF_LOG + LOGP * NF * 4;                       // [NF] fp32: previous sample per fold
   static constexpr int OFF_BAR = OFF_XS + NF * 4;
   static constexpr int BYTES = OFF_BAR + NBAR * 8 + 64;
@@ -75,8 +75,8 @@ constexpr int BAR_FULL = 0, BAR_EMPTY = MAX_STAGES, BAR_ACC_FULL = 2 * MAX_STAGE
 static_assert(BAR_COND_FREE + 2 <= NBAR, "barrier table");
 
 struct StreamParams {
-  const unsigned char* blob; const uint4* prog; int n_chunks;
-  const unsigned short* mine[N_ISSUERS]; int n_mine[N_ISSUERS];     // per issuing warp: its chunk indices, ascending
+  const unsigned char* blob; const unsigned short* pair_size16; int n_pairs;    // the weight stream and the TMA size (>> 4) of each chunk pair
+  const uint4* mine[N_ISSUERS]; int n_mine[N_ISSUERS];              // per issuing warp: its DevChunk records (pairs adjacent)
   const float* qk; const float* vq; const float* b1h; const float* b2h; const float* b3;
   const float* mels_up; const float* aux; long long L; long long seg_stride; long long row_base;
   int n_total, steps, out_pitch, seg_first;
@@ -89,14 +89,14 @@ struct StreamParams {
   long long* prof;              // optional cycle counters of CTA 0
 };
 
-template <int NF, int FMT, bool FRAMES>
+template <int NF, int FMT, bool FRAMES, bool PROF>
 __global__ void __launch_bounds__(NT, 1) wrnn_stream_kernel(const StreamParams p) {
   using SM = Smem<NF>;
   extern __shared__ __align__(1024) unsigned char smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM::OFF_BAR);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM::OFF_BAR + NBAR * 8);
   volatile int* s_abort = reinterpret_cast<volatile int*>(smem + SM::OFF_BAR + NBAR * 8 + 16);   // CTA-local copy of the abort flag
-  volatile unsigned* issued_s = reinterpret_cast<volatile unsigned*>(smem + SM::OFF_BAR + NBAR * 8 + 32);   // chunks the producer has issued
+  volatile unsigned* issued_s = reinterpret_cast<volatile unsigned*>(smem + SM::OFF_BAR + NBAR * 8 + 32);   // chunk PAIRS the producer has issued
   float* x_s = reinterpret_cast<float*>(smem + SM::OFF_XS);
   float* log_s = reinterpret_cast<float*>(smem + SM::OFF_LOG);
   auto bar = [&](int i) -> uint32_t { return smem_u32(&bars[i]); };
@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(NT, 1) wrnn_stream_kernel(const StreamParams p
   if (tid == 0) {
     for (int i = 0; i < SM::STAGES; ++i) {
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar(BAR_FULL + i)));
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar(BAR_EMPTY + i)));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar(BAR_EMPTY + i)));            // one commit by the pair's issuer
     }
     for (int i = 0; i < 4; ++i) {
       asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar(BAR_ACC_FULL + i)), "n"(N_ISSUERS));   // one commit per issuing warp
@@ -156,14 +156,17 @@ __global__ void __launch_bounds__(NT, 1) wrnn_stream_kernel(const StreamParams p
 
   if (warp == 0) {
     // ===================================================================================================== producer
-    unsigned g = 0;                                           // chunks issued so far (ring position)
+    // one TMA (and one full / empty barrier) per PAIR of consecutive chunks
+    unsigned g = 0;                                           // pairs issued so far (ring position)
     for (int t = 0; t < S && !*s_abort; ++t) {
       size_t off = 0;
-      for (int c = 0; c < p.n_chunks; ++c, ++g) {
-        const uint32_t bytes = __ldg(reinterpret_cast<const uint32_t*>(p.prog + c));
+      uint32_t sz = __ldg(p.pair_size16);
+      for (int c = 0; c < p.n_pairs; ++c, ++g) {
+        const uint32_t bytes = sz * 16u;
+        if (c + 1 < p.n_pairs) sz = __ldg(p.pair_size16 + c + 1);
         const int slot = g % SM::STAGES;
-        wait(bar(BAR_EMPTY + slot), ((g / SM::STAGES) & 1) ^ 1);      // slot drained by the MMAs
-        tma_bulk_g2s(smem_u32(smem + SM::OFF_RING + slot * CHUNK_BYTES), p.blob + off, bytes, bar(BAR_FULL + slot));
+        wait(bar(BAR_EMPTY + slot), ((g / SM::STAGES) & 1) ^ 1);      // slot drained by the MMAs of both chunks
+        tma_bulk_g2s(smem_u32(smem + SM::OFF_RING + slot * PAIR_BYTES), p.blob + off, bytes, bar(BAR_FULL + slot));
         __syncwarp();
         if (lane == 0) *issued_s = g + 1;                      // see the issuers: parity waits need "this phase is armed"
         off += bytes;
@@ -171,87 +174,99 @@ __global__ void __launch_bounds__(NT, 1) wrnn_stream_kernel(const StreamParams p
     }
   } else if (warp <= N_ISSUERS) {
     // ====================================================================================================== issuers
+    // Lean by construction: the records are pre-digested (wrnn_stream_plan.h::DevChunk), a pair of chunks (eight MMAs)
+    // costs one ring hand-shake, and the four MMAs of a chunk go out under one elect.  (First multi-warp version: ~1800
+    // cycles per chunk, two thirds of it plain instruction issue -- ncu source view, profiles/r02_stream.md.)
     const int q = warp - 1;
     const uint32_t idesc = umma_idesc(MROWS, NF, FMT);
-    const unsigned short* my = p.mine[q];
+    const uint4* my = p.mine[q];
     const int n_my = p.n_mine[q];
-    const bool profiling = p.prof != nullptr && blockIdx.x == 0 && q == 0;
+    const bool profiling = PROF && blockIdx.x == 0 && q == 0;
     long long t_ring = 0, t_b = 0, t_acc = 0, t_issue = 0;
-    const uint32_t ring0 = smem_u32(smem + SM::OFF_RING), s0 = smem_u32(smem);
+    constexpr uint32_t LBO = (128u >> 4) << 16, VER = 1u << 14;       // descriptor: LBO field (low word), version bit (high word)
+    constexpr uint32_t HI_A4 = (1024u >> 4) | VER, HI_A1 = (256u >> 4) | VER, HI_BH = ((uint32_t)SBO_H >> 4) | VER, HI_BQ = ((uint32_t)SBO_Q >> 4) | VER;
+    const uint32_t s0_lo = smem_u32(smem) >> 4, ring_lo = smem_u32(smem + SM::OFF_RING) >> 4;
     unsigned issued_seen = 0;
+    // four (or one) MMAs of one chunk: D[tmem] (+)= A[ring] * B[image]^T, K advancing by 16 (+16 in the address field)
+    auto mma4 = [&](uint32_t d_col, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t acc_first, bool one) {
+      if (one) {
+        asm volatile("{\n\t.reg .pred e, p;\n\t.reg .b64 da, db;\n\t"
+                     "elect.sync _|e, 0xffffffff;\n\tsetp.ne.b32 p, %6, 0;\n\t"
+                     "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+                     "@e tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}\n"
+                     :: "r"(d_col), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(acc_first) : "memory");
+      } else {
+        asm volatile("{\n\t.reg .pred e, p, pt;\n\t.reg .b64 da, db;\n\t.reg .b32 al, bl;\n\t"
+                     "elect.sync _|e, 0xffffffff;\n\tsetp.ne.b32 p, %6, 0;\n\tsetp.eq.b32 pt, %6, %6;\n\t"
+                     "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+                     "@e tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
+                     "add.u32 al, %1, 16;\n\tadd.u32 bl, %3, 16;\n\tmov.b64 da, {al, %2};\n\tmov.b64 db, {bl, %4};\n\t"
+                     "@e tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, pt;\n\t"
+                     "add.u32 al, %1, 32;\n\tadd.u32 bl, %3, 32;\n\tmov.b64 da, {al, %2};\n\tmov.b64 db, {bl, %4};\n\t"
+                     "@e tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, pt;\n\t"
+                     "add.u32 al, %1, 48;\n\tadd.u32 bl, %3, 48;\n\tmov.b64 da, {al, %2};\n\tmov.b64 db, {bl, %4};\n\t"
+                     "@e tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, pt;\n\t}\n"
+                     :: "r"(d_col), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(acc_first) : "memory");
+      }
+    };
     for (int t = 0; t < S && !*s_abort; ++t) {
       const int cur = t & 1;
-      const unsigned gbase = (unsigned)t * (unsigned)p.n_chunks;       // ring position of this step's chunk 0
-      uint4 raw = __ldg(p.prog + __ldg(my));
-      for (int i = 0; i < n_my; ++i) {
-        const unsigned c = __ldg(my + i);
-        const uint4 cur_raw = raw;
-        if (i + 1 < n_my) raw = __ldg(p.prog + __ldg(my + i + 1));     // next record: its latency hides under this chunk
-        const uint32_t acc = cur_raw.y & 0xff, nk = (cur_raw.y >> 8) & 0xff, b_buf = (cur_raw.y >> 16) & 0xff, b_buf2 = cur_raw.y >> 24;
-        const uint32_t k0 = cur_raw.z & 0xffff, flags = (cur_raw.z >> 16) & 0xff, wait_b = cur_raw.z >> 24;
-        const uint32_t wait_acc = cur_raw.w & 0xff, commit = (cur_raw.w >> 8) & 0xff, phase = cur_raw.w >> 24;
-        long long c0 = 0, c1 = 0, c2 = 0, c3 = 0;
-        if (profiling) c0 = clock64();
-        if (wait_acc) {
-          // the epilogue of the previous (phase, block) use must have drained the block: its arrivals on acc_empty[blk] are
-          // numbered A*t + phase (A = 5 for block 0, which also serves fc3; 4 otherwise); we need number A*t + phase - 1
-          const int blk = wait_acc - 1;
-          const int idx = (blk == 0 ? N_PHASES : N_PHASES - 1) * t + (int)phase - 1;
-          if (idx >= 0) wait(bar(BAR_ACC_EMPTY + blk), (uint32_t)idx & 1u);
-        }
-        if (profiling) c1 = clock64();
-        if (wait_b == W_COND) wait(bar(BAR_READY + cur), (uint32_t)(t >> 1) & 1);
-        else if (wait_b != W_NONE) wait(bar(BAR_READY + wait_b), (uint32_t)t & 1);
-        if (profiling) c2 = clock64();
-        const unsigned g = gbase + c;
+      const unsigned gbase = (unsigned)t * (unsigned)p.n_pairs;         // ring position of this step's pair 0
+      uint4 nx0 = __ldg(my), nx1 = __ldg(my + 1);
+      for (int i = 0; i < n_my; i += 2) {
+        const uint4 rec[2] = {nx0, nx1};
+        if (i + 2 < n_my) { nx0 = __ldg(my + i + 2); nx1 = __ldg(my + i + 3); }      // next pair's records: plain sequential loads
+        const unsigned g = gbase + (rec[0].w >> 16);
         const int slot = g % SM::STAGES;
-        // The ring is filled in stream order but drained by four warps: this warp may get here while the slot still holds
-        // (or waits for) the chunk STAGES positions earlier, owned by another warp -- a parity wait would then alias
-        // "previous phase" with "this phase".  The producer publishes how many chunks it has issued; once ours is issued
-        // the slot's barrier is in OUR phase and the parity wait is exact.
-        if (issued_seen <= g) {
-          const long long tw = clock64();
-          unsigned spins = 0;
-          while ((issued_seen = *issued_s) <= g) {
-            if ((++spins & 255u) == 0) {
-              if (*s_abort) break;
-              if (ld_relaxed_s32(p.abort_flag) != 0) { *s_abort = 1; break; }
-              if (clock64() - tw > kWatchdogCycles) { atomicExch(p.abort_flag, 2); *s_abort = 1; break; }
+        const uint32_t slot_lo = ring_lo + (uint32_t)slot * (PAIR_BYTES >> 4);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const uint4 r = rec[j];
+          const uint32_t flags = r.z >> 24, acc = (r.z >> 16) & 0xf, phase = (r.z >> 20) & 0xf;
+          const uint32_t wait_b = r.w & 7u, wait_acc = (r.w >> 3) & 7u, commit = (r.w >> 6) & 7u;
+          long long c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+          if (profiling) c0 = clock64();
+          if (wait_acc) {
+            // the epilogue of the previous (phase, block) use must have drained the block: its arrivals on acc_empty[blk] are
+            // numbered A*t + phase (A = 5 for block 0, which also serves fc3; 4 otherwise); we need number A*t + phase - 1
+            const int blk = wait_acc - 1;
+            const int idx = (blk == 0 ? N_PHASES : N_PHASES - 1) * t + (int)phase - 1;
+            if (idx >= 0) wait(bar(BAR_ACC_EMPTY + blk), (uint32_t)idx & 1u);
+          }
+          if (profiling) c1 = clock64();
+          if (wait_b == W_COND) wait(bar(BAR_READY + cur), (uint32_t)(t >> 1) & 1);
+          else if (wait_b != W_NONE) wait(bar(BAR_READY + wait_b), (uint32_t)t & 1);
+          if (profiling) c2 = clock64();
+          if (j == 0) {
+            // The ring is filled in stream order but drained by four warps: this warp may get here while the slot still
+            // holds (or waits for) the pair STAGES positions earlier, owned by another warp -- a parity wait would then
+            // alias "previous phase" with "this phase".  The producer publishes how many pairs it has issued; once ours
+            // is issued the slot's barrier is in OUR phase and the parity wait is exact.
+            if (issued_seen <= g) {
+              const long long tw = clock64();
+              unsigned spins = 0;
+              while ((issued_seen = *issued_s) <= g) {
+                if ((++spins & 255u) == 0) {
+                  if (*s_abort) break;
+                  if (ld_relaxed_s32(p.abort_flag) != 0) { *s_abort = 1; break; }
+                  if (clock64() - tw > kWatchdogCycles) { atomicExch(p.abort_flag, 2); *s_abort = 1; break; }
+                }
+              }
             }
+            wait(bar(BAR_FULL + slot), (g / SM::STAGES) & 1);
+            tc_fence_after();
           }
+          if (profiling) c3 = clock64();
+          const uint32_t a_lo = (slot_lo + (r.x & 0xffffu)) | LBO, a_hi = (flags & DF_NK1) ? HI_A1 : HI_A4;
+          const uint32_t b_lo = (s0_lo + (cur ? (r.y & 0xffffu) : (r.x >> 16))) | LBO, b_hi = (flags & DF_B_COND) ? HI_BQ : HI_BH;
+          const uint32_t d_col = tmem + acc * NF;
+          mma4(d_col, a_lo, a_hi, b_lo, b_hi, (flags & DF_FIRST) ? 0u : 1u, (flags & DF_NK1) != 0);
+          if (flags & DF_HAS_B2) mma4(d_col, a_lo, a_hi, (s0_lo + (cur ? (r.z & 0xffffu) : (r.y >> 16))) | LBO, HI_BH, 1u, false);
+          if (commit) umma_commit(bar(BAR_ACC_FULL + commit - 1));
+          if (flags & DF_COND_RELEASE) umma_commit(bar(BAR_COND_FREE + cur));
+          if (j == 1) umma_commit(bar(BAR_EMPTY + slot));
+          if (profiling) { const long long c4 = clock64(); t_acc += c1 - c0; t_b += c2 - c1; t_ring += c3 - c2; t_issue += c4 - c3; }
         }
-        wait(bar(BAR_FULL + slot), (g / SM::STAGES) & 1);
-        tc_fence_after();
-        if (profiling) c3 = clock64();
-        auto b_desc = [&](uint32_t buf) -> uint64_t {
-          // h1 ping-pong: this step's h1 (previous state) is X[cur], the new h1' goes to X[cur^1]; y1 reuses X[cur]
-          uint32_t base, sbo = SBO_H;
-          switch (buf) {
-            case B_COND: base = SM::OFF_COND + cur * SM::COND; sbo = SBO_Q; break;
-            case B_H1NEW: base = cur ? SM::OFF_X0 : SM::OFF_X1; break;
-            case B_H2: base = SM::OFF_H2; break;
-            default: base = cur ? SM::OFF_X1 : SM::OFF_X0; break;      // B_H1PREV, B_Y1, B_Y2
-          }
-          return umma_desc(s0 + base + k0 * 16, 128, sbo);
-        };
-        const uint64_t dA = umma_desc(ring0 + slot * CHUNK_BYTES, 128, nk * 256);
-        const uint64_t dB = b_desc(b_buf);
-        const uint32_t d_col = tmem + acc * NF;
-        if (nk == 4) {
-#pragma unroll
-          for (uint32_t k = 0; k < 4; ++k) umma_f16(d_col, dA + (uint64_t)(k * 16), dB + (uint64_t)(k * 16), idesc, (k > 0 || !(flags & F_FIRST)) ? 1u : 0u);
-        } else {
-          for (uint32_t k = 0; k < nk; ++k) umma_f16(d_col, dA + (uint64_t)(k * 16), dB + (uint64_t)(k * 16), idesc, (k > 0 || !(flags & F_FIRST)) ? 1u : 0u);
-        }
-        if (b_buf2 != B_NONE) {
-          const uint64_t dB2 = b_desc(b_buf2);
-#pragma unroll
-          for (uint32_t k = 0; k < 4; ++k) umma_f16(d_col, dA + (uint64_t)(k * 16), dB2 + (uint64_t)(k * 16), idesc, 1u);
-        }
-        umma_commit(bar(BAR_EMPTY + slot));
-        if (commit) umma_commit(bar(BAR_ACC_FULL + commit - 1));
-        if (flags & F_COND_RELEASE) umma_commit(bar(BAR_COND_FREE + cur));
-        if (profiling) { const long long c4 = clock64(); t_acc += c1 - c0; t_b += c2 - c1; t_ring += c3 - c2; t_issue += c4 - c3; }
       }
     }
     if (profiling && lane == 0) { p.prof[0] = t_acc; p.prof[1] = t_b; p.prof[2] = t_ring; p.prof[3] = t_issue; }
@@ -264,26 +279,17 @@ __global__ void __launch_bounds__(NT, 1) wrnn_stream_kernel(const StreamParams p
       return p.fold_row0 ? __ldg(p.fold_row0 + f0 + f) : (long long)(f0 + f + (FRAMES ? p.seg_first : 0)) * p.seg_stride - p.row_base;
     };
     auto end_of = [&](int f) -> long long { return p.fold_row_end ? __ldg(p.fold_row_end + f0 + f) : p.L; };
-    constexpr int TASKS = (NF * KQ + 31) / 32;
-    long long t_row0[TASKS], t_left[TASKS];
-#pragma unroll
-    for (int j = 0; j < TASKS; ++j) {
-      const int task = st + j * 32, f = task / KQ;
-      t_row0[j] = 0; t_left[j] = 0;
-      if (task < NF * KQ && f < B) { t_row0[j] = row0_of(f); t_left[j] = end_of(f) - t_row0[j]; }
-    }
     for (int s = 0; s < S && !*s_abort; ++s) {
       const int par = s & 1;
       if (s >= 2) wait(bar(BAR_COND_FREE + par), (uint32_t)((s >> 1) - 1) & 1);   // step s-2 has consumed this buffer
       unsigned char* img = smem + SM::OFF_COND + par * SM::COND;
-#pragma unroll
-      for (int j = 0; j < TASKS; ++j) {
-        const int task = st + j * 32;
-        if (task >= NF * KQ) continue;
+      // a rolled loop on purpose: this warp shares its instruction caches with an issuing warp
+#pragma unroll 2
+      for (int task = st; task < NF * KQ; task += 32) {
         const int f = task / KQ, c8 = task - f * KQ;
         float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
-        if (s < t_left[j]) {
-          const long long row = t_row0[j] + s;
+        const long long row = (f < B) ? row0_of(f) + s : 0;
+        if (f < B && row < end_of(f)) {
           if constexpr (!FRAMES) {
             const float* src = (c8 < FEAT / 8) ? p.mels_up + row * FEAT + c8 * 8 : p.aux + row * (4 * AUXD) + (c8 - FEAT / 8) * 8;
             a = __ldg(reinterpret_cast<const float4*>(src)); b = __ldg(reinterpret_cast<const float4*>(src) + 1);
@@ -320,7 +326,7 @@ __global__ void __launch_bounds__(NT, 1) wrnn_stream_kernel(const StreamParams p
     float* st_h2 = p.state + ((size_t)tile * 2 + 1) * H * NF;
     unsigned full_par = 0;                                    // per block: parity of the accumulator-full waits so far
     unsigned rows_known = p.uniforms_ready ? 0u : 0xffffffffu;   // rows of p.uniforms known to have landed (streamed draws)
-    const bool profiling = p.prof != nullptr && blockIdx.x == 0 && tid == EPI_TID0;
+    const bool profiling = PROF && blockIdx.x == 0 && tid == EPI_TID0;
     long long t_wait = 0, t_work = 0;
     auto wait_full = [&](int blk) {
       long long c0 = 0;
@@ -550,15 +556,17 @@ class StreamEngine : public Engine {
  public:
   ~StreamEngine() override {
     cudaSetDevice(device);
-    cudaFree(d_blob_); cudaFree(d_prog_); cudaFree(d_mine_); cudaFree(d_vec_); cudaFree(d_state_); cudaFree(d_sync_);
+    cudaFree(d_blob_); cudaFree(d_prog_[0]); cudaFree(d_prog_[1]); cudaFree(d_pairs_); cudaFree(d_vec_); cudaFree(d_state_); cudaFree(d_sync_);
   }
   const char* name() const override { return cfg.precision == WRNN_PREC_BF16 ? "tcgen05-stream-bf16" : "tcgen05-stream-fp16"; }
   int grid_ctas() const override { return last_grid_; }
 
-  template <int NF> const void* kernel_nf(bool frames) const {
-    if (cfg.precision == WRNN_PREC_BF16) return frames ? (const void*)wrnn_stream_kernel<NF, 1, true> : (const void*)wrnn_stream_kernel<NF, 1, false>;
-    return frames ? (const void*)wrnn_stream_kernel<NF, 0, true> : (const void*)wrnn_stream_kernel<NF, 0, false>;
+  template <int NF, bool PROF> const void* kernel_p(bool frames) const {
+    if (cfg.precision == WRNN_PREC_BF16) return frames ? (const void*)wrnn_stream_kernel<NF, 1, true, PROF> : (const void*)wrnn_stream_kernel<NF, 1, false, PROF>;
+    return frames ? (const void*)wrnn_stream_kernel<NF, 0, true, PROF> : (const void*)wrnn_stream_kernel<NF, 0, false, PROF>;
   }
+  template <int NF> const void* kernel_nf(bool frames, bool prof) const { return prof ? kernel_p<NF, true>(frames) : kernel_p<NF, false>(frames); }
+  template <int NF> static SmemLayout layout() { return SmemLayout{Smem<NF>::OFF_X0, Smem<NF>::OFF_X1, Smem<NF>::OFF_H2, Smem<NF>::OFF_COND, Smem<NF>::COND}; }
 
   int init(const HostWeights& w) {
     Plan plan;
@@ -566,13 +574,22 @@ class StreamEngine : public Engine {
     n_chunks_ = (int)plan.prog.size(); n_mma_ = plan.n_mma;
     WRNN_CUDA_OK(cudaMalloc(&d_blob_, plan.blob.size()));
     WRNN_CUDA_OK(cudaMemcpy(d_blob_, plan.blob.data(), plan.blob.size(), cudaMemcpyHostToDevice));
-    WRNN_CUDA_OK(cudaMalloc(&d_prog_, plan.prog.size() * sizeof(Chunk)));
-    WRNN_CUDA_OK(cudaMemcpy(d_prog_, plan.prog.data(), plan.prog.size() * sizeof(Chunk), cudaMemcpyHostToDevice));
-    {
-      std::vector<uint16_t> lists;
-      for (int o = 0; o < N_ISSUERS; ++o) { off_mine_[o] = lists.size(); n_mine_[o] = (int)plan.mine[o].size(); lists.insert(lists.end(), plan.mine[o].begin(), plan.mine[o].end()); }
-      WRNN_CUDA_OK(cudaMalloc(&d_mine_, lists.size() * sizeof(uint16_t)));
-      WRNN_CUDA_OK(cudaMemcpy(d_mine_, lists.data(), lists.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    if (plan.prog.size() % 2) { set_error("stream plan: odd chunk count"); return WRNN_E_INVALID; }
+    for (size_t i = 0; i < plan.prog.size(); i += 2)
+      if (plan.prog[i].owner != plan.prog[i + 1].owner) { set_error("stream plan: a chunk pair with two owners"); return WRNN_E_INVALID; }
+    n_pairs_ = (int)plan.prog.size() / 2;
+    // device programs for the two shared-memory layouts (folds per CTA)
+    for (int v = 0; v < 2; ++v) {
+      DevProgram dp;
+      compile_device(plan, v == 0 ? layout<16>() : layout<32>(), dp);
+      std::vector<DevChunk> all;
+      for (int o = 0; o < N_ISSUERS; ++o) { off_mine_[v][o] = all.size(); n_mine_[o] = (int)dp.mine[o].size(); all.insert(all.end(), dp.mine[o].begin(), dp.mine[o].end()); }
+      WRNN_CUDA_OK(cudaMalloc(&d_prog_[v], all.size() * sizeof(DevChunk)));
+      WRNN_CUDA_OK(cudaMemcpy(d_prog_[v], all.data(), all.size() * sizeof(DevChunk), cudaMemcpyHostToDevice));
+      if (v == 0) {
+        WRNN_CUDA_OK(cudaMalloc(&d_pairs_, dp.pair_size16.size() * sizeof(uint16_t)));
+        WRNN_CUDA_OK(cudaMemcpy(d_pairs_, dp.pair_size16.data(), dp.pair_size16.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+      }
     }
     std::vector<float> vec;
     off_qk_ = 0; vec.insert(vec.end(), plan.qk.begin(), plan.qk.end());
@@ -584,9 +601,9 @@ class StreamEngine : public Engine {
     WRNN_CUDA_OK(cudaMemcpy(d_vec_, vec.data(), vec.size() * sizeof(float), cudaMemcpyHostToDevice));
     WRNN_CUDA_OK(cudaMalloc(&d_sync_, 256));
     WRNN_CUDA_OK(cudaMemset(d_sync_, 0, 256));
-    for (int fr = 0; fr < 2; ++fr) {
-      WRNN_CUDA_OK(cudaFuncSetAttribute(kernel_nf<16>(fr != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<16>::BYTES));
-      WRNN_CUDA_OK(cudaFuncSetAttribute(kernel_nf<32>(fr != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<32>::BYTES));
+    for (int v = 0; v < 4; ++v) {
+      WRNN_CUDA_OK(cudaFuncSetAttribute(kernel_nf<16>((v & 1) != 0, (v & 2) != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<16>::BYTES));
+      WRNN_CUDA_OK(cudaFuncSetAttribute(kernel_nf<32>((v & 1) != 0, (v & 2) != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<32>::BYTES));
     }
     WRNN_CUDA_OK(cudaDeviceGetAttribute(&n_sm_, cudaDevAttrMultiProcessorCount, device));
     return WRNN_OK;
@@ -611,8 +628,8 @@ class StreamEngine : public Engine {
     }
     StreamParams p{};
     const float* v = static_cast<const float*>(d_vec_);
-    p.blob = static_cast<const unsigned char*>(d_blob_); p.prog = static_cast<const uint4*>(d_prog_); p.n_chunks = n_chunks_;
-    for (int o = 0; o < N_ISSUERS; ++o) { p.mine[o] = static_cast<const unsigned short*>(d_mine_) + off_mine_[o]; p.n_mine[o] = n_mine_[o]; }
+    p.blob = static_cast<const unsigned char*>(d_blob_); p.pair_size16 = static_cast<const unsigned short*>(d_pairs_); p.n_pairs = n_pairs_;
+    for (int o = 0; o < N_ISSUERS; ++o) { p.mine[o] = static_cast<const uint4*>(d_prog_[nf == 16 ? 0 : 1]) + off_mine_[nf == 16 ? 0 : 1][o]; p.n_mine[o] = n_mine_[o]; }
     p.qk = v + off_qk_; p.vq = v + off_vq_; p.b1h = v + off_b1h_; p.b2h = v + off_b2h_; p.b3 = v + off_b3_;
     p.mels_up = job.mels_up; p.aux = job.aux; p.L = job.L; p.seg_stride = job.seg_stride; p.row_base = 0;
     p.n_total = job.n_seg; p.steps = job.steps > 0 ? job.steps : job.seg_len; p.out_pitch = p.steps; p.seg_first = job.seg_first;
@@ -622,9 +639,10 @@ class StreamEngine : public Engine {
     p.mel_frames = job.mel_frames; p.aux_frames = job.aux_frames; p.up_taps = job.up_taps; p.hop = job.hop;
     p.state = static_cast<float*>(d_state_);
     p.abort_flag = reinterpret_cast<int*>(static_cast<unsigned*>(d_sync_) + 8);
-    p.prof = getenv("WRNN_STREAM_PROF") ? reinterpret_cast<long long*>(static_cast<unsigned char*>(d_sync_) + 64) : nullptr;
+    const bool prof = getenv("WRNN_STREAM_PROF") != nullptr;
+    p.prof = reinterpret_cast<long long*>(static_cast<unsigned char*>(d_sync_) + 64);
     const bool frames = job.mel_frames != nullptr;             // rows are formed by the staging warps (no scratch of size L)
-    const void* fn = nf == 16 ? kernel_nf<16>(frames) : kernel_nf<32>(frames);
+    const void* fn = nf == 16 ? kernel_nf<16>(frames, prof) : kernel_nf<32>(frames, prof);
     const int smem = nf == 16 ? Smem<16>::BYTES : Smem<32>::BYTES;
     void* args[] = {&p};
     WRNN_CUDA_OK(cudaLaunchKernel(fn, dim3(tiles), dim3(NT), args, smem, stream));
@@ -639,19 +657,19 @@ class StreamEngine : public Engine {
     WRNN_CUDA_OK(cudaMemcpy(buf, d_sync_, 256, cudaMemcpyDeviceToHost));
     const int flag = reinterpret_cast<int*>(buf)[8];
     if (getenv("WRNN_STREAM_PROF") && last_steps_ > 0) {
-      long long prof[8]; std::memcpy(prof, buf + 64, sizeof(prof));
+      long long prof[16]; std::memcpy(prof, buf + 64, sizeof(prof));
       const long long n = last_steps_;
       fprintf(stderr, "[wrnn_stream prof] NF=%d tiles=%d steps=%d mma/step=%d chunks/step=%d | issuer 0: acc-wait=%lld operand-wait=%lld ring-wait=%lld "
-              "issue=%lld | epilogue thread: mma-wait=%lld step=%lld (cycles per step)\n", last_nf_, last_grid_, last_steps_, n_mma_, n_chunks_,
-              prof[0] / n, prof[1] / n, prof[2] / n, prof[3] / n, prof[4] / n, prof[5] / n);
+              "issue=%lld | epilogue thread: mma-wait=%lld step=%lld (cycles per step)\n",
+              last_nf_, last_grid_, last_steps_, n_mma_, n_chunks_, prof[0] / n, prof[1] / n, prof[2] / n, prof[3] / n, prof[4] / n, prof[5] / n);
     }
     if (flag != 0) { set_error("stream kernel aborted: an mbarrier wait (TMA / MMA / operand hand-off) timed out"); return WRNN_E_WATCHDOG; }
     return WRNN_OK;
   }
 
  private:
-  void *d_blob_ = nullptr, *d_prog_ = nullptr, *d_mine_ = nullptr, *d_vec_ = nullptr, *d_state_ = nullptr, *d_sync_ = nullptr;
-  size_t off_mine_[N_ISSUERS] = {0, 0, 0, 0}; int n_mine_[N_ISSUERS] = {0, 0, 0, 0};
+  void *d_blob_ = nullptr, *d_prog_[2] = {nullptr, nullptr}, *d_pairs_ = nullptr, *d_vec_ = nullptr, *d_state_ = nullptr, *d_sync_ = nullptr;
+  size_t off_mine_[2][N_ISSUERS] = {{0, 0, 0, 0}, {0, 0, 0, 0}}; int n_mine_[N_ISSUERS] = {0, 0, 0, 0}; int n_pairs_ = 0;
   size_t state_bytes_ = 0, off_qk_ = 0, off_vq_ = 0, off_b1h_ = 0, off_b2h_ = 0, off_b3_ = 0;
   int n_chunks_ = 0, n_mma_ = 0, n_sm_ = 0, last_grid_ = 0, last_steps_ = 0, last_nf_ = 0;
 };

@@ -32,7 +32,8 @@ namespace stream {
 
 constexpr int MROWS = 128;          // weight rows per MMA tile (UMMA M)
 constexpr int KCH = 64;             // K elements per streamed chunk (4 MMAs of K = 16)
-constexpr int CHUNK_BYTES = MROWS * KCH * 2;   // 16 KB ring slot
+constexpr int CHUNK_BYTES = MROWS * KCH * 2;   // 16 KB: one chunk
+constexpr int PAIR_BYTES = 2 * CHUNK_BYTES;    // 32 KB ring slot: chunks are loaded two at a time (halves the producer's work per byte)
 
 // B operand (activation image) selectors
 enum : uint8_t { B_COND = 0, B_H1PREV = 1, B_H1NEW = 2, B_H2 = 3, B_Y1 = 4, B_Y2 = 5, B_NONE = 0xff };
@@ -43,7 +44,9 @@ constexpr int N_ISSUERS = 4;        // issuing warps; every accumulator chain be
 constexpr int N_PHASES = 5;
 
 struct Chunk {            // 16 bytes, read as one uint4
-  uint32_t bytes;         // size of this chunk in the weight stream (chunks are consecutive): 128 rows x (16*nk) x 2 B
+  uint16_t size16;        // size of this chunk in the weight stream in 16-byte units (chunks are consecutive): 128 rows x (16*nk) x 2 B
+  uint16_t a_off16;       // where the chunk lands inside its ring slot (16-byte units): chunks travel in PAIRS (one TMA, one
+                          // barrier per pair), the second chunk of a pair sits right behind the first
   uint8_t acc;            // accumulator index: TMEM column = acc * NF
   uint8_t nk;             // K = 16 steps in this chunk
   uint8_t b_buf;          // B operand image (B_*)
@@ -108,7 +111,7 @@ inline void build_plan(const HostWeights& w, bool bf, Plan& p) {
         for (int k = 0; k < kc; ++k) pd.img[tile_index(r, k, kc)] = cvt(M[(size_t)(row0 + r) * K + k0 + k]);
       }
       Chunk c{};
-      c.bytes = (uint32_t)(MROWS * kc * 2); c.acc = acc; c.nk = (uint8_t)(kc / 16); c.b_buf = b_buf; c.b_buf2 = b_buf2;
+      c.size16 = (uint16_t)(MROWS * kc * 2 / 16); c.a_off16 = 0; c.acc = acc; c.nk = (uint8_t)(kc / 16); c.b_buf = b_buf; c.b_buf2 = b_buf2;
       c.k0 = (uint16_t)k0; c.flags = first ? F_FIRST : 0; c.wait_b = wait_b; c.wait_acc = fresh[owner] ? (uint8_t)(blk + 1) : 0;
       c.commit = 0; c.owner = (uint8_t)owner; c.phase = (uint8_t)phase;
       first = false; fresh[owner] = false;
@@ -118,7 +121,9 @@ inline void build_plan(const HostWeights& w, bool bf, Plan& p) {
     }
   };
   auto mark_commit = [&](int owner, int blk) { q[owner].back().c.commit = (uint8_t)(blk + 1); };
-  // appends the queued chunks to the stream, round-robin over the issuers
+  // appends the queued chunks to the stream, round-robin over the issuers TWO chunks at a time: chunks travel through the
+  // ring in pairs (one TMA, one full / empty barrier per pair) and both chunks of a pair belong to the same issuer, which
+  // therefore pays the ring hand-shake once per eight MMAs.  Every flush group has an even chunk count per issuer.
   auto flush = [&]() {
     size_t pos[N_ISSUERS] = {0, 0, 0, 0};
     for (bool any = true; any;) {
@@ -126,12 +131,15 @@ inline void build_plan(const HostWeights& w, bool bf, Plan& p) {
       for (int o = 0; o < N_ISSUERS; ++o) {
         if (pos[o] >= q[o].size()) continue;
         any = true;
-        Pending& pd = q[o][pos[o]++];
-        p.mine[o].push_back((uint16_t)p.prog.size());
-        p.prog.push_back(pd.c);
-        const size_t base = p.blob.size();
-        p.blob.resize(base + pd.img.size() * 2);
-        std::memcpy(p.blob.data() + base, pd.img.data(), pd.img.size() * 2);
+        for (int j = 0; j < 2 && pos[o] < q[o].size(); ++j) {
+          Pending& pd = q[o][pos[o]++];
+          p.mine[o].push_back((uint16_t)p.prog.size());
+          if (p.prog.size() & 1) pd.c.a_off16 = p.prog.back().size16;     // second chunk of a pair
+          p.prog.push_back(pd.c);
+          const size_t base = p.blob.size();
+          p.blob.resize(base + pd.img.size() * 2);
+          std::memcpy(p.blob.data() + base, pd.img.data(), pd.img.size() * 2);
+        }
       }
     }
     for (auto& v : q) v.clear();
@@ -195,8 +203,8 @@ inline void build_plan(const HostWeights& w, bool bf, Plan& p) {
         else emit(o, 3, b, F, H, H, b * MROWS, 128 * o, 128 * o + 128, (uint8_t)(4 * b + o), B_Y1, B_NONE, first, W_Y1);
         mark_commit(o, b);
       }
-      flush();
     }
+    flush();            // per layer: 3 chunks per issuer and block -> 12 per issuer, even
   }
   // ---- P5: fc3 (phase 4): partial accumulators 0..3 of block 0
   new_block();
@@ -206,6 +214,58 @@ inline void build_plan(const HostWeights& w, bool bf, Plan& p) {
     mark_commit(o, 0);
   }
   flush();
+}
+
+// ---- what the kernel reads -----------------------------------------------------------------------------------------
+// One 16-byte record per chunk with everything pre-digested for a given shared-memory layout (NF), so that the issuing
+// warps spend their instructions on MMAs, not on decoding: operand addresses are descriptor start-address fields
+// (byte offset >> 4 from the start of dynamic shared memory) for both parities of the h1 ping-pong.
+enum : uint8_t { DF_FIRST = 1, DF_COND_RELEASE = 2, DF_B_COND = 4, DF_NK1 = 8, DF_HAS_B2 = 16 };
+struct DevChunk {
+  uint16_t a_lo;          // chunk offset inside its 32 KB ring slot, >> 4
+  uint16_t b_lo[2];       // B operand start (>> 4) when the step parity cur is 0 / 1
+  uint16_t b2_lo[2];      // second B operand (fc1: h2'), same
+  uint8_t acc_phase;      // accumulator index | phase << 4
+  uint8_t flags;          // DF_*
+  uint16_t sync;          // wait_b | wait_acc << 3 | commit << 6     (W_* / block + 1 / block + 1)
+  uint16_t pair;          // index of the chunk's pair in stream order (ring position within the step)
+};
+static_assert(sizeof(DevChunk) == 16, "DevChunk must stay one uint4");
+
+struct SmemLayout { int off_x0, off_x1, off_h2, off_cond, cond_bytes; };   // byte offsets of the operand images
+
+struct DevProgram {
+  std::vector<DevChunk> mine[N_ISSUERS];     // per issuing warp, in its own order (pairs are adjacent records)
+  std::vector<uint16_t> pair_size16;         // per pair in stream order: bytes >> 4 of the TMA that loads it
+};
+
+inline void compile_device(const Plan& p, const SmemLayout& L, DevProgram& d) {
+  for (auto& v : d.mine) v.clear();
+  d.pair_size16.assign((p.prog.size() + 1) / 2, 0);
+  auto base_of = [&](uint8_t buf, int cur) -> int {
+    switch (buf) {
+      case B_COND: return L.off_cond + cur * L.cond_bytes;
+      case B_H1NEW: return cur ? L.off_x0 : L.off_x1;
+      case B_H2: return L.off_h2;
+      default: return cur ? L.off_x1 : L.off_x0;          // B_H1PREV, B_Y1, B_Y2
+    }
+  };
+  for (size_t i = 0; i < p.prog.size(); ++i) {
+    const Chunk& c = p.prog[i];
+    d.pair_size16[i / 2] = (uint16_t)(d.pair_size16[i / 2] + c.size16);
+    DevChunk r{};
+    r.a_lo = c.a_off16;
+    for (int cur = 0; cur < 2; ++cur) {
+      r.b_lo[cur] = (uint16_t)((base_of(c.b_buf, cur) + c.k0 * 16) >> 4);
+      r.b2_lo[cur] = c.b_buf2 == B_NONE ? 0 : (uint16_t)((base_of(c.b_buf2, cur) + c.k0 * 16) >> 4);
+    }
+    r.acc_phase = (uint8_t)(c.acc | (c.phase << 4));
+    r.flags = (uint8_t)(((c.flags & F_FIRST) ? DF_FIRST : 0) | ((c.flags & F_COND_RELEASE) ? DF_COND_RELEASE : 0) |
+                        (c.b_buf == B_COND ? DF_B_COND : 0) | (c.nk == 1 ? DF_NK1 : 0) | (c.b_buf2 != B_NONE ? DF_HAS_B2 : 0));
+    r.sync = (uint16_t)(c.wait_b | (c.wait_acc << 3) | (c.commit << 6));
+    r.pair = (uint16_t)(i / 2);
+    d.mine[c.owner].push_back(r);
+  }
 }
 
 }  // namespace stream
