@@ -76,12 +76,16 @@ def build_model(device, mode="MOL"):
 
 def measured_traffic(args, model):
     """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel on this workload, taken from
-    the committed ncu --set full capture (profiles/r01_tc_traffic.json); None when no capture matches."""
-    p = ROOT / "profiles" / "r01_tc_traffic.json"
-    if not p.is_file() or args.workload != "cfg2" or args.seg_steps:
+    the committed ncu --set full capture (profiles/r02_tc_traffic.json, else round 1's); None when no capture matches."""
+    if args.workload != "cfg2" or args.seg_steps:
         return None
-    d = json.loads(p.read_text())
-    return d.get("dram_bytes_per_launch") if d.get("engine") == model.gen_stats.get("engine") else None
+    for name in ("r02_tc_traffic.json", "r01_tc_traffic.json"):
+        p = ROOT / "profiles" / name
+        if p.is_file():
+            d = json.loads(p.read_text())
+            if str(d.get("engine", "")).startswith("tcgen05"):
+                return d.get("dram_bytes_per_launch")
+    return None
 
 
 def measured_peaks():
@@ -385,8 +389,10 @@ def run_ours(args):
                     "d2h_bytes_per_step": int(B_total * S * 4), "ms_per_step": t_e2e / args.steps * 1e3},
             "roofline": {"bound": "tensor", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": ach_tf / peak_tf, "traffic": measured_traffic(args, model), "peak_source": peaks["src"],
-                         "note": "latency/sync-bound at 19 folds per GPU (SURVEY 8d): fraction of the dense-fp16 "
-                                 "tensor roofline is reported for completeness",
+                         "note": ("stream engine: one pass over the fp16 weights per step through each SM's shared memory; bounded by the MMA "
+                                  "front end (~40 cycles per M=128 MMA with A from shared memory) and the ring depth, DESIGN.md 3.2") if cfg5 else
+                                 ("latency/sync-bound at 19 folds per GPU (four L2 exchanges per step, DESIGN.md 3.1): fraction of the "
+                                  "dense-fp16 tensor roofline is reported for completeness"),
                          "hbm_achieved_gbs": value / world * BYTES_PER_SAMPLE / 1e9, "hbm_peak_gbs": peaks["hbm_gbs"]},
             "x_realtime": value / 22050.0, "x_realtime_per_fold": 1.0 / (step_us * 1e-6) / 22050.0,
             "us_per_sequential_step": step_us,

@@ -148,7 +148,8 @@ typedef struct {
   int32_t cond_mode;
   /* Optional (MoL parity mode, tensor-core engines): `uniforms` may still be in flight when the job is enqueued.
    * *uniforms_ready (device, uint32) = number of leading rows of `uniforms` that are valid; the kernel consumes row t at
-   * step t and waits (bounded by the watchdog) while t >= *uniforms_ready.  The caller uploads the draws in step
+   * step t and waits (bounded by the watchdog) until rows t .. min(t+3, steps-1) are valid (a margin that keeps its
+   * cached loads from ever touching a line that is still in flight).  The caller uploads the draws in step
    * chunks on another stream and bumps the counter after each chunk (a 4-byte copy on that same stream), so the
    * host-side replay of torch's generator overlaps the kernel instead of preceding it.  NULL: all rows are valid.  */
   const uint32_t *uniforms_ready;

@@ -90,7 +90,7 @@ def interpret(blob, prog, v, m_up, aux, U, *, n_seg, seg_len, seg_stride, steps,
     for t in range(steps):
         cur = t & 1
         cond = rnd(cond_z[np.minimum(base + t, L)])
-        ready = {W_COND}                      # staging runs ahead of the step
+        ready = {(W_COND, 0)}                 # staging runs ahead of the step
         waited = set()
         n_commit = [0] * NB                   # phase of each block within the step
         n_arrive = [0] * NB                   # commits of the current (phase, block): the epilogue runs after all four issuers'
@@ -114,15 +114,23 @@ def interpret(blob, prog, v, m_up, aux, U, *, n_seg, seg_len, seg_stride, steps,
                 seen_owner.add(key)
             else:
                 assert c["wait_acc"] == 0
+            k0, kc = int(c["k0"]), int(c["nk"]) * 16
             if c["wait_b"]:
-                assert int(c["wait_b"]) in ready, f"chunk {i} waits for operand {c['wait_b']} that no epilogue of this step produces before it"
-                waited.add(int(c["wait_b"]))
-            need = {B_COND: W_COND, B_H1NEW: W_H1NEW, B_Y1: W_Y1, B_Y2: W_Y2}
+                wkind, wblk = int(c["wait_b"]) & 15, int(c["wait_b"]) >> 4
+                key_w = (wkind, wblk) if wkind in (W_H1NEW, W_H2NEW, W_Y1) else (wkind, 0)
+                assert key_w in ready, f"chunk {i} waits for operand {key_w} that no epilogue of this step produces before it"
+                waited.add(key_w)
+            # operands are waited for per 128-unit block (h1', h2', y1) or as a whole (cond, y2); fc1's h1' read rides on its
+            # h2' wait (the GRU2 epilogue of a block starts only after every h1' block has been written and waited for)
+            blk_k = k0 // 128
+            ph_c = int(c["phase"])
             for buf in (int(c["b_buf"]), int(c["b_buf2"])):
                 if buf == B_NONE: continue
-                if buf in need: assert need[buf] in waited, f"chunk {i} reads operand {buf} without having waited for it"
-                if buf == B_H2 and h2_touched: assert W_H2NEW in waited, f"chunk {i} reads h2 while the GRU2 epilogue rewrites it"
-            k0, kc = int(c["k0"]), int(c["nk"]) * 16
+                if buf == B_COND: assert (W_COND, 0) in waited
+                if buf == B_H1NEW and ph_c == 1: assert (W_H1NEW, blk_k) in waited, f"chunk {i} reads h1' block {blk_k} unwaited"
+                if buf == B_H2 and (h2_touched or ph_c == 2): assert (W_H2NEW, blk_k) in waited, f"chunk {i} reads h2' block {blk_k} unwaited"
+                if buf == B_Y1: assert (W_Y1, blk_k) in waited, f"chunk {i} reads y1 block {blk_k} unwaited"
+                if buf == B_Y2: assert (W_Y2, 0) in waited
             a = int(c["acc"])
             if c["flags"] & 1:
                 acc[a] = 0
@@ -151,21 +159,21 @@ def interpret(blob, prog, v, m_up, aux, U, *, n_seg, seg_len, seg_stride, steps,
                     hs[u] = hn
                     (H2 if ph else X[cur ^ 1])[:, u] = rnd(hn).T
                     if ph: h2_touched = True
-                    if n_commit == [ph + 1] * NB: ready.add(W_H2NEW if ph else W_H1NEW)
+                    ready.add((W_H2NEW if ph else W_H1NEW, b))
                 elif ph in (2, 3):                     # fc1 / fc2
                     q0 = 6 * H + (ph - 2) * H
                     y = np.maximum(((acc[4 * b] + acc[4 * b + 1]) + (acc[4 * b + 2] + acc[4 * b + 3])) + v["qk"][q0 + b * 128: q0 + b * 128 + 128][:, None]
                                    + xs[None, :] * v["vq"][q0 + b * 128: q0 + b * 128 + 128][:, None], 0).astype(np.float32)
                     if ph == 2:
                         X[cur][:, u] = rnd(y).T
-                        if n_commit == [3] * NB: ready.add(W_Y1)
+                        ready.add((W_Y1, b))
                     else:                              # y2 replaces y1 only after the LAST block's fc2 MMAs (kernel: registers)
                         y2_pending[b] = rnd(y).T
                         if n_commit == [4] * NB:
                             for bb, val in y2_pending.items():
                                 X[cur][:, bb * 128: bb * 128 + 128] = val
                             y2_pending.clear()
-                            ready.add(W_Y2)
+                            ready.add((W_Y2, 0))
                 else:                                  # fc3 + sampler
                     assert b == 0 and ph == 4
                     lg = (((acc[0] + acc[1]) + (acc[2] + acc[3]))[:30] + v["b3"][:30, None]).T.astype(np.float32)

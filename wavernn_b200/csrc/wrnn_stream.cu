@@ -48,7 +48,7 @@ constexpr int SBO_Q = KQ * 128;              // 3328: stride between 8-fold grou
 constexpr int SBO_H = (H / 8) * 128;         // 8192: same for the K = 512 images
 constexpr int TMEM_COLS = 512;
 constexpr int NBAR = 40;
-constexpr int MAX_STAGES = 6;               // ring slots of PAIR_BYTES (two chunks each)
+constexpr int MAX_STAGES = 6;               // ring slots (one or two chunks each)
 
 template <int NF> struct Smem {
   static constexpr int GROUPS = NF / 8;
@@ -59,10 +59,14 @@ template <int NF> struct Smem {
   static constexpr int OFF_X0 = 0, OFF_X1 = ACT, OFF_H2 = 2 * ACT;
   static constexpr int OFF_COND = 3 * ACT;                   // two conditioning images (double buffer)
   static constexpr int OFF_RING = (OFF_COND + 2 * COND + 1023) / 1024 * 1024;
+  // chunks per ring slot / TMA / full-empty barrier pair.  NF = 16 has room for five 32 KB slots and gains from halving
+  // the hand-shakes; NF = 32 has 96 KB of ring in all, where six 16 KB slots refill sooner than three 32 KB ones
+  static constexpr int CPS = (NF == 32) ? 1 : 2;
+  static constexpr int SLOT_BYTES = CPS * CHUNK_BYTES;
   static constexpr int LOGP = 33;                                            // padded row of the logits transpose (conflict-free both ways)
   static constexpr int MISC = LOGP * NF * 4 + NF * 4 + NBAR * 8 + 64;        // logits transpose, x, barriers, tmem slot
-  static constexpr int STAGES = (227 * 1024 - OFF_RING - MISC) / PAIR_BYTES > MAX_STAGES ? MAX_STAGES : (227 * 1024 - OFF_RING - MISC) / PAIR_BYTES;
-  static constexpr int OFF_LOG = OFF_RING + STAGES * PAIR_BYTES;             // [NF][LOGP] fp32
+  static constexpr int STAGES = (227 * 1024 - OFF_RING - MISC) / SLOT_BYTES > MAX_STAGES ? MAX_STAGES : (227 * 1024 - OFF_RING - MISC) / SLOT_BYTES;
+  static constexpr int OFF_LOG = OFF_RING + STAGES * SLOT_BYTES;             // [NF][LOGP] fp32
   static constexpr int OFF_XS = OFF_LOG + LOGP * NF * 4;                       // [NF] fp32: previous sample per fold
   static constexpr int OFF_BAR = OFF_XS + NF * 4;
   static constexpr int BYTES = OFF_BAR + NBAR * 8 + 64;
@@ -71,11 +75,12 @@ template <int NF> struct Smem {
 };
 // barrier indices
 constexpr int BAR_FULL = 0, BAR_EMPTY = MAX_STAGES, BAR_ACC_FULL = 2 * MAX_STAGES, BAR_ACC_EMPTY = BAR_ACC_FULL + 4,
-              BAR_READY = BAR_ACC_EMPTY + 4 /* + {0: cond[0], 1: cond[1], 2: h1new, 3: h2new, 4: y1, 5: y2} */, BAR_COND_FREE = BAR_READY + 6;
+              BAR_READY = BAR_ACC_EMPTY + 4 /* + {0, 1: cond[parity]; 2..5: h1' block b; 6..9: h2' block b; 10..13: y1 block b; 14: y2} */,
+              BAR_COND_FREE = BAR_READY + 15;
 static_assert(BAR_COND_FREE + 2 <= NBAR, "barrier table");
 
 struct StreamParams {
-  const unsigned char* blob; const unsigned short* pair_size16; int n_pairs;    // the weight stream and the TMA size (>> 4) of each chunk pair
+  const unsigned char* blob; const unsigned short* slot_size16; int n_slots; int n_pairs;   // the weight stream, the TMA size (>> 4) of each ring-slot load, loads / pairs per step
   const uint4* mine[N_ISSUERS]; int n_mine[N_ISSUERS];              // per issuing warp: its DevChunk records (pairs adjacent)
   const float* qk; const float* vq; const float* b1h; const float* b2h; const float* b3;
   const float* mels_up; const float* aux; long long L; long long seg_stride; long long row_base;
@@ -124,7 +129,7 @@ __global__ void __launch_bounds__(NT, 1) wrnn_stream_kernel(const StreamParams p
     }
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 32;" :: "r"(bar(BAR_READY + 0)));
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 32;" :: "r"(bar(BAR_READY + 1)));
-    for (int i = 2; i < 6; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 128;" :: "r"(bar(BAR_READY + i)));
+    for (int i = 2; i < 15; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 128;" :: "r"(bar(BAR_READY + i)));
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar(BAR_COND_FREE + 0)), "n"(N_ISSUERS));
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar(BAR_COND_FREE + 1)), "n"(N_ISSUERS));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -156,17 +161,17 @@ __global__ void __launch_bounds__(NT, 1) wrnn_stream_kernel(const StreamParams p
 
   if (warp == 0) {
     // ===================================================================================================== producer
-    // one TMA (and one full / empty barrier) per PAIR of consecutive chunks
-    unsigned g = 0;                                           // pairs issued so far (ring position)
+    // one TMA (and one full / empty barrier) per ring slot = CPS consecutive chunks
+    unsigned g = 0;                                           // slot loads issued so far (ring position)
     for (int t = 0; t < S && !*s_abort; ++t) {
       size_t off = 0;
-      uint32_t sz = __ldg(p.pair_size16);
-      for (int c = 0; c < p.n_pairs; ++c, ++g) {
+      uint32_t sz = __ldg(p.slot_size16);
+      for (int c = 0; c < p.n_slots; ++c, ++g) {
         const uint32_t bytes = sz * 16u;
-        if (c + 1 < p.n_pairs) sz = __ldg(p.pair_size16 + c + 1);
+        if (c + 1 < p.n_slots) sz = __ldg(p.slot_size16 + c + 1);
         const int slot = g % SM::STAGES;
-        wait(bar(BAR_EMPTY + slot), ((g / SM::STAGES) & 1) ^ 1);      // slot drained by the MMAs of both chunks
-        tma_bulk_g2s(smem_u32(smem + SM::OFF_RING + slot * PAIR_BYTES), p.blob + off, bytes, bar(BAR_FULL + slot));
+        wait(bar(BAR_EMPTY + slot), ((g / SM::STAGES) & 1) ^ 1);      // slot drained by the MMAs of its chunk(s)
+        tma_bulk_g2s(smem_u32(smem + SM::OFF_RING + slot * SM::SLOT_BYTES), p.blob + off, bytes, bar(BAR_FULL + slot));
         __syncwarp();
         if (lane == 0) *issued_s = g + 1;                      // see the issuers: parity waits need "this phase is armed"
         off += bytes;
@@ -211,19 +216,22 @@ __global__ void __launch_bounds__(NT, 1) wrnn_stream_kernel(const StreamParams p
     };
     for (int t = 0; t < S && !*s_abort; ++t) {
       const int cur = t & 1;
-      const unsigned gbase = (unsigned)t * (unsigned)p.n_pairs;         // ring position of this step's pair 0
+      const unsigned gbase = (unsigned)t * (unsigned)p.n_slots;         // ring position of this step's first slot load
       uint4 nx0 = __ldg(my), nx1 = __ldg(my + 1);
       for (int i = 0; i < n_my; i += 2) {
         const uint4 rec[2] = {nx0, nx1};
         if (i + 2 < n_my) { nx0 = __ldg(my + i + 2); nx1 = __ldg(my + i + 3); }      // next pair's records: plain sequential loads
-        const unsigned g = gbase + (rec[0].w >> 16);
-        const int slot = g % SM::STAGES;
-        const uint32_t slot_lo = ring_lo + (uint32_t)slot * (PAIR_BYTES >> 4);
+        unsigned g = 0; int slot = 0; uint32_t slot_lo = 0;
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
           const uint4 r = rec[j];
+          if (j == 0 || SM::CPS == 1) {                         // ring slot of this chunk (CPS == 2: of the pair)
+            g = gbase + (SM::CPS == 2 ? (r.w >> 16) : 2u * (r.w >> 16) + (unsigned)j);
+            slot = g % SM::STAGES;
+            slot_lo = ring_lo + (uint32_t)slot * (SM::SLOT_BYTES >> 4);
+          }
           const uint32_t flags = r.z >> 24, acc = (r.z >> 16) & 0xf, phase = (r.z >> 20) & 0xf;
-          const uint32_t wait_b = r.w & 7u, wait_acc = (r.w >> 3) & 7u, commit = (r.w >> 6) & 7u;
+          const uint32_t wait_b = r.w & 7u, wait_acc = (r.w >> 3) & 7u, commit = (r.w >> 6) & 7u, wait_blk = (r.w >> 9) & 3u;
           long long c0 = 0, c1 = 0, c2 = 0, c3 = 0;
           if (profiling) c0 = clock64();
           if (wait_acc) {
@@ -235,9 +243,9 @@ __global__ void __launch_bounds__(NT, 1) wrnn_stream_kernel(const StreamParams p
           }
           if (profiling) c1 = clock64();
           if (wait_b == W_COND) wait(bar(BAR_READY + cur), (uint32_t)(t >> 1) & 1);
-          else if (wait_b != W_NONE) wait(bar(BAR_READY + wait_b), (uint32_t)t & 1);
+          else if (wait_b != W_NONE) wait(bar(BAR_READY + 2 + (wait_b - W_H1NEW) * 4 + wait_blk), (uint32_t)t & 1);   // the block this K range reads
           if (profiling) c2 = clock64();
-          if (j == 0) {
+          if (j == 0 || SM::CPS == 1) {
             // The ring is filled in stream order but drained by four warps: this warp may get here while the slot still
             // holds (or waits for) the pair STAGES positions earlier, owned by another warp -- a parity wait would then
             // alias "previous phase" with "this phase".  The producer publishes how many pairs it has issued; once ours
@@ -257,14 +265,14 @@ __global__ void __launch_bounds__(NT, 1) wrnn_stream_kernel(const StreamParams p
             tc_fence_after();
           }
           if (profiling) c3 = clock64();
-          const uint32_t a_lo = (slot_lo + (r.x & 0xffffu)) | LBO, a_hi = (flags & DF_NK1) ? HI_A1 : HI_A4;
+          const uint32_t a_lo = (slot_lo + (SM::CPS == 2 ? (r.x & 0xffffu) : 0u)) | LBO, a_hi = (flags & DF_NK1) ? HI_A1 : HI_A4;
           const uint32_t b_lo = (s0_lo + (cur ? (r.y & 0xffffu) : (r.x >> 16))) | LBO, b_hi = (flags & DF_B_COND) ? HI_BQ : HI_BH;
           const uint32_t d_col = tmem + acc * NF;
           mma4(d_col, a_lo, a_hi, b_lo, b_hi, (flags & DF_FIRST) ? 0u : 1u, (flags & DF_NK1) != 0);
           if (flags & DF_HAS_B2) mma4(d_col, a_lo, a_hi, (s0_lo + (cur ? (r.z & 0xffffu) : (r.y >> 16))) | LBO, HI_BH, 1u, false);
           if (commit) umma_commit(bar(BAR_ACC_FULL + commit - 1));
           if (flags & DF_COND_RELEASE) umma_commit(bar(BAR_COND_FREE + cur));
-          if (j == 1) umma_commit(bar(BAR_EMPTY + slot));
+          if (j == 1 || SM::CPS == 1) umma_commit(bar(BAR_EMPTY + slot));
           if (profiling) { const long long c4 = clock64(); t_acc += c1 - c0; t_b += c2 - c1; t_ring += c3 - c2; t_issue += c4 - c3; }
         }
       }
@@ -339,9 +347,9 @@ __global__ void __launch_bounds__(NT, 1) wrnn_stream_kernel(const StreamParams p
       tc_fence_before();
       asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar(BAR_ACC_EMPTY + blk)) : "memory");
     };
-    auto publish_ready = [&](int which) {
+    auto publish_ready = [&](int kind, int blk) {                 // this thread's part of operand `kind`, unit block `blk`, is written
       proxy_fence_smem();
-      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar(BAR_READY + which)) : "memory");
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar(BAR_READY + 2 + (kind - W_H1NEW) * 4 + blk)) : "memory");
     };
     // element (fold f, unit k) of a K = 512 operand image
     auto img_ptr = [&](int off, int f, int k) -> uint16_t* {
@@ -362,14 +370,17 @@ __global__ void __launch_bounds__(NT, 1) wrnn_stream_kernel(const StreamParams p
 #pragma unroll
       for (int i = 0; i < 11; ++i) ur[i] = 0.5f;
       const bool sampler = (warp & 3) == 0 && lane < B;
-      if (p.uniforms && (warp & 3) == 0 && (unsigned)t >= rows_known) rows_known = rows_wait(p.uniforms_ready, (unsigned)t + 1u, p.abort_flag);
+      if (p.uniforms && (warp & 3) == 0) {                     // streamed draws: read row t once rows t .. t+3 have landed (see wrnn_tc.cu)
+        const unsigned need = min((unsigned)S, (unsigned)t + 4u);
+        if (rows_known < need) rows_known = rows_wait(p.uniforms_ready, need, p.abort_flag);
+      }
       if (sampler) {
         const int gf = f0 + lane;
         if (p.uniforms) {
           const float* u = p.uniforms + (size_t)t * 11 * p.n_total;
 #pragma unroll
-          for (int i = 0; i < 10; ++i) ur[i] = __ldcg(u + gf * 10 + i);
-          ur[10] = __ldcg(u + 10 * p.n_total + gf);
+          for (int i = 0; i < 10; ++i) ur[i] = __ldca(u + gf * 10 + i);
+          ur[10] = __ldca(u + 10 * p.n_total + gf);
         } else {
           const unsigned gg = (unsigned)(p.seg_first + gf), k0 = (unsigned)p.seed, k1 = (unsigned)(p.seed >> 32), o0 = (unsigned)p.offset;
           const Philox4 r0 = philox4x32_10((unsigned)t, gg, 0u, o0, k0, k1), r1 = philox4x32_10((unsigned)t, gg, 1u, o0, k0, k1),
@@ -429,8 +440,8 @@ __global__ void __launch_bounds__(NT, 1) wrnn_stream_kernel(const StreamParams p
 #pragma unroll
           for (int i = 0; i < NF / 4; ++i)
             __stcg(reinterpret_cast<float4*>(hrow) + i, make_float4(hp[4 * i], hp[4 * i + 1], hp[4 * i + 2], hp[4 * i + 3]));
+          publish_ready(cell ? W_H2NEW : W_H1NEW, b);           // block by block: the consumers' K chunks wait per block
         }
-        publish_ready(cell ? W_H2NEW : W_H1NEW);
       }
 
       // ---- P3: fc1 -> y1 into X[cur] (its readers, this step's W1h h1 MMAs, completed before P1's block-full) ------
@@ -456,8 +467,8 @@ __global__ void __launch_bounds__(NT, 1) wrnn_stream_kernel(const StreamParams p
               *img_ptr(off_y1, f, u) = to_bits(fmaxf(((a[i] + a1[i]) + (a2[i] + a3[i])) + qk_u + x_s[f] * vq_u, 0.f));
             }
           }
+          publish_ready(W_Y1, b);
         }
-        publish_ready(W_Y1);
       }
       // ---- P4: fc2 -> y2.  y2 REPLACES y1 in X[cur], which the fc2 MMAs of the later blocks still read: the values are
       // held in registers (packed pairs) until block 3's block-full, i.e. until every fc2 MMA of every issuing warp has
@@ -495,7 +506,7 @@ __global__ void __launch_bounds__(NT, 1) wrnn_stream_kernel(const StreamParams p
             *img_ptr(off_y1, 2 * i + 1, b * MROWS + row) = (uint16_t)(ypk[b][i] >> 16);
           }
         }
-        publish_ready(W_Y2);
+        publish_ready(W_Y2, 0);
       }
 
       // ---- P5: logits -> transpose through shared memory -> one thread per fold samples ----------------------------
@@ -586,9 +597,11 @@ class StreamEngine : public Engine {
       for (int o = 0; o < N_ISSUERS; ++o) { off_mine_[v][o] = all.size(); n_mine_[o] = (int)dp.mine[o].size(); all.insert(all.end(), dp.mine[o].begin(), dp.mine[o].end()); }
       WRNN_CUDA_OK(cudaMalloc(&d_prog_[v], all.size() * sizeof(DevChunk)));
       WRNN_CUDA_OK(cudaMemcpy(d_prog_[v], all.data(), all.size() * sizeof(DevChunk), cudaMemcpyHostToDevice));
-      if (v == 0) {
-        WRNN_CUDA_OK(cudaMalloc(&d_pairs_, dp.pair_size16.size() * sizeof(uint16_t)));
-        WRNN_CUDA_OK(cudaMemcpy(d_pairs_, dp.pair_size16.data(), dp.pair_size16.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+      if (v == 0) {          // TMA sizes for both ring granularities: pairs first, then single chunks
+        std::vector<uint16_t> sizes(dp.pair_size16);
+        sizes.insert(sizes.end(), dp.chunk_size16.begin(), dp.chunk_size16.end());
+        WRNN_CUDA_OK(cudaMalloc(&d_pairs_, sizes.size() * sizeof(uint16_t)));
+        WRNN_CUDA_OK(cudaMemcpy(d_pairs_, sizes.data(), sizes.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
       }
     }
     std::vector<float> vec;
@@ -628,7 +641,10 @@ class StreamEngine : public Engine {
     }
     StreamParams p{};
     const float* v = static_cast<const float*>(d_vec_);
-    p.blob = static_cast<const unsigned char*>(d_blob_); p.pair_size16 = static_cast<const unsigned short*>(d_pairs_); p.n_pairs = n_pairs_;
+    p.blob = static_cast<const unsigned char*>(d_blob_); p.n_pairs = n_pairs_;
+    const bool pair_slots = nf == 16 ? Smem<16>::CPS == 2 : Smem<32>::CPS == 2;
+    p.slot_size16 = static_cast<const unsigned short*>(d_pairs_) + (pair_slots ? 0 : n_pairs_);
+    p.n_slots = pair_slots ? n_pairs_ : 2 * n_pairs_;
     for (int o = 0; o < N_ISSUERS; ++o) { p.mine[o] = static_cast<const uint4*>(d_prog_[nf == 16 ? 0 : 1]) + off_mine_[nf == 16 ? 0 : 1][o]; p.n_mine[o] = n_mine_[o]; }
     p.qk = v + off_qk_; p.vq = v + off_vq_; p.b1h = v + off_b1h_; p.b2h = v + off_b2h_; p.b3 = v + off_b3_;
     p.mels_up = job.mels_up; p.aux = job.aux; p.L = job.L; p.seg_stride = job.seg_stride; p.row_base = 0;

@@ -53,7 +53,8 @@ struct Chunk {            // 16 bytes, read as one uint4
   uint8_t b_buf2;         // second B operand for the same weight chunk (fc1: h2'), B_NONE otherwise
   uint16_t k0;            // K offset of the chunk inside the B image (elements)
   uint8_t flags;          // F_FIRST: first MMA of the accumulator in this phase overwrites; F_COND_RELEASE: this issuer's last cond read
-  uint8_t wait_b;         // W_*: readiness barrier to wait for before issuing
+  uint8_t wait_b;         // W_* | block << 4: readiness barrier to wait for before issuing.  h1', h2' and y1 become ready BLOCK by
+                          // block (128 units = 128 K columns each): a chunk waits only for the block its K range reads
   uint8_t wait_acc;       // 0, or block + 1: first chunk of this issuer in (phase, block): the previous phase's epilogue must have drained the block
   uint8_t commit;         // 0, or block + 1: last chunk of this issuer in (phase, block): signal "my accumulators of the block are full"
   uint8_t owner;          // issuing warp 0..3
@@ -112,7 +113,9 @@ inline void build_plan(const HostWeights& w, bool bf, Plan& p) {
       }
       Chunk c{};
       c.size16 = (uint16_t)(MROWS * kc * 2 / 16); c.a_off16 = 0; c.acc = acc; c.nk = (uint8_t)(kc / 16); c.b_buf = b_buf; c.b_buf2 = b_buf2;
-      c.k0 = (uint16_t)k0; c.flags = first ? F_FIRST : 0; c.wait_b = wait_b; c.wait_acc = fresh[owner] ? (uint8_t)(blk + 1) : 0;
+      c.k0 = (uint16_t)k0; c.flags = first ? F_FIRST : 0; c.wait_acc = fresh[owner] ? (uint8_t)(blk + 1) : 0;
+      c.wait_b = wait_b;
+      if (wait_b == W_H1NEW || wait_b == W_H2NEW || wait_b == W_Y1) c.wait_b = (uint8_t)(wait_b | ((k0 / MROWS) << 4));   // per-block readiness
       c.commit = 0; c.owner = (uint8_t)owner; c.phase = (uint8_t)phase;
       first = false; fresh[owner] = false;
       pd.c = c;
@@ -227,7 +230,7 @@ struct DevChunk {
   uint16_t b2_lo[2];      // second B operand (fc1: h2'), same
   uint8_t acc_phase;      // accumulator index | phase << 4
   uint8_t flags;          // DF_*
-  uint16_t sync;          // wait_b | wait_acc << 3 | commit << 6     (W_* / block + 1 / block + 1)
+  uint16_t sync;          // wait_b | wait_acc << 3 | commit << 6 | wait_blk << 9     (W_* / block + 1 / block + 1 / block of the operand)
   uint16_t pair;          // index of the chunk's pair in stream order (ring position within the step)
 };
 static_assert(sizeof(DevChunk) == 16, "DevChunk must stay one uint4");
@@ -237,11 +240,14 @@ struct SmemLayout { int off_x0, off_x1, off_h2, off_cond, cond_bytes; };   // by
 struct DevProgram {
   std::vector<DevChunk> mine[N_ISSUERS];     // per issuing warp, in its own order (pairs are adjacent records)
   std::vector<uint16_t> pair_size16;         // per pair in stream order: bytes >> 4 of the TMA that loads it
+  std::vector<uint16_t> chunk_size16;        // per chunk in stream order (layouts whose ring slot holds one chunk)
 };
 
 inline void compile_device(const Plan& p, const SmemLayout& L, DevProgram& d) {
   for (auto& v : d.mine) v.clear();
   d.pair_size16.assign((p.prog.size() + 1) / 2, 0);
+  d.chunk_size16.clear();
+  for (const Chunk& c : p.prog) d.chunk_size16.push_back(c.size16);
   auto base_of = [&](uint8_t buf, int cur) -> int {
     switch (buf) {
       case B_COND: return L.off_cond + cur * L.cond_bytes;
@@ -262,7 +268,7 @@ inline void compile_device(const Plan& p, const SmemLayout& L, DevProgram& d) {
     r.acc_phase = (uint8_t)(c.acc | (c.phase << 4));
     r.flags = (uint8_t)(((c.flags & F_FIRST) ? DF_FIRST : 0) | ((c.flags & F_COND_RELEASE) ? DF_COND_RELEASE : 0) |
                         (c.b_buf == B_COND ? DF_B_COND : 0) | (c.nk == 1 ? DF_NK1 : 0) | (c.b_buf2 != B_NONE ? DF_HAS_B2 : 0));
-    r.sync = (uint16_t)(c.wait_b | (c.wait_acc << 3) | (c.commit << 6));
+    r.sync = (uint16_t)((c.wait_b & 7) | (c.wait_acc << 3) | (c.commit << 6) | ((c.wait_b >> 4) << 9));
     r.pair = (uint16_t)(i / 2);
     d.mine[c.owner].push_back(r);
   }

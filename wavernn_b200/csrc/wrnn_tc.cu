@@ -234,12 +234,24 @@ __global__ void __launch_bounds__(NT, 1) wrnn_tc_kernel(const TcParams p) {
           }
         }
       } else if (p.uniforms) {
-        if ((unsigned)t >= rows_known) rows_known = rows_wait(p.uniforms_ready, (unsigned)t + 1u, p.abort_flag);   // streamed draws
-        if (owns_fold) {                                   // L2 loads (.cg): rows may land while the kernel runs
+        if (p.uniforms_ready) {
+          // Streamed draws: rows land (DMA) while the kernel runs.  All 128 CTAs read the same row, so the loads must stay
+          // L1-cached (as L2 loads they cost 1 us per step: 27 k requests on a few hot lines, measured) -- which is safe
+          // only if no line is ever cached before all of it has landed: a row is >= 44 B, a 128 B line spans at most four
+          // rows, so row t is read once rows t .. t+3 are in (the host uploads in chunks of ~1000 rows: free).
+          const unsigned need = min((unsigned)S, (unsigned)t + 4u);
+          if (rows_known < need) rows_known = rows_wait(p.uniforms_ready, need, p.abort_flag);
+          if (owns_fold) {
+            const float* u = p.uniforms + (size_t)t * 11 * p.n_total;
+#pragma unroll
+            for (int i = 0; i < 10; ++i) ur[i] = __ldca(u + (p.f0 + fold) * 10 + i);
+            ur[10] = __ldca(u + 10 * p.n_total + p.f0 + fold);
+          }
+        } else if (owns_fold) {                            // resident draws: read-only path (11 values = 2 lines per fold)
           const float* u = p.uniforms + (size_t)t * 11 * p.n_total;
 #pragma unroll
-          for (int i = 0; i < 10; ++i) ur[i] = __ldcg(u + (p.f0 + fold) * 10 + i);
-          ur[10] = __ldcg(u + 10 * p.n_total + p.f0 + fold);
+          for (int i = 0; i < 10; ++i) ur[i] = __ldg(u + (p.f0 + fold) * 10 + i);
+          ur[10] = __ldg(u + 10 * p.n_total + p.f0 + fold);
         }
       } else if (owns_fold) {
         {
@@ -561,11 +573,20 @@ __global__ void __launch_bounds__(NT, 1) wrnn_tc_kernel(const TcParams p) {
       proxy_fence_smem();
     };
 
+    // Conditioning pipeline (round 2): the image of step n is written in the shadow of the y2 exchange of step n-2 and
+    // consumed by a 13-MMA chain issued after the S2 chain of step n-1, so that between two exchanges the issuing warps
+    // only ever do ONE of {store an image, issue the chain} and neither sits in front of a gather they could already
+    // have launched.  (Round 1 did wait + store + barrier + chain + fetch in one block between S2 and S3.)
     cond_fetch(0);
     cond_store(0);
     named_bar_sync(2, 128);
     if (q == 1) cond_chain(TC_Q0);
-    if (S > 1) cond_fetch(1);
+    if (S > 1) {
+      cond_fetch(1);
+      mbar_wait(bar_q, 0u, p.abort_flag);                                    // chain 0 has consumed the image
+      cond_store(1);
+      if (S > 2) cond_fetch(2);
+    }
 
     for (int t = 0; t < S; ++t) {
       const int par = t & 1;
@@ -576,16 +597,17 @@ __global__ void __launch_bounds__(NT, 1) wrnn_tc_kernel(const TcParams p) {
       if (leader) launch(1, target, base + 1 * xch_stride, img_bytes);
       quarter(dS2, TC_S2 + q * N_S2, idesc_s2);
       if (t + 1 < S) {
-        // Conditioning of step t+1: queued behind S2 in the tensor pipe.  (Measured: placing this block after
-        // the F3 chain instead costs ~0.5 us per step -- it then delays phase A of the next step.)
-        mbar_wait(bar_q, (uint32_t)(t & 1), p.abort_flag);           // chain t has consumed the cond image
-        cond_store(t + 1);
-        named_bar_sync(2, 128);
-        if (q == 1) cond_chain(par ? TC_Q0 : TC_Q1);
-        if (t + 2 < S) cond_fetch(t + 2);
+        named_bar_sync(2, 128);                                              // every staging thread has stored image t+1
+        if (q == 1) cond_chain(par ? TC_Q0 : TC_Q1);                         // pre_{t+1}, queued behind S2 in the tensor pipe
       }
       if (leader) launch(2, target, base + 2 * xch_stride, img_bytes);
       quarter(dS3, TC_S3 + q * N_S3, idesc_s3);
+      if (t + 2 < S) {
+        // y2 of this step is still two epilogues away: free time for the staging threads
+        mbar_wait(bar_q, (uint32_t)((t + 1) & 1), p.abort_flag);             // chain t+1 has consumed the image
+        cond_store(t + 2);
+        if (t + 3 < S) cond_fetch(t + 3);
+      }
       if (leader) launch(3, target, base + 3 * xch_stride, img_bytes);
       quarter(dF3, TC_F3 + q * N_F3, idesc_f3);
       if constexpr (RAW) {
