@@ -210,11 +210,16 @@ def run_reference_arm(args):
     # (the same number of fold-steps as at N = 1) so that a --steps K run still ends within minutes
     sample_steps = S if world == 1 else max(1210, S // world)
     times = []
+    on_cuda = args.ref_device == "cuda"
+    if on_cuda and not (use_ref and world == 1 and torch.cuda.is_available()):
+        raise SystemExit("--ref-device cuda needs oracle/_ref, --gpus 1 and a CUDA device")
     if use_ref and world == 1:
         os.environ["WAVERNN_REFERENCE"] = str(ROOT / "oracle" / "_ref")
         from oracle import ref_shim
         ref_shim.REF_ROOT = str(ROOT / "oracle" / "_ref")
         model = ref_shim.build_reference_model(seed=0, mode="MOL")
+        if on_cuda:                 # extra datapoint (not the driver's arm): the unmodified reference's eager CUDA path on this GPU
+            model = model.to("cuda")
         torch.manual_seed(0)
         mel = torch.rand(1, 80, frames_for(world))
         for i in range(args.warmup + args.steps):
@@ -226,7 +231,8 @@ def run_reference_arm(args):
                 times.append(dt)
         assert len(wav) == (frames_for(world) - 1) * HOP
         kind = "reference"
-        how = "UNMODIFIED reference WaveRNN.generate() (oracle/_ref, CPU, fp32), whole call: upsample network + fold + 12100-step loop + xfade"
+        how = ("UNMODIFIED reference WaveRNN.generate() (oracle/_ref, " + ("eager torch CUDA operators on this GPU" if on_cuda else "CPU") +
+               ", fp32), whole call: upsample network + fold + 12100-step loop + xfade")
     else:
         from oracle import torch_port
         for i in range(args.warmup + args.steps):
@@ -243,7 +249,7 @@ def run_reference_arm(args):
     line = {"impl": "reference", "metric": "audio samples/sec (22.05 kHz) batched MoL generate", "value": value,
             "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": per_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": cfg,
+            "dtype": "f32", "data": "synthetic", "config": cfg, "reference_device": args.ref_device,
             "cpu_baseline": {"value": value, "unit": "samples/s", "cores": threads, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "x_realtime": value / 22050.0}
@@ -506,6 +512,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="fp16", choices=["fp16", "bf16", "fp32"])
     ap.add_argument("--engine", default="auto", choices=["auto", "simt", "tcgen05", "stream"])
+    ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"],
+                    help="--impl reference only: 'cuda' times the unmodified reference's eager CUDA path instead (extra datapoint)")
     ap.add_argument("--cpu-sample-steps", type=int, default=3000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg4", "cfg5"],

@@ -59,9 +59,9 @@ template <int NF> struct Smem {
   static constexpr int OFF_X0 = 0, OFF_X1 = ACT, OFF_H2 = 2 * ACT;
   static constexpr int OFF_COND = 3 * ACT;                   // two conditioning images (double buffer)
   static constexpr int OFF_RING = (OFF_COND + 2 * COND + 1023) / 1024 * 1024;
-  // chunks per ring slot / TMA / full-empty barrier pair.  NF = 16 has room for five 32 KB slots and gains from halving
-  // the hand-shakes; NF = 32 has 96 KB of ring in all, where six 16 KB slots refill sooner than three 32 KB ones
-  static constexpr int CPS = (NF == 32) ? 1 : 2;
+  // chunks per ring slot / TMA / full-empty barrier pair.  Two is better for both layouts (measured at NF = 32, 96 KB of
+  // ring: three 32 KB slots 95 us per step, six 16 KB slots 107 us -- the hand-shakes cost more than the coarser refill)
+  static constexpr int CPS = 2;
   static constexpr int SLOT_BYTES = CPS * CHUNK_BYTES;
   static constexpr int LOGP = 33;                                            // padded row of the logits transpose (conflict-free both ways)
   static constexpr int MISC = LOGP * NF * 4 + NF * 4 + NBAR * 8 + 64;        // logits transpose, x, barriers, tmem slot
