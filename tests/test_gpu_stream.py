@@ -28,7 +28,7 @@ def mol():
 def test_stream_engine_matches_emulation_and_reference_fixture(mol, precision):
     out, lg, name = run_engine(mol["model"], mol["m_up"], mol["aux"], uniforms=mol["U"], want_logits=True,
                                precision=precision, engine="stream", **mol["kw"])
-    assert name == f"tcgen05-stream-{precision}"
+    assert name in (f"tcgen05-stream-{precision}", f"tcgen05-stream-x4-{precision}")
     emu, lemu = C.generate_segments(mol["w"], mol["m_up"], mol["aux"], uniforms=mol["U"], precision=precision,
                                     want_logits=True, **mol["kw"])
     d_emu, d_ref = np.abs(out - emu), np.abs(out - mol["g"]["raw"])
@@ -177,7 +177,7 @@ def test_stream_engine_cfg5_4096_folds_shard_invariance_and_agreement_with_the_p
 
     eng = cabi.Engine(model.hot_state(), n_classes=30, mode="MOL", precision="fp16", engine="stream", device=0)
     big = run(eng, 0, 4096)
-    assert eng.name.startswith("tcgen05-stream") and eng.grid_ctas == 128 and eng.launch_count == 1
+    assert eng.name == "tcgen05-stream-fp16" and eng.grid_ctas == 128 and eng.launch_count == 1
     assert np.isfinite(big).all() and np.abs(big).max() <= 1.0 and big.std() > 0.05
     for f0, n in ((0, 64), (64 * 37, 64), (4096 - 64, 64), (512 * 5, 512), (4000, 96)):
         assert np.array_equal(run(eng, f0, n), big[f0:f0 + n]), (f0, n)
@@ -189,3 +189,58 @@ def test_stream_engine_cfg5_4096_folds_shard_invariance_and_agreement_with_the_p
     d = np.abs(ref - big[64 * 37:64 * 38]).max()
     print("cfg5 fold tile 37: stream engine vs persistent engine:", d)
     assert d <= 1e-3
+
+
+@pytest.mark.parametrize("n_seg", [3, 16, 17, 50, 70])
+def test_stream_engine_cluster_form_equals_single_cta_form_and_the_emulation(n_seg, monkeypatch):
+    """Cluster form (WRNN_STREAM_CL=4: four CTAs split the rows of every layer, operand images written into each other's
+    shared memory over DSMEM, cluster-scope barriers) vs the one-CTA form on the same job: the same MMAs in the same
+    order, so the samples must be IDENTICAL; both within the emulation's tolerance.  Tiles of 16 and 32 folds."""
+    model = helpers.make_model(3, "MOL", "cuda")
+    w = O.hot_weights(helpers.state_numpy(model))
+    rs = np.random.RandomState(n_seg)
+    seg_len, stride = 120, 80
+    L = (n_seg - 1) * stride + 70
+    m_up, aux = rs.rand(L, 80).astype(np.float32), rs.randn(L, 128).astype(np.float32)
+    U = helpers.replay_uniforms(5, seg_len, n_seg)
+    kw = dict(n_seg=n_seg, seg_len=seg_len, seg_stride=stride, uniforms=U, engine="stream", want_logits=True)
+    emu, lemu = C.generate_segments(w, m_up, aux, precision="fp16", want_logits=True, n_seg=n_seg, seg_len=seg_len, seg_stride=stride, uniforms=U)
+    outs = {}
+    for nf in ("16", "32"):
+        for cl in ("1", "4"):
+            monkeypatch.setenv("WRNN_STREAM_NF", nf); monkeypatch.setenv("WRNN_STREAM_CL", cl)
+            out, lg, name = run_engine(model, m_up, aux, **kw)
+            assert name.startswith("tcgen05-stream-x4" if cl == "4" else "tcgen05-stream-fp16"), name
+            outs[(nf, cl)] = (out, lg)
+            assert np.abs(out - emu).max() <= 1e-3 and np.abs(lg - lemu).max() <= 1e-3, (nf, cl)
+    for nf in ("16", "32"):
+        assert np.array_equal(outs[(nf, "1")][0], outs[(nf, "4")][0]) and np.array_equal(outs[(nf, "1")][1], outs[(nf, "4")][1]), nf
+    print(f"cluster form n_seg={n_seg}: identical to the one-CTA form; vs emulation {np.abs(outs[('16', '4')][0] - emu).max():.3e}")
+
+
+def test_stream_engine_cluster_form_public_generate_and_trained_logits(mol, monkeypatch):
+    """The cluster form through the public call (frame-rate conditioning, streamed draws) and on the trained checkpoint."""
+    model, g = mol["model"], mol["g"]
+    monkeypatch.setenv("WRNN_STREAM_CL", "4")
+    mel = helpers.make_mel(30, 0)
+    model.gen_engine = "stream"
+    try:
+        torch.manual_seed(1234)
+        wav = model.generate(mel, None, True, 2750, 275, False)
+        assert model.gen_stats["engine"].startswith("tcgen05-stream-x4")
+    finally:
+        model.gen_engine = "auto"
+    print("cluster form generate() vs reference wav:", np.abs(wav - g["wav"]).max())
+    assert np.abs(wav - g["wav"]).max() <= 2e-2
+    gt = helpers.load_golden("trained_tacotron.npz")
+    tm = helpers.make_model(0, "MOL", "cpu")
+    tm.load_state_dict(helpers.pretrained_state_dict(), strict=False)
+    tm = tm.to("cuda")
+    sd = helpers.state_numpy(tm)
+    m_up, aux = O.upsample_network(sd, O.pad_time(helpers.tacotron_mels()[int(gt["sentence"])].T, 2).T, pad=2)
+    U = helpers.replay_uniforms(int(gt["seed"]), 12100, 4)
+    _, lg, name = run_engine(tm, m_up, aux, uniforms=U, x_force=gt["raw"].T.copy(), want_logits=True, steps=600, engine="stream",
+                             n_seg=4, seg_len=12100, seg_stride=11550)
+    e = np.abs(lg - gt["logits"])
+    print(f"{name} trained teacher-forced logits: max {e.max():.3e} median {np.median(e):.3e}")
+    assert name.startswith("tcgen05-stream-x4") and e.max() <= 1e-1 and np.quantile(e, 0.999) <= 3e-2 and np.median(e) <= 1e-3

@@ -23,10 +23,10 @@ CHUNK = np.dtype([("size16", "<u2"), ("a_off16", "<u2"), ("acc", "u1"), ("nk", "
                   ("flags", "u1"), ("wait_b", "u1"), ("wait_acc", "u1"), ("commit", "u1"), ("owner", "u1"), ("phase", "u1")])
 
 
-def get_plan(sd, precision="fp16"):
+def get_plan(sd, precision="fp16", only_block=-1):
     lib = cabi.load()
     lib.wrnn_debug_stream_plan.restype = C.c_int
-    lib.wrnn_debug_stream_plan.argtypes = [C.c_void_p] * 8
+    lib.wrnn_debug_stream_plan.argtypes = [C.c_void_p] * 8 + [C.c_int32]
     cfg = cabi.WrnnCfg(512, 512, 80, 32, 30, cabi.MODE_MOL, {"fp16": cabi.PREC_F16, "bf16": cabi.PREC_BF16}[precision], 3)
     w = cabi.WrnnWeights()
     keep = []
@@ -35,19 +35,21 @@ def get_plan(sd, precision="fp16"):
         keep.append(a)
         setattr(w, field, a.ctypes.data)
     nb, nc = C.c_uint64(0), C.c_uint64(0)
-    assert lib.wrnn_debug_stream_plan(C.byref(cfg), C.byref(w), None, C.byref(nb), None, C.byref(nc), None, None) == 0
+    assert lib.wrnn_debug_stream_plan(C.byref(cfg), C.byref(w), None, C.byref(nb), None, C.byref(nc), None, None, only_block) == 0
     blob = np.zeros(nb.value, np.uint8)
     prog = np.zeros(nc.value, CHUNK)
     vec = np.zeros(4096 * 2 + 1536 * 2 + 128, np.float32)
     mine = np.zeros((4, nc.value), np.uint16)
     assert lib.wrnn_debug_stream_plan(C.byref(cfg), C.byref(w), blob.ctypes.data, C.byref(nb), prog.ctypes.data, C.byref(nc),
-                                      vec.ctypes.data, mine.ctypes.data) == 0
+                                      vec.ctypes.data, mine.ctypes.data, only_block) == 0
     # the four issuing warps' lists partition the program, ascending, and agree with the owner field
     lists = [m[m != 0xFFFF].astype(int) for m in mine]
     assert sorted(np.concatenate(lists).tolist()) == list(range(nc.value))
     for o, l in enumerate(lists):
         assert np.all(np.diff(l) > 0) and np.all(prog["owner"][l] == o)
-    assert nc.value % 2 == 0 and np.all(prog["owner"][0::2] == prog["owner"][1::2])     # a pair travels to ONE issuing warp
+    if only_block < 0:
+        assert nc.value % 2 == 0 and np.all(prog["owner"][0::2] == prog["owner"][1::2])     # a pair travels to ONE issuing warp
+    assert all(len(l) % 2 == 0 for l in lists)                                                  # the issuing loop takes two records per turn
     v = dict(qk=vec[:4096], vq=vec[4096:8192], b1h=vec[8192:9728], b2h=vec[9728:11264], b3=vec[11264:])
     return blob, prog, v
 
@@ -117,7 +119,7 @@ def interpret(blob, prog, v, m_up, aux, U, *, n_seg, seg_len, seg_stride, steps,
             k0, kc = int(c["k0"]), int(c["nk"]) * 16
             if c["wait_b"]:
                 wkind, wblk = int(c["wait_b"]) & 15, int(c["wait_b"]) >> 4
-                key_w = (wkind, wblk) if wkind in (W_H1NEW, W_H2NEW, W_Y1) else (wkind, 0)
+                key_w = (wkind, wblk) if wkind in (W_H1NEW, W_H2NEW, W_Y1, W_Y2) else (wkind, 0)
                 assert key_w in ready, f"chunk {i} waits for operand {key_w} that no epilogue of this step produces before it"
                 waited.add(key_w)
             # operands are waited for per 128-unit block (h1', h2', y1) or as a whole (cond, y2); fc1's h1' read rides on its
@@ -130,7 +132,7 @@ def interpret(blob, prog, v, m_up, aux, U, *, n_seg, seg_len, seg_stride, steps,
                 if buf == B_H1NEW and ph_c == 1: assert (W_H1NEW, blk_k) in waited, f"chunk {i} reads h1' block {blk_k} unwaited"
                 if buf == B_H2 and (h2_touched or ph_c == 2): assert (W_H2NEW, blk_k) in waited, f"chunk {i} reads h2' block {blk_k} unwaited"
                 if buf == B_Y1: assert (W_Y1, blk_k) in waited, f"chunk {i} reads y1 block {blk_k} unwaited"
-                if buf == B_Y2: assert (W_Y2, 0) in waited
+                if buf == B_Y2: assert (W_Y2, blk_k) in waited, f"chunk {i} reads y2 block {blk_k} unwaited"
             a = int(c["acc"])
             if c["flags"] & 1:
                 acc[a] = 0
@@ -173,7 +175,7 @@ def interpret(blob, prog, v, m_up, aux, U, *, n_seg, seg_len, seg_stride, steps,
                             for bb, val in y2_pending.items():
                                 X[cur][:, bb * 128: bb * 128 + 128] = val
                             y2_pending.clear()
-                            ready.add((W_Y2, 0))
+                            for bb in range(NB): ready.add((W_Y2, bb))
                 else:                                  # fc3 + sampler
                     assert b == 0 and ph == 4
                     lg = (((acc[0] + acc[1]) + (acc[2] + acc[3]))[:30] + v["b3"][:30, None]).T.astype(np.float32)
@@ -228,3 +230,40 @@ def test_stream_plan_on_the_trained_checkpoint_teacher_forced():
     e = np.abs(lg - g["logits"][:steps])
     print("trained, teacher forced, interpreted plan: max", e.max(), "median", np.median(e))
     assert e.max() <= 1e-1 and np.median(e) <= 1e-3
+
+
+@pytest.mark.skipif(not cabi.is_built(), reason="library not built")
+def test_cluster_rank_programs_are_the_blocks_of_the_whole_program():
+    """Cluster form (four CTAs split the rows of every layer): the program of rank r is exactly the chunks of unit block r
+    of the whole program -- same weight tiles, same operands, K offsets, first / wait / owner / phase fields -- with the
+    accumulators and block ids renumbered to block 0; fc3 only in rank 0.  (The whole program is the one the numpy
+    interpreter above checks against the engine contract.)"""
+    sd = helpers.state_numpy(helpers.make_model(0, "MOL"))
+    blob, prog, _ = get_plan(sd)
+    nbytes = prog["size16"].astype(np.int64) * 16
+    offs = np.concatenate([[0], np.cumsum(nbytes)])
+    total = 0
+    for r in range(4):
+        b_r, p_r, _ = get_plan(sd, only_block=r)
+        o_r = np.concatenate([[0], np.cumsum(p_r["size16"].astype(np.int64) * 16)])
+        sel = [i for i, c in enumerate(prog) if int(c["acc"]) // 4 == r]
+        assert len(sel) == len(p_r), (r, len(sel), len(p_r))
+        total += len(p_r)
+        # same multiset of chunks; compare per (owner, phase) in order (the interleaving across owners may differ)
+        for o in range(4):
+            a = [i for i in sel if prog["owner"][i] == o]
+            b = [i for i in range(len(p_r)) if p_r["owner"][i] == o]
+            assert len(a) == len(b)
+            for i, j in zip(a, b):
+                c, d = prog[i], p_r[j]
+                for f in ("size16", "nk", "b_buf", "b_buf2", "k0", "flags", "wait_b", "phase"):
+                    if f == "flags" and int(c["phase"]) == 3:        # the cond-release mark sits on the LAST block of the program
+                        assert int(c[f]) & 1 == int(d[f]) & 1
+                        continue
+                    assert c[f] == d[f], (r, o, f, i, j)
+                assert int(d["acc"]) == int(c["acc"]) % 4
+                assert (int(c["wait_acc"]) > 0) == (int(d["wait_acc"]) > 0) and int(d["wait_acc"]) in (0, 1)
+                assert (int(c["commit"]) > 0) == (int(d["commit"]) > 0) and int(d["commit"]) in (0, 1)
+                assert np.array_equal(blob[offs[i]:offs[i + 1]], b_r[o_r[j]:o_r[j + 1]])
+        assert ((p_r["flags"] & 2) > 0).sum() == 4 and (p_r["phase"] == 4).sum() == (8 if r == 0 else 0)
+    assert total == len(prog)

@@ -242,7 +242,8 @@ int wrnn_expand_conditioning(const float* mel_frames, const float* aux_frames, c
 // Call with blob == NULL to obtain the sizes.  Not part of the reference-facing surface.
 int wrnn_debug_stream_plan(const wrnn_cfg* cfg, const wrnn_weights* w, uint8_t* blob, uint64_t* blob_bytes, uint8_t* prog,
                            uint64_t* n_chunks, float* vectors /* qk[4096] vq[4096] b1h[1536] b2h[1536] b3[128] */,
-                           uint16_t* mine /* [4][n_chunks]: per issuing warp, its chunk indices; unused tail = 0xffff */) {
+                           uint16_t* mine /* [4][n_chunks]: per issuing warp, its chunk indices; unused tail = 0xffff */,
+                           int32_t only_block /* -1: the whole program; 0..3: the share of that rank of a 4-CTA cluster */) {
   if (!cfg || !w || !blob_bytes || !n_chunks) { set_error("null argument"); return WRNN_E_INVALID; }
   HostWeights hw;
   hw.n_classes = cfg->n_classes;
@@ -257,7 +258,7 @@ int wrnn_debug_stream_plan(const wrnn_cfg* cfg, const wrnn_weights* w, uint8_t* 
   take(hw.f2w, w->fc2_weight, (size_t)H * W2W); take(hw.f2b, w->fc2_bias, H);
   take(hw.f3w, w->fc3_weight, (size_t)cfg->n_classes * H); take(hw.f3b, w->fc3_bias, cfg->n_classes);
   stream::Plan plan;
-  stream::build_plan(hw, cfg->precision == WRNN_PREC_BF16, plan);
+  stream::build_plan(hw, cfg->precision == WRNN_PREC_BF16, plan, only_block);
   if (blob) {
     if (*blob_bytes < plan.blob.size() || *n_chunks < plan.prog.size()) { set_error("buffers too small"); return WRNN_E_INVALID; }
     std::memcpy(blob, plan.blob.data(), plan.blob.size());

@@ -47,21 +47,23 @@ constexpr int KQ = CDIM / 8;                 // 26 16-byte chunks per conditioni
 constexpr int SBO_Q = KQ * 128;              // 3328: stride between 8-fold groups of the conditioning image
 constexpr int SBO_H = (H / 8) * 128;         // 8192: same for the K = 512 images
 constexpr int TMEM_COLS = 512;
-constexpr int NBAR = 40;
+constexpr int NBAR = 48;
 constexpr int MAX_STAGES = 6;               // ring slots (one or two chunks each)
 
-template <int NF> struct Smem {
+template <int NF, int CL> struct Smem {
   static constexpr int GROUPS = NF / 8;
   static constexpr int ACT = GROUPS * SBO_H;                 // one K = 512 activation image
   static constexpr int COND = GROUPS * SBO_Q;                // one conditioning image
   // Three K = 512 operand images: X0 / X1 = h1 ping-pong (this step's h1 is X[cur], h1' goes to X[cur^1]); y1 and then y2
   // reuse X[cur] once its readers are done (y2 is written only after ALL fc2 MMAs have completed); h2 is updated in place.
-  static constexpr int OFF_X0 = 0, OFF_X1 = ACT, OFF_H2 = 2 * ACT;
-  static constexpr int OFF_COND = 3 * ACT;                   // two conditioning images (double buffer)
+  // Cluster form (CL = 4, rows of every layer split over four CTAs that write into each other's images): h2 ping-pongs
+  // too (H0 / H1; a peer cannot know when this CTA's W2h MMAs are done), y1 -> X[cur], y2 -> H[cur], nothing deferred.
+  static constexpr int OFF_X0 = 0, OFF_X1 = ACT, OFF_H2 = 2 * ACT, OFF_H2B = (CL == 1) ? 2 * ACT : 3 * ACT;
+  static constexpr int OFF_COND = (CL == 1 ? 3 : 4) * ACT;   // two conditioning images (double buffer)
   static constexpr int OFF_RING = (OFF_COND + 2 * COND + 1023) / 1024 * 1024;
   // chunks per ring slot / TMA / full-empty barrier pair.  Two is better for both layouts (measured at NF = 32, 96 KB of
   // ring: three 32 KB slots 95 us per step, six 16 KB slots 107 us -- the hand-shakes cost more than the coarser refill)
-  static constexpr int CPS = 2;
+  static constexpr int CPS = (CL == 1) ? 2 : 1;          // (one-block programs have odd chunk groups: one chunk per slot)
   static constexpr int SLOT_BYTES = CPS * CHUNK_BYTES;
   static constexpr int LOGP = 33;                                            // padded row of the logits transpose (conflict-free both ways)
   static constexpr int MISC = LOGP * NF * 4 + NF * 4 + NBAR * 8 + 64;        // logits transpose, x, barriers, tmem slot
@@ -75,13 +77,16 @@ template <int NF> struct Smem {
 };
 // barrier indices
 constexpr int BAR_FULL = 0, BAR_EMPTY = MAX_STAGES, BAR_ACC_FULL = 2 * MAX_STAGES, BAR_ACC_EMPTY = BAR_ACC_FULL + 4,
-              BAR_READY = BAR_ACC_EMPTY + 4 /* + {0, 1: cond[parity]; 2..5: h1' block b; 6..9: h2' block b; 10..13: y1 block b; 14: y2} */,
-              BAR_COND_FREE = BAR_READY + 15;
-static_assert(BAR_COND_FREE + 2 <= NBAR, "barrier table");
+              BAR_READY = BAR_ACC_EMPTY + 4 /* + {0, 1: cond[parity]; 2..5: h1' block b; 6..9: h2' block b; 10..13: y1 block b; 14..17: y2 block b} */,
+              BAR_COND_FREE = BAR_READY + 18;
+constexpr int BAR_X = BAR_COND_FREE + 2;    // cluster form: "the sample of this step has been written into this CTA's x_s"
+static_assert(BAR_X + 1 <= NBAR, "barrier table");
 
 struct StreamParams {
-  const unsigned char* blob; const unsigned short* slot_size16; int n_slots; int n_pairs;   // the weight stream, the TMA size (>> 4) of each ring-slot load, loads / pairs per step
-  const uint4* mine[N_ISSUERS]; int n_mine[N_ISSUERS];              // per issuing warp: its DevChunk records (pairs adjacent)
+  // per cluster rank (one-CTA form: rank 0 only): the weight stream, the TMA size (>> 4) of each ring-slot load, loads per step,
+  // and per issuing warp its DevChunk records
+  const unsigned char* blob[4]; const unsigned short* slot_size16[4]; int n_slots[4];
+  const uint4* mine[4 * N_ISSUERS]; int n_mine[4 * N_ISSUERS];
   const float* qk; const float* vq; const float* b1h; const float* b2h; const float* b3;
   const float* mels_up; const float* aux; long long L; long long seg_stride; long long row_base;
   int n_total, steps, out_pitch, seg_first;
@@ -94,9 +99,17 @@ struct StreamParams {
   long long* prof;              // optional cycle counters of CTA 0
 };
 
-template <int NF, int FMT, bool FRAMES, bool PROF>
+__device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t map_to_rank(uint32_t addr, uint32_t rank) {
+  uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank)); return r;
+}
+
+template <int NF, int FMT, bool FRAMES, bool PROF, int CL>
 __global__ void __launch_bounds__(NT, 1) wrnn_stream_kernel(const StreamParams p) {
-  using SM = Smem<NF>;
+  using SM = Smem<NF, CL>;
   extern __shared__ __align__(1024) unsigned char smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM::OFF_BAR);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM::OFF_BAR + NBAR * 8);
@@ -107,7 +120,8 @@ __global__ void __launch_bounds__(NT, 1) wrnn_stream_kernel(const StreamParams p
   auto bar = [&](int i) -> uint32_t { return smem_u32(&bars[i]); };
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int tile = blockIdx.x, f0 = tile * NF;
+  const int rank = (CL == 1) ? 0 : (int)cluster_rank();                  // which 128-unit block of every layer this CTA computes
+  const int tile = blockIdx.x / CL, f0 = tile * NF;
   const int B = (p.n_total - f0 < NF) ? (p.n_total - f0) : NF;          // real folds of this tile
   const int S = p.steps;
 
@@ -129,9 +143,10 @@ __global__ void __launch_bounds__(NT, 1) wrnn_stream_kernel(const StreamParams p
     }
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 32;" :: "r"(bar(BAR_READY + 0)));
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 32;" :: "r"(bar(BAR_READY + 1)));
-    for (int i = 2; i < 15; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 128;" :: "r"(bar(BAR_READY + i)));
+    for (int i = 2; i < 18; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 128;" :: "r"(bar(BAR_READY + i)));
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar(BAR_COND_FREE + 0)), "n"(N_ISSUERS));
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar(BAR_COND_FREE + 1)), "n"(N_ISSUERS));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar(BAR_X)));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -143,6 +158,7 @@ __global__ void __launch_bounds__(NT, 1) wrnn_stream_kernel(const StreamParams p
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  if constexpr (CL > 1) cluster_sync_all();                  // every peer's barriers and zeroed images exist before anyone writes into them
   // Bounded wait (a protocol bug must end in WRNN_E_WATCHDOG, never in a hung GPU): once any wait of this CTA has given
   // up, or another CTA has raised the global flag, every later wait returns at once and the role loops end.
   auto wait = [&](uint32_t b, uint32_t parity) {
@@ -159,19 +175,43 @@ __global__ void __launch_bounds__(NT, 1) wrnn_stream_kernel(const StreamParams p
     }
   };
 
+  // same, for barriers peers arrive on after writing into this CTA's shared memory (acquire at cluster scope)
+  auto wait_peer = [&](uint32_t b, uint32_t parity) {
+    if constexpr (CL == 1) { wait(b, parity); return; }
+    auto try_cl = [&]() -> bool {
+      uint32_t ok;
+      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                   : "=r"(ok) : "r"(b), "r"(parity) : "memory");
+      return ok != 0;
+    };
+    if (try_cl()) return;
+    if (*s_abort) return;
+    const long long t0 = clock64();
+    unsigned spins = 0;
+    while (!try_cl()) {
+      if ((++spins & 1023u) == 0) {
+        if (*s_abort) return;
+        if (ld_relaxed_s32(p.abort_flag) != 0) { *s_abort = 1; return; }
+        if (clock64() - t0 > kWatchdogCycles) { atomicExch(p.abort_flag, 2); *s_abort = 1; return; }
+      }
+    }
+  };
+
   if (warp == 0) {
     // ===================================================================================================== producer
     // one TMA (and one full / empty barrier) per ring slot = CPS consecutive chunks
     unsigned g = 0;                                           // slot loads issued so far (ring position)
     for (int t = 0; t < S && !*s_abort; ++t) {
       size_t off = 0;
-      uint32_t sz = __ldg(p.slot_size16);
-      for (int c = 0; c < p.n_slots; ++c, ++g) {
+      const unsigned short* sizes = p.slot_size16[rank];
+      const int n_slots = p.n_slots[rank];
+      uint32_t sz = __ldg(sizes);
+      for (int c = 0; c < n_slots; ++c, ++g) {
         const uint32_t bytes = sz * 16u;
-        if (c + 1 < p.n_slots) sz = __ldg(p.slot_size16 + c + 1);
+        if (c + 1 < n_slots) sz = __ldg(sizes + c + 1);
         const int slot = g % SM::STAGES;
         wait(bar(BAR_EMPTY + slot), ((g / SM::STAGES) & 1) ^ 1);      // slot drained by the MMAs of its chunk(s)
-        tma_bulk_g2s(smem_u32(smem + SM::OFF_RING + slot * SM::SLOT_BYTES), p.blob + off, bytes, bar(BAR_FULL + slot));
+        tma_bulk_g2s(smem_u32(smem + SM::OFF_RING + slot * SM::SLOT_BYTES), p.blob[rank] + off, bytes, bar(BAR_FULL + slot));
         __syncwarp();
         if (lane == 0) *issued_s = g + 1;                      // see the issuers: parity waits need "this phase is armed"
         off += bytes;
@@ -184,8 +224,8 @@ __global__ void __launch_bounds__(NT, 1) wrnn_stream_kernel(const StreamParams p
     // cycles per chunk, two thirds of it plain instruction issue -- ncu source view, profiles/r02_stream.md.)
     const int q = warp - 1;
     const uint32_t idesc = umma_idesc(MROWS, NF, FMT);
-    const uint4* my = p.mine[q];
-    const int n_my = p.n_mine[q];
+    const uint4* my = p.mine[rank * N_ISSUERS + q];
+    const int n_my = p.n_mine[rank * N_ISSUERS + q];
     const bool profiling = PROF && blockIdx.x == 0 && q == 0;
     long long t_ring = 0, t_b = 0, t_acc = 0, t_issue = 0;
     constexpr uint32_t LBO = (128u >> 4) << 16, VER = 1u << 14;       // descriptor: LBO field (low word), version bit (high word)
@@ -216,7 +256,7 @@ __global__ void __launch_bounds__(NT, 1) wrnn_stream_kernel(const StreamParams p
     };
     for (int t = 0; t < S && !*s_abort; ++t) {
       const int cur = t & 1;
-      const unsigned gbase = (unsigned)t * (unsigned)p.n_slots;         // ring position of this step's first slot load
+      const unsigned gbase = (unsigned)t * (unsigned)p.n_slots[rank];   // ring position of this step's first slot load
       uint4 nx0 = __ldg(my), nx1 = __ldg(my + 1);
       for (int i = 0; i < n_my; i += 2) {
         const uint4 rec[2] = {nx0, nx1};
@@ -226,7 +266,7 @@ __global__ void __launch_bounds__(NT, 1) wrnn_stream_kernel(const StreamParams p
         for (int j = 0; j < 2; ++j) {
           const uint4 r = rec[j];
           if (j == 0 || SM::CPS == 1) {                         // ring slot of this chunk (CPS == 2: of the pair)
-            g = gbase + (SM::CPS == 2 ? (r.w >> 16) : 2u * (r.w >> 16) + (unsigned)j);
+            g = gbase + (r.w >> 16);
             slot = g % SM::STAGES;
             slot_lo = ring_lo + (uint32_t)slot * (SM::SLOT_BYTES >> 4);
           }
@@ -238,12 +278,18 @@ __global__ void __launch_bounds__(NT, 1) wrnn_stream_kernel(const StreamParams p
             // the epilogue of the previous (phase, block) use must have drained the block: its arrivals on acc_empty[blk] are
             // numbered A*t + phase (A = 5 for block 0, which also serves fc3; 4 otherwise); we need number A*t + phase - 1
             const int blk = wait_acc - 1;
-            const int idx = (blk == 0 ? N_PHASES : N_PHASES - 1) * t + (int)phase - 1;
+            const int idx = ((CL == 1 ? blk == 0 : rank == 0) ? N_PHASES : N_PHASES - 1) * t + (int)phase - 1;
             if (idx >= 0) wait(bar(BAR_ACC_EMPTY + blk), (uint32_t)idx & 1u);
           }
           if (profiling) c1 = clock64();
           if (wait_b == W_COND) wait(bar(BAR_READY + cur), (uint32_t)(t >> 1) & 1);
-          else if (wait_b != W_NONE) wait(bar(BAR_READY + 2 + (wait_b - W_H1NEW) * 4 + wait_blk), (uint32_t)t & 1);   // the block this K range reads
+          else if (wait_b != W_NONE) {
+            wait_peer(bar(BAR_READY + 2 + (wait_b - W_H1NEW) * 4 + wait_blk), (uint32_t)t & 1);   // the block this K range reads
+            if constexpr (CL > 1) {
+              asm volatile("fence.acq_rel.cluster;" ::: "memory");
+              asm volatile("fence.proxy.async;" ::: "memory");   // peers' generic stores into this CTA -> our tensor-core reads
+            }
+          }
           if (profiling) c2 = clock64();
           if (j == 0 || SM::CPS == 1) {
             // The ring is filled in stream order but drained by four warps: this warp may get here while the slot still
@@ -265,11 +311,13 @@ __global__ void __launch_bounds__(NT, 1) wrnn_stream_kernel(const StreamParams p
             tc_fence_after();
           }
           if (profiling) c3 = clock64();
-          const uint32_t a_lo = (slot_lo + (SM::CPS == 2 ? (r.x & 0xffffu) : 0u)) | LBO, a_hi = (flags & DF_NK1) ? HI_A1 : HI_A4;
-          const uint32_t b_lo = (s0_lo + (cur ? (r.y & 0xffffu) : (r.x >> 16))) | LBO, b_hi = (flags & DF_B_COND) ? HI_BQ : HI_BH;
+          // (address field: 14 bits of byte address >> 4 -- masked, because in a cluster launch the shared::cta window of
+          //  ranks > 0 does not start at 0)
+          const uint32_t a_lo = ((slot_lo + (SM::CPS == 2 ? (r.x & 0xffffu) : 0u)) & 0x3fffu) | LBO, a_hi = (flags & DF_NK1) ? HI_A1 : HI_A4;
+          const uint32_t b_lo = ((s0_lo + (cur ? (r.y & 0xffffu) : (r.x >> 16))) & 0x3fffu) | LBO, b_hi = (flags & DF_B_COND) ? HI_BQ : HI_BH;
           const uint32_t d_col = tmem + acc * NF;
           mma4(d_col, a_lo, a_hi, b_lo, b_hi, (flags & DF_FIRST) ? 0u : 1u, (flags & DF_NK1) != 0);
-          if (flags & DF_HAS_B2) mma4(d_col, a_lo, a_hi, (s0_lo + (cur ? (r.z & 0xffffu) : (r.y >> 16))) | LBO, HI_BH, 1u, false);
+          if (flags & DF_HAS_B2) mma4(d_col, a_lo, a_hi, ((s0_lo + (cur ? (r.z & 0xffffu) : (r.y >> 16))) & 0x3fffu) | LBO, HI_BH, 1u, false);
           if (commit) umma_commit(bar(BAR_ACC_FULL + commit - 1));
           if (flags & DF_COND_RELEASE) umma_commit(bar(BAR_COND_FREE + cur));
           if (j == 1 || SM::CPS == 1) umma_commit(bar(BAR_EMPTY + slot));
@@ -347,14 +395,38 @@ __global__ void __launch_bounds__(NT, 1) wrnn_stream_kernel(const StreamParams p
       tc_fence_before();
       asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar(BAR_ACC_EMPTY + blk)) : "memory");
     };
-    auto publish_ready = [&](int kind, int blk) {                 // this thread's part of operand `kind`, unit block `blk`, is written
-      proxy_fence_smem();
-      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar(BAR_READY + 2 + (kind - W_H1NEW) * 4 + blk)) : "memory");
+    // this thread's part of operand `kind`, unit block `blk` (GLOBAL block id), is written -- in the cluster form into all four
+    // CTAs' images, so all four are told (release at cluster scope; the proxy fence orders the generic stores, local and
+    // remote, before the peers' tensor-core reads)
+    auto publish_ready = [&](int kind, int blk) {
+      const uint32_t b = bar(BAR_READY + 2 + (kind - W_H1NEW) * 4 + blk);
+      if constexpr (CL == 1) {
+        proxy_fence_smem();
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(b) : "memory");
+      } else {
+        asm volatile("fence.acq_rel.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async;" ::: "memory");
+#pragma unroll
+        for (int r = 0; r < CL; ++r)
+          asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" :: "r"(map_to_rank(b, (uint32_t)r)) : "memory");
+      }
     };
     // element (fold f, unit k) of a K = 512 operand image
     auto img_ptr = [&](int off, int f, int k) -> uint16_t* {
       return reinterpret_cast<uint16_t*>(smem + off + (f >> 3) * SBO_H + (k >> 3) * 128 + (f & 7) * 16 + (k & 7) * 2);
     };
+    // store it: locally, or (cluster form) into the same place of every CTA of the cluster
+    auto img_store = [&](int off, int f, int k, uint16_t bits) {
+      if constexpr (CL == 1) {
+        *img_ptr(off, f, k) = bits;
+      } else {
+        const uint32_t a = smem_u32(img_ptr(off, f, k));
+#pragma unroll
+        for (int r = 0; r < CL; ++r)
+          asm volatile("st.shared::cluster.u16 [%0], %1;" :: "r"(map_to_rank(a, (uint32_t)r)), "h"(bits) : "memory");
+      }
+    };
+    constexpr int NBLK = (CL == 1) ? 4 : 1;                      // unit blocks this CTA computes: all four, or block `rank`
     auto to_bits = [&](float v) -> uint16_t { return (uint16_t)(pack2<FMT>(v, 0.f) & 0xffffu); };
 
     volatile int* ep_stop = s_abort + 1;                      // the epilogue warps leave the loop together (named barrier inside)
@@ -363,14 +435,16 @@ __global__ void __launch_bounds__(NT, 1) wrnn_stream_kernel(const StreamParams p
     for (int t = 0; t < S; ++t) {
       const int cur = t & 1;
       const int off_h1new = cur ? SM::OFF_X0 : SM::OFF_X1, off_y1 = cur ? SM::OFF_X1 : SM::OFF_X0;
+      const int off_h2new = (CL == 1) ? SM::OFF_H2 : (cur ? SM::OFF_H2 : SM::OFF_H2B);        // in place, or H[cur^1]
+      const int off_y2 = (CL == 1) ? off_y1 : (cur ? SM::OFF_H2B : SM::OFF_H2);                 // over y1 (deferred), or H[cur]
       long long w0 = 0;
       if (profiling) w0 = clock64();
       // draws of this step for the fold this thread samples (threads of lane quarter 0, lane < B)
       float ur[11];
 #pragma unroll
       for (int i = 0; i < 11; ++i) ur[i] = 0.5f;
-      const bool sampler = (warp & 3) == 0 && lane < B;
-      if (p.uniforms && (warp & 3) == 0) {                     // streamed draws: read row t once rows t .. t+3 have landed (see wrnn_tc.cu)
+      const bool sampler = rank == 0 && (warp & 3) == 0 && lane < B;
+      if (p.uniforms && rank == 0 && (warp & 3) == 0) {        // streamed draws: read row t once rows t .. t+3 have landed (see wrnn_tc.cu)
         const unsigned need = min((unsigned)S, (unsigned)t + 4u);
         if (rows_known < need) rows_known = rows_wait(p.uniforms_ready, need, p.abort_flag);
       }
@@ -397,9 +471,10 @@ __global__ void __launch_bounds__(NT, 1) wrnn_stream_kernel(const StreamParams p
         float* st = cell ? st_h2 : st_h1;
         const float* bh = cell ? p.b2h : p.b1h;
         const int qbase = cell * 3 * H;                        // rows of qk / vq: gi1 = 0.., gi2 = 3H..
-        const int off_out = cell ? SM::OFF_H2 : off_h1new;
+        const int off_out = cell ? off_h2new : off_h1new;
 #pragma unroll 1
-        for (int b = 0; b < 4; ++b) {
+        for (int ba = 0; ba < NBLK; ++ba) {                    // ba: accumulator / barrier block in this CTA; b: unit block of the layer
+          const int b = (CL == 1) ? ba : rank;
           const int u = b * MROWS + row;
           const float qk_r = __ldg(p.qk + qbase + u), qk_z = __ldg(p.qk + qbase + H + u), qk_n = __ldg(p.qk + qbase + 2 * H + u);
           const float vq_r = __ldg(p.vq + qbase + u), vq_z = __ldg(p.vq + qbase + H + u), vq_n = __ldg(p.vq + qbase + 2 * H + u);
@@ -416,16 +491,16 @@ __global__ void __launch_bounds__(NT, 1) wrnn_stream_kernel(const StreamParams p
 #pragma unroll
             for (int i = 0; i < NF; ++i) hp[i] = 0.f;
           }
-          wait_full(b);
+          wait_full(ba);
 #pragma unroll
           for (int half = 0; half < NF / 16; ++half) {
             float ar[16], az[16], ai[16], ah[16];
-            tmem_ld16(tlane + (4 * b + 0) * NF + half * 16, ar);
-            tmem_ld16(tlane + (4 * b + 1) * NF + half * 16, az);
-            tmem_ld16(tlane + (4 * b + 2) * NF + half * 16, ai);
-            tmem_ld16(tlane + (4 * b + 3) * NF + half * 16, ah);
+            tmem_ld16(tlane + (4 * ba + 0) * NF + half * 16, ar);
+            tmem_ld16(tlane + (4 * ba + 1) * NF + half * 16, az);
+            tmem_ld16(tlane + (4 * ba + 2) * NF + half * 16, ai);
+            tmem_ld16(tlane + (4 * ba + 3) * NF + half * 16, ah);
             tmem_ld_wait();
-            if (half == NF / 16 - 1) release_acc(b);
+            if (half == NF / 16 - 1) release_acc(ba);
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
               const int f = half * 16 + i;
@@ -434,7 +509,7 @@ __global__ void __launch_bounds__(NT, 1) wrnn_stream_kernel(const StreamParams p
                                             bh_r, bh_z, ah[i] + bh_n, hp[f]);
               // (the recurrent r / z contributions are already inside ar / az: one accumulator per gate)
               hp[f] = h;
-              *img_ptr(off_out, f, u) = to_bits(h);
+              img_store(off_out, f, u, to_bits(h));
             }
           }
 #pragma unroll
@@ -448,23 +523,24 @@ __global__ void __launch_bounds__(NT, 1) wrnn_stream_kernel(const StreamParams p
       {
         const int qbase = 6 * H;
 #pragma unroll 1
-        for (int b = 0; b < 4; ++b) {
+        for (int ba = 0; ba < NBLK; ++ba) {
+          const int b = (CL == 1) ? ba : rank;
           const int u = b * MROWS + row;
           const float qk_u = __ldg(p.qk + qbase + u), vq_u = __ldg(p.vq + qbase + u);
-          wait_full(b);
+          wait_full(ba);
 #pragma unroll
           for (int half = 0; half < NF / 16; ++half) {
             float a[16], a1[16], a2[16], a3[16];                // the four K-quarter partials (one per issuing warp)
-            tmem_ld16(tlane + (4 * b + 0) * NF + half * 16, a);
-            tmem_ld16(tlane + (4 * b + 1) * NF + half * 16, a1);
-            tmem_ld16(tlane + (4 * b + 2) * NF + half * 16, a2);
-            tmem_ld16(tlane + (4 * b + 3) * NF + half * 16, a3);
+            tmem_ld16(tlane + (4 * ba + 0) * NF + half * 16, a);
+            tmem_ld16(tlane + (4 * ba + 1) * NF + half * 16, a1);
+            tmem_ld16(tlane + (4 * ba + 2) * NF + half * 16, a2);
+            tmem_ld16(tlane + (4 * ba + 3) * NF + half * 16, a3);
             tmem_ld_wait();
-            if (half == NF / 16 - 1) release_acc(b);
+            if (half == NF / 16 - 1) release_acc(ba);
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
               const int f = half * 16 + i;
-              *img_ptr(off_y1, f, u) = to_bits(fmaxf(((a[i] + a1[i]) + (a2[i] + a3[i])) + qk_u + x_s[f] * vq_u, 0.f));
+              img_store(off_y1, f, u, to_bits(fmaxf(((a[i] + a1[i]) + (a2[i] + a3[i])) + qk_u + x_s[f] * vq_u, 0.f)));
             }
           }
           publish_ready(W_Y1, b);
@@ -474,6 +550,7 @@ __global__ void __launch_bounds__(NT, 1) wrnn_stream_kernel(const StreamParams p
       // held in registers (packed pairs) until block 3's block-full, i.e. until every fc2 MMA of every issuing warp has
       // completed (each warp's block-3 commit follows its chunks of blocks 0-2), and written then.  One image saved =
       // two more ring slots for the weight stream.
+      if constexpr (CL == 1)
       {
         const int qbase = 7 * H;
         uint32_t ypk[4][NF / 2];
@@ -506,12 +583,13 @@ __global__ void __launch_bounds__(NT, 1) wrnn_stream_kernel(const StreamParams p
             *img_ptr(off_y1, 2 * i + 1, b * MROWS + row) = (uint16_t)(ypk[b][i] >> 16);
           }
         }
-        publish_ready(W_Y2, 0);
+#pragma unroll
+        for (int b = 0; b < 4; ++b) publish_ready(W_Y2, b);
       }
-
-      // ---- P5: logits -> transpose through shared memory -> one thread per fold samples ----------------------------
-      wait_full(0);
-      if ((warp & 3) == 0) {
+      else {                                                     // cluster form: y2 has its own place (the stale h2 image), nothing to defer
+        const int u = rank * MROWS + row;
+        const float qk_u = __ldg(p.qk + 7 * H + u);
+        wait_full(0);
 #pragma unroll
         for (int half = 0; half < NF / 16; ++half) {
           float a[16], a1[16], a2[16], a3[16];
@@ -520,33 +598,70 @@ __global__ void __launch_bounds__(NT, 1) wrnn_stream_kernel(const StreamParams p
           tmem_ld16(tlane + 2 * NF + half * 16, a2);
           tmem_ld16(tlane + 3 * NF + half * 16, a3);
           tmem_ld_wait();
+          if (half == NF / 16 - 1) release_acc(0);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) a[i] = (a[i] + a1[i]) + (a2[i] + a3[i]);
-          const float b3 = __ldg(p.b3 + row);
-#pragma unroll
-          for (int i = 0; i < 16; ++i) log_s[(half * 16 + i) * SM::LOGP + lane] = a[i] + b3;   // [fold][class], class == lane
+          for (int i = 0; i < 16; ++i) img_store(off_y2, half * 16 + i, u, to_bits(fmaxf(((a[i] + a1[i]) + (a2[i] + a3[i])) + qk_u, 0.f)));
         }
+        publish_ready(W_Y2, rank);                               // each CTA delivers ITS block of y2; rank 0's fc3 chunks wait per block
       }
-      release_acc(0);
-      if ((warp & 3) == 0) {
-        __syncwarp();
-        float xnew = 0.f;
-        if (sampler) {
-          float lgo[32];
+
+      // ---- P5: logits -> transpose through shared memory -> one thread per fold samples ----------------------------
+      // (cluster form: fc3 lives in rank 0 only; it samples and hands x to the other three CTAs)
+      if (rank == 0) {
+        wait_full(0);
+        if ((warp & 3) == 0) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) lgo[i] = log_s[lane * SM::LOGP + i];
-          xnew = mol_sample_fast(lgo, ur);
-          const int gf = f0 + lane;
-          p.out[(size_t)gf * p.out_pitch + t] = xnew;
-          if (p.logits_out) {
+          for (int half = 0; half < NF / 16; ++half) {
+            float a[16], a1[16], a2[16], a3[16];
+            tmem_ld16(tlane + 0 * NF + half * 16, a);
+            tmem_ld16(tlane + 1 * NF + half * 16, a1);
+            tmem_ld16(tlane + 2 * NF + half * 16, a2);
+            tmem_ld16(tlane + 3 * NF + half * 16, a3);
+            tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 30; ++i) p.logits_out[((size_t)t * p.n_total + gf) * 30 + i] = lgo[i];
+            for (int i = 0; i < 16; ++i) a[i] = (a[i] + a1[i]) + (a2[i] + a3[i]);
+            const float b3 = __ldg(p.b3 + row);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) log_s[(half * 16 + i) * SM::LOGP + lane] = a[i] + b3;   // [fold][class], class == lane
           }
-          if (p.x_force) xnew = __ldg(p.x_force + (size_t)t * p.n_total + gf);               // teacher forcing: step t+1 consumes x_force[t]
         }
-        __syncwarp();
-        if (lane < NF) x_s[lane] = xnew;
+        release_acc(0);
+        if ((warp & 3) == 0) {
+          __syncwarp();
+          float xnew = 0.f;
+          if (sampler) {
+            float lgo[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) lgo[i] = log_s[lane * SM::LOGP + i];
+            xnew = mol_sample_fast(lgo, ur);
+            const int gf = f0 + lane;
+            p.out[(size_t)gf * p.out_pitch + t] = xnew;
+            if (p.logits_out) {
+#pragma unroll
+              for (int i = 0; i < 30; ++i) p.logits_out[((size_t)t * p.n_total + gf) * 30 + i] = lgo[i];
+            }
+            if (p.x_force) xnew = __ldg(p.x_force + (size_t)t * p.n_total + gf);             // teacher forcing: step t+1 consumes x_force[t]
+          }
+          __syncwarp();
+          if constexpr (CL == 1) {
+            if (lane < NF) x_s[lane] = xnew;
+          } else {
+            if (lane < NF) {
+              const uint32_t a = smem_u32(x_s + lane);
+#pragma unroll
+              for (int r = 0; r < CL; ++r)
+                asm volatile("st.shared::cluster.f32 [%0], %1;" :: "r"(map_to_rank(a, (uint32_t)r)), "f"(xnew) : "memory");
+            }
+            __syncwarp();
+            if (lane == 0) {
+#pragma unroll
+              for (int r = 0; r < CL; ++r)
+                asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" :: "r"(map_to_rank(bar(BAR_X), (uint32_t)r)) : "memory");
+            }
+          }
+        }
       }
+      if constexpr (CL > 1) wait_peer(bar(BAR_X), (uint32_t)t & 1);   // every epilogue thread of the cluster: x of this step has landed here
       if (tid == EPI_TID0) *ep_stop = *s_abort;
       named_bar_sync(1, 128);                                  // x of this step (and the stop decision) visible to all epilogue threads
       if (profiling) t_work += clock64() - w0;
@@ -557,6 +672,7 @@ __global__ void __launch_bounds__(NT, 1) wrnn_stream_kernel(const StreamParams p
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (CL > 1) cluster_sync_all();                  // nobody leaves while a peer may still write into its shared memory
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "n"(TMEM_COLS));
 }
 
@@ -567,43 +683,73 @@ class StreamEngine : public Engine {
  public:
   ~StreamEngine() override {
     cudaSetDevice(device);
-    cudaFree(d_blob_); cudaFree(d_prog_[0]); cudaFree(d_prog_[1]); cudaFree(d_pairs_); cudaFree(d_vec_); cudaFree(d_state_); cudaFree(d_sync_);
+    for (auto& v : var_) { cudaFree(v.d_blob); cudaFree(v.d_prog); cudaFree(v.d_sizes); }
+    cudaFree(d_vec_); cudaFree(d_state_); cudaFree(d_sync_);
   }
-  const char* name() const override { return cfg.precision == WRNN_PREC_BF16 ? "tcgen05-stream-bf16" : "tcgen05-stream-fp16"; }
+  const char* name() const override {
+    if (last_cluster_) return cfg.precision == WRNN_PREC_BF16 ? "tcgen05-stream-x4-bf16" : "tcgen05-stream-x4-fp16";
+    return cfg.precision == WRNN_PREC_BF16 ? "tcgen05-stream-bf16" : "tcgen05-stream-fp16";
+  }
   int grid_ctas() const override { return last_grid_; }
 
-  template <int NF, bool PROF> const void* kernel_p(bool frames) const {
-    if (cfg.precision == WRNN_PREC_BF16) return frames ? (const void*)wrnn_stream_kernel<NF, 1, true, PROF> : (const void*)wrnn_stream_kernel<NF, 1, false, PROF>;
-    return frames ? (const void*)wrnn_stream_kernel<NF, 0, true, PROF> : (const void*)wrnn_stream_kernel<NF, 0, false, PROF>;
+  template <int NF, int CL, bool PROF> const void* kernel_p(bool frames) const {
+    if (cfg.precision == WRNN_PREC_BF16) return frames ? (const void*)wrnn_stream_kernel<NF, 1, true, PROF, CL> : (const void*)wrnn_stream_kernel<NF, 1, false, PROF, CL>;
+    return frames ? (const void*)wrnn_stream_kernel<NF, 0, true, PROF, CL> : (const void*)wrnn_stream_kernel<NF, 0, false, PROF, CL>;
   }
-  template <int NF> const void* kernel_nf(bool frames, bool prof) const { return prof ? kernel_p<NF, true>(frames) : kernel_p<NF, false>(frames); }
-  template <int NF> static SmemLayout layout() { return SmemLayout{Smem<NF>::OFF_X0, Smem<NF>::OFF_X1, Smem<NF>::OFF_H2, Smem<NF>::OFF_COND, Smem<NF>::COND}; }
+  template <int NF, int CL> const void* kernel_nf(bool frames, bool prof) const { return prof ? kernel_p<NF, CL, true>(frames) : kernel_p<NF, CL, false>(frames); }
+  template <int NF, int CL> static SmemLayout layout() {
+    using S = Smem<NF, CL>;
+    return SmemLayout{S::OFF_X0, S::OFF_X1, {S::OFF_H2, S::OFF_H2B}, S::OFF_COND, S::COND, S::CPS, CL > 1};
+  }
+
+  // one (cluster size, folds per CTA) combination: its weight streams (one per cluster rank), device programs and kernel
+  struct Variant {
+    int nf = 0, cl = 1, smem = 0;
+    void *d_blob = nullptr, *d_prog = nullptr, *d_sizes = nullptr;
+    size_t blob_off[4] = {0, 0, 0, 0}, prog_off[4][N_ISSUERS] = {}, sizes_off[4] = {0, 0, 0, 0};
+    int n_mine[4][N_ISSUERS] = {}, n_slots[4] = {0, 0, 0, 0};
+  };
+
+  int upload(Variant& v, const std::vector<Plan>& plans, const SmemLayout& L) {
+    std::vector<uint8_t> blob; std::vector<DevChunk> prog; std::vector<uint16_t> sizes;
+    for (size_t r = 0; r < plans.size(); ++r) {
+      const Plan& pl = plans[r];
+      if (L.cps == 2) {
+        if (pl.prog.size() % 2) { set_error("stream plan: odd chunk count"); return WRNN_E_INVALID; }
+        for (size_t i = 0; i < pl.prog.size(); i += 2)
+          if (pl.prog[i].owner != pl.prog[i + 1].owner) { set_error("stream plan: a chunk pair with two owners"); return WRNN_E_INVALID; }
+      }
+      for (int o = 0; o < N_ISSUERS; ++o)
+        if (pl.mine[o].size() % 2) { set_error("stream plan: an issuing warp with an odd number of chunks"); return WRNN_E_INVALID; }
+      DevProgram dp;
+      compile_device(pl, L, dp);
+      v.blob_off[r] = blob.size(); blob.insert(blob.end(), pl.blob.begin(), pl.blob.end());
+      while (blob.size() % 16) blob.push_back(0);
+      for (int o = 0; o < N_ISSUERS; ++o) { v.prog_off[r][o] = prog.size(); v.n_mine[r][o] = (int)dp.mine[o].size(); prog.insert(prog.end(), dp.mine[o].begin(), dp.mine[o].end()); }
+      const std::vector<uint16_t>& sz = L.cps == 2 ? dp.pair_size16 : dp.chunk_size16;
+      v.sizes_off[r] = sizes.size(); v.n_slots[r] = (int)sz.size(); sizes.insert(sizes.end(), sz.begin(), sz.end());
+    }
+    WRNN_CUDA_OK(cudaMalloc(&v.d_blob, blob.size()));
+    WRNN_CUDA_OK(cudaMemcpy(v.d_blob, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+    WRNN_CUDA_OK(cudaMalloc(&v.d_prog, prog.size() * sizeof(DevChunk)));
+    WRNN_CUDA_OK(cudaMemcpy(v.d_prog, prog.data(), prog.size() * sizeof(DevChunk), cudaMemcpyHostToDevice));
+    WRNN_CUDA_OK(cudaMalloc(&v.d_sizes, sizes.size() * sizeof(uint16_t)));
+    WRNN_CUDA_OK(cudaMemcpy(v.d_sizes, sizes.data(), sizes.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    return WRNN_OK;
+  }
 
   int init(const HostWeights& w) {
-    Plan plan;
-    build_plan(w, cfg.precision == WRNN_PREC_BF16, plan);
-    n_chunks_ = (int)plan.prog.size(); n_mma_ = plan.n_mma;
-    WRNN_CUDA_OK(cudaMalloc(&d_blob_, plan.blob.size()));
-    WRNN_CUDA_OK(cudaMemcpy(d_blob_, plan.blob.data(), plan.blob.size(), cudaMemcpyHostToDevice));
-    if (plan.prog.size() % 2) { set_error("stream plan: odd chunk count"); return WRNN_E_INVALID; }
-    for (size_t i = 0; i < plan.prog.size(); i += 2)
-      if (plan.prog[i].owner != plan.prog[i + 1].owner) { set_error("stream plan: a chunk pair with two owners"); return WRNN_E_INVALID; }
-    n_pairs_ = (int)plan.prog.size() / 2;
-    // device programs for the two shared-memory layouts (folds per CTA)
-    for (int v = 0; v < 2; ++v) {
-      DevProgram dp;
-      compile_device(plan, v == 0 ? layout<16>() : layout<32>(), dp);
-      std::vector<DevChunk> all;
-      for (int o = 0; o < N_ISSUERS; ++o) { off_mine_[v][o] = all.size(); n_mine_[o] = (int)dp.mine[o].size(); all.insert(all.end(), dp.mine[o].begin(), dp.mine[o].end()); }
-      WRNN_CUDA_OK(cudaMalloc(&d_prog_[v], all.size() * sizeof(DevChunk)));
-      WRNN_CUDA_OK(cudaMemcpy(d_prog_[v], all.data(), all.size() * sizeof(DevChunk), cudaMemcpyHostToDevice));
-      if (v == 0) {          // TMA sizes for both ring granularities: pairs first, then single chunks
-        std::vector<uint16_t> sizes(dp.pair_size16);
-        sizes.insert(sizes.end(), dp.chunk_size16.begin(), dp.chunk_size16.end());
-        WRNN_CUDA_OK(cudaMalloc(&d_pairs_, sizes.size() * sizeof(uint16_t)));
-        WRNN_CUDA_OK(cudaMemcpy(d_pairs_, sizes.data(), sizes.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
-      }
-    }
+    const bool bf = cfg.precision == WRNN_PREC_BF16;
+    std::vector<Plan> whole(1), split(4);
+    build_plan(w, bf, whole[0]);
+    for (int r = 0; r < 4; ++r) build_plan(w, bf, split[r], r);
+    n_chunks_ = (int)whole[0].prog.size(); n_mma_ = whole[0].n_mma;
+    int rc;
+    var_[0].nf = 16; var_[0].cl = 1; var_[0].smem = Smem<16, 1>::BYTES; if ((rc = upload(var_[0], whole, layout<16, 1>())) != WRNN_OK) return rc;
+    var_[1].nf = 32; var_[1].cl = 1; var_[1].smem = Smem<32, 1>::BYTES; if ((rc = upload(var_[1], whole, layout<32, 1>())) != WRNN_OK) return rc;
+    var_[2].nf = 16; var_[2].cl = 4; var_[2].smem = Smem<16, 4>::BYTES; if ((rc = upload(var_[2], split, layout<16, 4>())) != WRNN_OK) return rc;
+    var_[3].nf = 32; var_[3].cl = 4; var_[3].smem = Smem<32, 4>::BYTES; if ((rc = upload(var_[3], split, layout<32, 4>())) != WRNN_OK) return rc;
+    const Plan& plan = whole[0];
     std::vector<float> vec;
     off_qk_ = 0; vec.insert(vec.end(), plan.qk.begin(), plan.qk.end());
     off_vq_ = vec.size(); vec.insert(vec.end(), plan.vq.begin(), plan.vq.end());
@@ -614,9 +760,12 @@ class StreamEngine : public Engine {
     WRNN_CUDA_OK(cudaMemcpy(d_vec_, vec.data(), vec.size() * sizeof(float), cudaMemcpyHostToDevice));
     WRNN_CUDA_OK(cudaMalloc(&d_sync_, 256));
     WRNN_CUDA_OK(cudaMemset(d_sync_, 0, 256));
-    for (int v = 0; v < 4; ++v) {
-      WRNN_CUDA_OK(cudaFuncSetAttribute(kernel_nf<16>((v & 1) != 0, (v & 2) != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<16>::BYTES));
-      WRNN_CUDA_OK(cudaFuncSetAttribute(kernel_nf<32>((v & 1) != 0, (v & 2) != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<32>::BYTES));
+    for (int k = 0; k < 4; ++k) {
+      const bool fr = (k & 1) != 0, pr = (k & 2) != 0;
+      WRNN_CUDA_OK(cudaFuncSetAttribute(kernel_nf<16, 1>(fr, pr), cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<16, 1>::BYTES));
+      WRNN_CUDA_OK(cudaFuncSetAttribute(kernel_nf<32, 1>(fr, pr), cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<32, 1>::BYTES));
+      WRNN_CUDA_OK(cudaFuncSetAttribute(kernel_nf<16, 4>(fr, pr), cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<16, 4>::BYTES));
+      WRNN_CUDA_OK(cudaFuncSetAttribute(kernel_nf<32, 4>(fr, pr), cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<32, 4>::BYTES));
     }
     WRNN_CUDA_OK(cudaDeviceGetAttribute(&n_sm_, cudaDevAttrMultiProcessorCount, device));
     return WRNN_OK;
@@ -627,11 +776,25 @@ class StreamEngine : public Engine {
   }
   bool supports(const wrnn_job& job) const override { return job.expo == nullptr && !(job.mel_frames && job.cond_mode == WRNN_COND_EXPAND && job.fold_row0); }
 
+  // Which form serves n folds (per-step times measured on B200, profiles/r02_stream.md):
+  //   one CTA per tile : ~66 us (16 folds per CTA, <= 148 tiles), ~95 us (32 folds per CTA) per wave of 148 tiles
+  //   cluster of 4     : the rows of every layer split over four CTAs -> a quarter of the stream per SM; used while the
+  //                      clusters of the job are co-resident (33 clusters of 4 with this shared-memory footprint)
+  void choose(int n_seg, int& nf, int& cl) const {
+    const int max_cl = (n_sm_ / 4) - 4;            // 33 on a 148-SM part (GPC granularity), measured with cudaOccupancyMaxActiveClusters
+    if ((n_seg + 15) / 16 <= max_cl) { nf = 16; cl = 4; }
+    else if ((n_seg + 31) / 32 <= max_cl) { nf = 32; cl = 4; }
+    else if ((n_seg + 15) / 16 <= n_sm_) { nf = 16; cl = 1; }
+    else { nf = 32; cl = 1; }
+    if (const char* e = getenv("WRNN_STREAM_NF")) { const int v = atoi(e); if (v == 16 || v == 32) nf = v; }   // experiments
+    if (const char* e = getenv("WRNN_STREAM_CL")) { const int v = atoi(e); if (v == 1 || v == 4) cl = v; }
+  }
+
   int generate(const wrnn_job& job, cudaStream_t stream) override {
     WRNN_CUDA_OK(cudaSetDevice(device));
-    // folds per CTA: 16 while that still gives every tile its own SM, else 32 (twice the folds per streamed byte)
-    int nf = ((job.n_seg + 15) / 16 <= n_sm_) ? 16 : 32;
-    if (const char* e = getenv("WRNN_STREAM_NF")) { const int v = atoi(e); if (v == 16 || v == 32) nf = v; }   // experiments
+    int nf = 16, cl = 1;
+    choose(job.n_seg, nf, cl);
+    const Variant& V = var_[(cl == 4 ? 2 : 0) + (nf == 32 ? 1 : 0)];
     const int tiles = (job.n_seg + nf - 1) / nf;
     const size_t need = (size_t)tiles * 2 * H * nf * sizeof(float);
     if (need > state_bytes_) {
@@ -641,11 +804,12 @@ class StreamEngine : public Engine {
     }
     StreamParams p{};
     const float* v = static_cast<const float*>(d_vec_);
-    p.blob = static_cast<const unsigned char*>(d_blob_); p.n_pairs = n_pairs_;
-    const bool pair_slots = nf == 16 ? Smem<16>::CPS == 2 : Smem<32>::CPS == 2;
-    p.slot_size16 = static_cast<const unsigned short*>(d_pairs_) + (pair_slots ? 0 : n_pairs_);
-    p.n_slots = pair_slots ? n_pairs_ : 2 * n_pairs_;
-    for (int o = 0; o < N_ISSUERS; ++o) { p.mine[o] = static_cast<const uint4*>(d_prog_[nf == 16 ? 0 : 1]) + off_mine_[nf == 16 ? 0 : 1][o]; p.n_mine[o] = n_mine_[o]; }
+    for (int r = 0; r < cl; ++r) {
+      p.blob[r] = static_cast<const unsigned char*>(V.d_blob) + V.blob_off[r];
+      p.slot_size16[r] = static_cast<const unsigned short*>(V.d_sizes) + V.sizes_off[r];
+      p.n_slots[r] = V.n_slots[r];
+      for (int o = 0; o < N_ISSUERS; ++o) { p.mine[r * N_ISSUERS + o] = static_cast<const uint4*>(V.d_prog) + V.prog_off[r][o]; p.n_mine[r * N_ISSUERS + o] = V.n_mine[r][o]; }
+    }
     p.qk = v + off_qk_; p.vq = v + off_vq_; p.b1h = v + off_b1h_; p.b2h = v + off_b2h_; p.b3 = v + off_b3_;
     p.mels_up = job.mels_up; p.aux = job.aux; p.L = job.L; p.seg_stride = job.seg_stride; p.row_base = 0;
     p.n_total = job.n_seg; p.steps = job.steps > 0 ? job.steps : job.seg_len; p.out_pitch = p.steps; p.seg_first = job.seg_first;
@@ -658,12 +822,17 @@ class StreamEngine : public Engine {
     const bool prof = getenv("WRNN_STREAM_PROF") != nullptr;
     p.prof = reinterpret_cast<long long*>(static_cast<unsigned char*>(d_sync_) + 64);
     const bool frames = job.mel_frames != nullptr;             // rows are formed by the staging warps (no scratch of size L)
-    const void* fn = nf == 16 ? kernel_nf<16>(frames, prof) : kernel_nf<32>(frames, prof);
-    const int smem = nf == 16 ? Smem<16>::BYTES : Smem<32>::BYTES;
+    const void* fn = cl == 4 ? (nf == 16 ? kernel_nf<16, 4>(frames, prof) : kernel_nf<32, 4>(frames, prof))
+                             : (nf == 16 ? kernel_nf<16, 1>(frames, prof) : kernel_nf<32, 1>(frames, prof));
     void* args[] = {&p};
-    WRNN_CUDA_OK(cudaLaunchKernel(fn, dim3(tiles), dim3(NT), args, smem, stream));
+    cudaLaunchConfig_t lc{};
+    lc.gridDim = dim3(tiles * cl); lc.blockDim = dim3(NT); lc.dynamicSmemBytes = V.smem; lc.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = cl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    lc.attrs = at; lc.numAttrs = cl > 1 ? 1 : 0;
+    WRNN_CUDA_OK(cudaLaunchKernelExC(&lc, fn, args));
     ++launches;
-    last_grid_ = tiles; last_steps_ = p.steps; last_nf_ = nf;
+    last_grid_ = tiles * cl; last_steps_ = p.steps; last_nf_ = nf; last_cluster_ = cl > 1;
     return WRNN_OK;
   }
 
@@ -675,19 +844,20 @@ class StreamEngine : public Engine {
     if (getenv("WRNN_STREAM_PROF") && last_steps_ > 0) {
       long long prof[16]; std::memcpy(prof, buf + 64, sizeof(prof));
       const long long n = last_steps_;
-      fprintf(stderr, "[wrnn_stream prof] NF=%d tiles=%d steps=%d mma/step=%d chunks/step=%d | issuer 0: acc-wait=%lld operand-wait=%lld ring-wait=%lld "
+      fprintf(stderr, "[wrnn_stream prof] NF=%d cluster=%d CTAs=%d steps=%d mma/step=%d chunks/step=%d | issuer 0: acc-wait=%lld operand-wait=%lld ring-wait=%lld "
               "issue=%lld | epilogue thread: mma-wait=%lld step=%lld (cycles per step)\n",
-              last_nf_, last_grid_, last_steps_, n_mma_, n_chunks_, prof[0] / n, prof[1] / n, prof[2] / n, prof[3] / n, prof[4] / n, prof[5] / n);
+              last_nf_, last_cluster_ ? 4 : 1, last_grid_, last_steps_, n_mma_, n_chunks_, prof[0] / n, prof[1] / n, prof[2] / n, prof[3] / n, prof[4] / n, prof[5] / n);
     }
     if (flag != 0) { set_error("stream kernel aborted: an mbarrier wait (TMA / MMA / operand hand-off) timed out"); return WRNN_E_WATCHDOG; }
     return WRNN_OK;
   }
 
  private:
-  void *d_blob_ = nullptr, *d_prog_[2] = {nullptr, nullptr}, *d_pairs_ = nullptr, *d_vec_ = nullptr, *d_state_ = nullptr, *d_sync_ = nullptr;
-  size_t off_mine_[2][N_ISSUERS] = {{0, 0, 0, 0}, {0, 0, 0, 0}}; int n_mine_[N_ISSUERS] = {0, 0, 0, 0}; int n_pairs_ = 0;
+  Variant var_[4];
+  void *d_vec_ = nullptr, *d_state_ = nullptr, *d_sync_ = nullptr;
   size_t state_bytes_ = 0, off_qk_ = 0, off_vq_ = 0, off_b1h_ = 0, off_b2h_ = 0, off_b3_ = 0;
   int n_chunks_ = 0, n_mma_ = 0, n_sm_ = 0, last_grid_ = 0, last_steps_ = 0, last_nf_ = 0;
+  bool last_cluster_ = false;
 };
 
 }  // namespace

@@ -54,7 +54,8 @@ struct Chunk {            // 16 bytes, read as one uint4
   uint16_t k0;            // K offset of the chunk inside the B image (elements)
   uint8_t flags;          // F_FIRST: first MMA of the accumulator in this phase overwrites; F_COND_RELEASE: this issuer's last cond read
   uint8_t wait_b;         // W_* | block << 4: readiness barrier to wait for before issuing.  h1', h2' and y1 become ready BLOCK by
-                          // block (128 units = 128 K columns each): a chunk waits only for the block its K range reads
+                          // block (128 units = 128 K columns each), y2 too (in the cluster form each CTA delivers its own block): a chunk waits only for
+                          // the block its K range reads
   uint8_t wait_acc;       // 0, or block + 1: first chunk of this issuer in (phase, block): the previous phase's epilogue must have drained the block
   uint8_t commit;         // 0, or block + 1: last chunk of this issuer in (phase, block): signal "my accumulators of the block are full"
   uint8_t owner;          // issuing warp 0..3
@@ -85,7 +86,10 @@ inline size_t tile_index(int r, int k, int kc) { return (size_t)(r / 8) * (kc / 
 //                recurrent operand, into its own partial accumulator 4b + q (the epilogue adds the four partials)
 // Stream order: the chains of one (phase, block) are interleaved round-robin, so consecutive ring slots go to different
 // warps; within P2 everything that does not depend on h1' is issued (for all blocks) before the W2x h1' chunks.
-inline void build_plan(const HostWeights& w, bool bf, Plan& p) {
+// `only_block` >= 0 builds the program of ONE 128-unit block of every layer (accumulators 0..3, block id 0 in the barrier
+// fields, fc3 only for block 0): the share of CTA `only_block` of a 4-CTA cluster that splits the rows of every layer
+// (wrnn_stream.cu, cluster form).  Operand readiness codes (wait_b) keep the GLOBAL block of the K range they read.
+inline void build_plan(const HostWeights& w, bool bf, Plan& p, int only_block = -1) {
   Folded f; fold(w, f);
   CtaSlice s; slice_for_cta(w, f, 0, H, s);          // P = 1: the dense matrices in the row order documented in wrnn_fold.h
   auto cvt = [&](double v) -> uint16_t { return bf ? f2bf((float)v) : f2h((float)v); };
@@ -115,7 +119,7 @@ inline void build_plan(const HostWeights& w, bool bf, Plan& p) {
       c.size16 = (uint16_t)(MROWS * kc * 2 / 16); c.a_off16 = 0; c.acc = acc; c.nk = (uint8_t)(kc / 16); c.b_buf = b_buf; c.b_buf2 = b_buf2;
       c.k0 = (uint16_t)k0; c.flags = first ? F_FIRST : 0; c.wait_acc = fresh[owner] ? (uint8_t)(blk + 1) : 0;
       c.wait_b = wait_b;
-      if (wait_b == W_H1NEW || wait_b == W_H2NEW || wait_b == W_Y1) c.wait_b = (uint8_t)(wait_b | ((k0 / MROWS) << 4));   // per-block readiness
+      if (wait_b >= W_H1NEW) c.wait_b = (uint8_t)(wait_b | ((k0 / MROWS) << 4));   // per-block readiness (h1', h2', y1, y2)
       c.commit = 0; c.owner = (uint8_t)owner; c.phase = (uint8_t)phase;
       first = false; fresh[owner] = false;
       pd.c = c;
@@ -156,67 +160,71 @@ inline void build_plan(const HostWeights& w, bool bf, Plan& p) {
   const double* W2x = S1; const double* W1h = S1 + (size_t)3 * H * H; const double* F1x = S1 + (size_t)6 * H * H;
   const double* W2h = S2 + (size_t)H * H; const double* F2x = S3;
   const int NB = H / MROWS;             // 4 unit blocks
+  const int B0 = only_block >= 0 ? only_block : 0, B1 = only_block >= 0 ? only_block + 1 : NB;     // blocks of this program
+  auto ab = [&](int b) -> int { return only_block >= 0 ? 0 : b; };                                   // block id used for accumulators / barriers
   std::vector<double> F3((size_t)MROWS * H, 0.0);
   for (int r = 0; r < w.n_classes && r < MROWS; ++r) for (int k = 0; k < H; ++k) F3[(size_t)r * H + k] = w.f3w[(size_t)r * H + k];
   const int QK[5] = {0, 64, 128, 192, CDIM};              // the four K-chunks of a conditioning row (64, 64, 64, 16)
 
   // ---- P1: GRU1 (phase 0).  Accumulators of block b: 4b + {0: r, 1: z, 2: in, 3: hn}
-  for (int b = 0; b < NB; ++b) {
+  for (int b = B0; b < B1; ++b) {
     new_block();
     for (int g = 0; g < 2; ++g) {                                  // r, z: conditioning + recurrent part in one accumulator
       bool first = true;
-      emit(g, 0, b, Q, CDIM, 8 * H, g * H + b * MROWS, 0, CDIM, (uint8_t)(4 * b + g), B_COND, B_NONE, first, W_COND);
-      emit(g, 0, b, W1h, H, 3 * H, g * H + b * MROWS, 0, H, (uint8_t)(4 * b + g), B_H1PREV, B_NONE, first, W_NONE);
-      mark_commit(g, b);
+      emit(g, 0, ab(b), Q, CDIM, 8 * H, g * H + b * MROWS, 0, CDIM, (uint8_t)(4 * ab(b) + g), B_COND, B_NONE, first, W_COND);
+      emit(g, 0, ab(b), W1h, H, 3 * H, g * H + b * MROWS, 0, H, (uint8_t)(4 * ab(b) + g), B_H1PREV, B_NONE, first, W_NONE);
+      mark_commit(g, ab(b));
     }
-    { bool first = true; emit(2, 0, b, Q, CDIM, 8 * H, 2 * H + b * MROWS, 0, CDIM, (uint8_t)(4 * b + 2), B_COND, B_NONE, first, W_COND); mark_commit(2, b); }
-    { bool first = true; emit(3, 0, b, W1h, H, 3 * H, 2 * H + b * MROWS, 0, H, (uint8_t)(4 * b + 3), B_H1PREV, B_NONE, first, W_NONE); mark_commit(3, b); }
+    { bool first = true; emit(2, 0, ab(b), Q, CDIM, 8 * H, 2 * H + b * MROWS, 0, CDIM, (uint8_t)(4 * ab(b) + 2), B_COND, B_NONE, first, W_COND); mark_commit(2, ab(b)); }
+    { bool first = true; emit(3, 0, ab(b), W1h, H, 3 * H, 2 * H + b * MROWS, 0, H, (uint8_t)(4 * ab(b) + 3), B_H1PREV, B_NONE, first, W_NONE); mark_commit(3, ab(b)); }
     flush();
   }
   // ---- P2: GRU2 (phase 1).  First everything that does not need h1' (overlaps the P1 gate math), then W2x h1'.
-  for (int b = 0; b < NB; ++b) {
+  for (int b = B0; b < B1; ++b) {
     new_block();
     for (int g = 0; g < 3; ++g) {
       bool first = true;
-      emit(g, 1, b, Q, CDIM, 8 * H, 3 * H + g * H + b * MROWS, 0, CDIM, (uint8_t)(4 * b + g), B_COND, B_NONE, first, W_COND);
-      if (g < 2) emit(g, 1, b, W2h, H, 3 * H, g * H + b * MROWS, 0, H, (uint8_t)(4 * b + g), B_H2, B_NONE, first, W_NONE);
+      emit(g, 1, ab(b), Q, CDIM, 8 * H, 3 * H + g * H + b * MROWS, 0, CDIM, (uint8_t)(4 * ab(b) + g), B_COND, B_NONE, first, W_COND);
+      if (g < 2) emit(g, 1, ab(b), W2h, H, 3 * H, g * H + b * MROWS, 0, H, (uint8_t)(4 * ab(b) + g), B_H2, B_NONE, first, W_NONE);
     }
-    { bool first = true; emit(3, 1, b, W2h, H, 3 * H, 2 * H + b * MROWS, 0, H, (uint8_t)(4 * b + 3), B_H2, B_NONE, first, W_NONE); mark_commit(3, b); }
+    { bool first = true; emit(3, 1, ab(b), W2h, H, 3 * H, 2 * H + b * MROWS, 0, H, (uint8_t)(4 * ab(b) + 3), B_H2, B_NONE, first, W_NONE); mark_commit(3, ab(b)); }
     flush();
   }
-  for (int b = 0; b < NB; ++b) {
+  for (int b = B0; b < B1; ++b) {
     for (bool& fr : fresh) fr = false;                             // the accumulators were opened by the independent part
     for (int g = 0; g < 3; ++g) {
       bool first = false;
-      emit(g, 1, b, W2x, H, 3 * H, g * H + b * MROWS, 0, H, (uint8_t)(4 * b + g), B_H1NEW, B_NONE, first, W_H1NEW);
-      mark_commit(g, b);
+      emit(g, 1, ab(b), W2x, H, 3 * H, g * H + b * MROWS, 0, H, (uint8_t)(4 * ab(b) + g), B_H1NEW, B_NONE, first, W_H1NEW);
+      mark_commit(g, ab(b));
     }
     flush();
   }
   // ---- P3 / P4: fc1 (phase 2), fc2 (phase 3): K split over the four issuers, partial accumulators 4b + q
   for (int layer = 0; layer < 2; ++layer) {
     const double* F = layer ? F2x : F1x;
-    for (int b = 0; b < NB; ++b) {
+    for (int b = B0; b < B1; ++b) {
       new_block();
       for (int o = 0; o < N_ISSUERS; ++o) {
         bool first = true;
-        emit(o, 2 + layer, b, Q, CDIM, 8 * H, (6 + layer) * H + b * MROWS, QK[o], QK[o + 1], (uint8_t)(4 * b + o), B_COND, B_NONE, first, W_COND);
-        if (layer == 1 && b == NB - 1) q[o].back().c.flags |= F_COND_RELEASE;      // this issuer's last read of the step's conditioning
-        if (layer == 0) emit(o, 2, b, F, H, H, b * MROWS, 128 * o, 128 * o + 128, (uint8_t)(4 * b + o), B_H1NEW, B_H2, first, W_H2NEW);
-        else emit(o, 3, b, F, H, H, b * MROWS, 128 * o, 128 * o + 128, (uint8_t)(4 * b + o), B_Y1, B_NONE, first, W_Y1);
-        mark_commit(o, b);
+        emit(o, 2 + layer, ab(b), Q, CDIM, 8 * H, (6 + layer) * H + b * MROWS, QK[o], QK[o + 1], (uint8_t)(4 * ab(b) + o), B_COND, B_NONE, first, W_COND);
+        if (layer == 1 && b == B1 - 1) q[o].back().c.flags |= F_COND_RELEASE;      // this issuer's last read of the step's conditioning
+        if (layer == 0) emit(o, 2, ab(b), F, H, H, b * MROWS, 128 * o, 128 * o + 128, (uint8_t)(4 * ab(b) + o), B_H1NEW, B_H2, first, W_H2NEW);
+        else emit(o, 3, ab(b), F, H, H, b * MROWS, 128 * o, 128 * o + 128, (uint8_t)(4 * ab(b) + o), B_Y1, B_NONE, first, W_Y1);
+        mark_commit(o, ab(b));
       }
     }
-    flush();            // per layer: 3 chunks per issuer and block -> 12 per issuer, even
+    flush();            // per layer: 3 chunks per issuer and block -> 12 per issuer, even (one-block programs: 3, their ring slots hold one chunk)
   }
   // ---- P5: fc3 (phase 4): partial accumulators 0..3 of block 0
-  new_block();
-  for (int o = 0; o < N_ISSUERS; ++o) {
-    bool first = true;
-    emit(o, 4, 0, F3.data(), H, MROWS, 0, 128 * o, 128 * o + 128, (uint8_t)o, B_Y2, B_NONE, first, W_Y2);
-    mark_commit(o, 0);
+  if (only_block <= 0) {
+    new_block();
+    for (int o = 0; o < N_ISSUERS; ++o) {
+      bool first = true;
+      emit(o, 4, 0, F3.data(), H, MROWS, 0, 128 * o, 128 * o + 128, (uint8_t)o, B_Y2, B_NONE, first, W_Y2);
+      mark_commit(o, 0);
+    }
+    flush();
   }
-  flush();
 }
 
 // ---- what the kernel reads -----------------------------------------------------------------------------------------
@@ -231,11 +239,14 @@ struct DevChunk {
   uint8_t acc_phase;      // accumulator index | phase << 4
   uint8_t flags;          // DF_*
   uint16_t sync;          // wait_b | wait_acc << 3 | commit << 6 | wait_blk << 9     (W_* / block + 1 / block + 1 / block of the operand)
-  uint16_t pair;          // index of the chunk's pair in stream order (ring position within the step)
+  uint16_t pair;          // ring position of the chunk's slot load within the step (pair index, or chunk index if a slot holds one chunk)
 };
 static_assert(sizeof(DevChunk) == 16, "DevChunk must stay one uint4");
 
-struct SmemLayout { int off_x0, off_x1, off_h2, off_cond, cond_bytes; };   // byte offsets of the operand images
+// byte offsets of the operand images.  One-CTA form: h2 updated in place (off_h2[0] == off_h2[1]), y2 over y1 in X[cur].
+// Cluster form: h2 ping-pongs like h1 (peers write into each other's images and cannot know when a peer's W2h MMAs are
+// done), y1 goes to the stale h1 image X[cur], y2 to the stale h2 image H[cur].  `cps`: chunks per ring slot.
+struct SmemLayout { int off_x0, off_x1, off_h2[2], off_cond, cond_bytes, cps; bool y2_in_h2; };
 
 struct DevProgram {
   std::vector<DevChunk> mine[N_ISSUERS];     // per issuing warp, in its own order (pairs are adjacent records)
@@ -248,12 +259,13 @@ inline void compile_device(const Plan& p, const SmemLayout& L, DevProgram& d) {
   d.pair_size16.assign((p.prog.size() + 1) / 2, 0);
   d.chunk_size16.clear();
   for (const Chunk& c : p.prog) d.chunk_size16.push_back(c.size16);
-  auto base_of = [&](uint8_t buf, int cur) -> int {
+  auto base_of = [&](uint8_t buf, int cur, int phase) -> int {
     switch (buf) {
       case B_COND: return L.off_cond + cur * L.cond_bytes;
       case B_H1NEW: return cur ? L.off_x0 : L.off_x1;
-      case B_H2: return L.off_h2;
-      default: return cur ? L.off_x1 : L.off_x0;          // B_H1PREV, B_Y1, B_Y2
+      case B_H2: return L.off_h2[phase <= 1 ? cur : cur ^ 1];       // GRU2 reads the previous h2 (H[cur]), fc1 the new one (H[cur^1])
+      case B_Y2: return L.y2_in_h2 ? L.off_h2[cur] : (cur ? L.off_x1 : L.off_x0);
+      default: return cur ? L.off_x1 : L.off_x0;          // B_H1PREV, B_Y1
     }
   };
   for (size_t i = 0; i < p.prog.size(); ++i) {
@@ -262,14 +274,14 @@ inline void compile_device(const Plan& p, const SmemLayout& L, DevProgram& d) {
     DevChunk r{};
     r.a_lo = c.a_off16;
     for (int cur = 0; cur < 2; ++cur) {
-      r.b_lo[cur] = (uint16_t)((base_of(c.b_buf, cur) + c.k0 * 16) >> 4);
-      r.b2_lo[cur] = c.b_buf2 == B_NONE ? 0 : (uint16_t)((base_of(c.b_buf2, cur) + c.k0 * 16) >> 4);
+      r.b_lo[cur] = (uint16_t)((base_of(c.b_buf, cur, c.phase) + c.k0 * 16) >> 4);
+      r.b2_lo[cur] = c.b_buf2 == B_NONE ? 0 : (uint16_t)((base_of(c.b_buf2, cur, c.phase) + c.k0 * 16) >> 4);
     }
     r.acc_phase = (uint8_t)(c.acc | (c.phase << 4));
     r.flags = (uint8_t)(((c.flags & F_FIRST) ? DF_FIRST : 0) | ((c.flags & F_COND_RELEASE) ? DF_COND_RELEASE : 0) |
                         (c.b_buf == B_COND ? DF_B_COND : 0) | (c.nk == 1 ? DF_NK1 : 0) | (c.b_buf2 != B_NONE ? DF_HAS_B2 : 0));
     r.sync = (uint16_t)((c.wait_b & 7) | (c.wait_acc << 3) | (c.commit << 6) | ((c.wait_b >> 4) << 9));
-    r.pair = (uint16_t)(i / 2);
+    r.pair = (uint16_t)(L.cps == 2 ? i / 2 : i);          // ring position within the step: pair index, or chunk index when a slot holds one chunk
     d.mine[c.owner].push_back(r);
   }
 }
