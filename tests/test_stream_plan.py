@@ -236,7 +236,8 @@ def test_stream_plan_on_the_trained_checkpoint_teacher_forced():
 def test_cluster_rank_programs_are_the_blocks_of_the_whole_program():
     """Cluster form (four CTAs split the rows of every layer): the program of rank r is exactly the chunks of unit block r
     of the whole program -- same weight tiles, same operands, K offsets, first / wait / owner / phase fields -- with the
-    accumulators and block ids renumbered to block 0; fc3 only in rank 0.  (The whole program is the one the numpy
+    accumulators and their barrier ids renumbered to one set per PHASE (set = phase & 3: nothing waits for the previous
+    phase's epilogue to drain); fc3 only in rank 0.  (The whole program is the one the numpy
     interpreter above checks against the engine contract.)"""
     sd = helpers.state_numpy(helpers.make_model(0, "MOL"))
     blob, prog, _ = get_plan(sd)
@@ -261,9 +262,10 @@ def test_cluster_rank_programs_are_the_blocks_of_the_whole_program():
                         assert int(c[f]) & 1 == int(d[f]) & 1
                         continue
                     assert c[f] == d[f], (r, o, f, i, j)
-                assert int(d["acc"]) == int(c["acc"]) % 4
-                assert (int(c["wait_acc"]) > 0) == (int(d["wait_acc"]) > 0) and int(d["wait_acc"]) in (0, 1)
-                assert (int(c["commit"]) > 0) == (int(d["commit"]) > 0) and int(d["commit"]) in (0, 1)
+                aset = int(c["phase"]) & 3
+                assert int(d["acc"]) == 4 * aset + int(c["acc"]) % 4
+                assert (int(c["wait_acc"]) > 0) == (int(d["wait_acc"]) > 0) and int(d["wait_acc"]) in (0, aset + 1)
+                assert (int(c["commit"]) > 0) == (int(d["commit"]) > 0) and int(d["commit"]) in (0, aset + 1)
                 assert np.array_equal(blob[offs[i]:offs[i + 1]], b_r[o_r[j]:o_r[j + 1]])
         assert ((p_r["flags"] & 2) > 0).sum() == 4 and (p_r["phase"] == 4).sum() == (8 if r == 0 else 0)
     assert total == len(prog)

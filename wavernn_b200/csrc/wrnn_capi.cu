@@ -99,10 +99,11 @@ int wrnn_create(wrnn_t** out, const wrnn_cfg* cfg, const wrnn_weights* w, int de
 }
 
 // Folds from which ENGINE_AUTO hands a job to the stream engine: the persistent engine serves tiles of 64 folds one
-// after the other at 15.5 us per step each, the stream engine serves up to 148 tiles of 16 folds at once at ~66 us per step
-// (profiles/r02_stream.md): break-even at 4.3 tiles = 272 folds.  WRNN_STREAM_MIN_FOLDS overrides (experiments).
+// after the other at 15.5 us per step each; the stream engine's cluster form serves up to 33 x 16 folds at once at
+// 28.5 us per step (33 x 32 at 39 us, then the one-CTA forms: 66 us for up to 148 x 16, 94 us per 148 x 32;
+// profiles/r02_stream.md): from the third tile on the stream engine is faster.  WRNN_STREAM_MIN_FOLDS overrides (experiments).
 static int stream_min_folds() {
-  static const int v = [] { const char* e = getenv("WRNN_STREAM_MIN_FOLDS"); return e ? atoi(e) : 288; }();
+  static const int v = [] { const char* e = getenv("WRNN_STREAM_MIN_FOLDS"); return e ? atoi(e) : 129; }();
   return v;
 }
 

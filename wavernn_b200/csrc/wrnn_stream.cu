@@ -48,7 +48,7 @@ constexpr int SBO_Q = KQ * 128;              // 3328: stride between 8-fold grou
 constexpr int SBO_H = (H / 8) * 128;         // 8192: same for the K = 512 images
 constexpr int TMEM_COLS = 512;
 constexpr int NBAR = 48;
-constexpr int MAX_STAGES = 6;               // ring slots (one or two chunks each)
+constexpr int MAX_STAGES = 9;               // ring slots (one or two chunks each)
 
 template <int NF, int CL> struct Smem {
   static constexpr int GROUPS = NF / 8;
@@ -143,7 +143,10 @@ __global__ void __launch_bounds__(NT, 1) wrnn_stream_kernel(const StreamParams p
     }
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 32;" :: "r"(bar(BAR_READY + 0)));
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 32;" :: "r"(bar(BAR_READY + 1)));
-    for (int i = 2; i < 18; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 128;" :: "r"(bar(BAR_READY + i)));
+    // operand blocks: written here by the 128 epilogue threads (one arrival each), or -- cluster form, a peer's block --
+    // delivered by the peer's bulk copies (one arrive.expect_tx by the sender + the bytes)
+    for (int i = 2; i < 18; ++i)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar(BAR_READY + i)), "r"((CL == 1 || ((i - 2) & 3) == rank) ? 128 : 1));
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar(BAR_COND_FREE + 0)), "n"(N_ISSUERS));
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar(BAR_COND_FREE + 1)), "n"(N_ISSUERS));
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar(BAR_X)));
@@ -277,18 +280,18 @@ __global__ void __launch_bounds__(NT, 1) wrnn_stream_kernel(const StreamParams p
           if (wait_acc) {
             // the epilogue of the previous (phase, block) use must have drained the block: its arrivals on acc_empty[blk] are
             // numbered A*t + phase (A = 5 for block 0, which also serves fc3; 4 otherwise); we need number A*t + phase - 1
+            // (cluster form: one accumulator set per phase, drained once per step; set 0 also serves fc3 in rank 0)
             const int blk = wait_acc - 1;
-            const int idx = ((CL == 1 ? blk == 0 : rank == 0) ? N_PHASES : N_PHASES - 1) * t + (int)phase - 1;
+            const int idx = (CL == 1) ? ((blk == 0 ? N_PHASES : N_PHASES - 1) * t + (int)phase - 1)
+                                      : ((blk == 0 && rank == 0) ? (2 * t + (phase == 4u ? 0 : -1)) : (t - 1));
             if (idx >= 0) wait(bar(BAR_ACC_EMPTY + blk), (uint32_t)idx & 1u);
           }
           if (profiling) c1 = clock64();
           if (wait_b == W_COND) wait(bar(BAR_READY + cur), (uint32_t)(t >> 1) & 1);
           else if (wait_b != W_NONE) {
-            wait_peer(bar(BAR_READY + 2 + (wait_b - W_H1NEW) * 4 + wait_blk), (uint32_t)t & 1);   // the block this K range reads
-            if constexpr (CL > 1) {
-              asm volatile("fence.acq_rel.cluster;" ::: "memory");
-              asm volatile("fence.proxy.async;" ::: "memory");   // peers' generic stores into this CTA -> our tensor-core reads
-            }
+            // the block this K range reads: written here through the generic proxy (fenced by its writers), or a peer's
+            // block that arrived by bulk copy (async proxy, complete_tx on this barrier) -- like a TMA load, no fence
+            wait_peer(bar(BAR_READY + 2 + (wait_b - W_H1NEW) * 4 + wait_blk), (uint32_t)t & 1);
           }
           if (profiling) c2 = clock64();
           if (j == 0 || SM::CPS == 1) {
@@ -395,37 +398,39 @@ __global__ void __launch_bounds__(NT, 1) wrnn_stream_kernel(const StreamParams p
       tc_fence_before();
       asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar(BAR_ACC_EMPTY + blk)) : "memory");
     };
-    // this thread's part of operand `kind`, unit block `blk` (GLOBAL block id), is written -- in the cluster form into all four
-    // CTAs' images, so all four are told (release at cluster scope; the proxy fence orders the generic stores, local and
-    // remote, before the peers' tensor-core reads)
-    auto publish_ready = [&](int kind, int blk) {
+    // This thread's part of operand `kind`, unit block `blk` (GLOBAL block id) of the image at `off` is written.  Cluster
+    // form: the block is written LOCALLY like in the one-CTA form, then three elected threads (one per peer) push it into
+    // the same place of the peers' images with bulk copies (shared::cta -> shared::cluster, NF/8 pieces of 2 KB: the 16
+    // K-chunks of the block are contiguous within a fold group) that complete_tx on the peer's readiness barrier.
+    // (Round-2 measurement: 2-byte st.shared::cluster stores into four CTAs + cluster-scope fences cost ~6,000 cycles per
+    //  phase; y2 is only needed by rank 0, which owns fc3.)
+    auto publish_ready = [&](int kind, int blk, int off) {
       const uint32_t b = bar(BAR_READY + 2 + (kind - W_H1NEW) * 4 + blk);
-      if constexpr (CL == 1) {
-        proxy_fence_smem();
-        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(b) : "memory");
-      } else {
-        asm volatile("fence.acq_rel.cluster;" ::: "memory");
-        asm volatile("fence.proxy.async;" ::: "memory");
+      proxy_fence_smem();
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(b) : "memory");
+      if constexpr (CL > 1) {
+        named_bar_sync(2, 128);                                // every epilogue thread's stores (and proxy fences) are done
+        const int q = warp & 3;
+        if (lane == 0 && q != 0) {
+          const uint32_t peer = (uint32_t)((rank + q) & 3);
+          if (kind != W_Y2 || peer == 0u) {
+            const uint32_t rb = map_to_rank(b, peer);
+            asm volatile("mbarrier.arrive.expect_tx.release.cluster.shared::cluster.b64 _, [%0], %1;" :: "r"(rb), "r"((uint32_t)(NF * 256)) : "memory");
 #pragma unroll
-        for (int r = 0; r < CL; ++r)
-          asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" :: "r"(map_to_rank(b, (uint32_t)r)) : "memory");
+            for (int g = 0; g < NF / 8; ++g) {
+              const uint32_t src = smem_u32(smem + off + g * SBO_H + blk * (MROWS / 8) * 128);
+              asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                           :: "r"(map_to_rank(src, peer)), "r"(src), "r"((uint32_t)((MROWS / 8) * 128)), "r"(rb) : "memory");
+            }
+          }
+        }
       }
     };
     // element (fold f, unit k) of a K = 512 operand image
     auto img_ptr = [&](int off, int f, int k) -> uint16_t* {
       return reinterpret_cast<uint16_t*>(smem + off + (f >> 3) * SBO_H + (k >> 3) * 128 + (f & 7) * 16 + (k & 7) * 2);
     };
-    // store it: locally, or (cluster form) into the same place of every CTA of the cluster
-    auto img_store = [&](int off, int f, int k, uint16_t bits) {
-      if constexpr (CL == 1) {
-        *img_ptr(off, f, k) = bits;
-      } else {
-        const uint32_t a = smem_u32(img_ptr(off, f, k));
-#pragma unroll
-        for (int r = 0; r < CL; ++r)
-          asm volatile("st.shared::cluster.u16 [%0], %1;" :: "r"(map_to_rank(a, (uint32_t)r)), "h"(bits) : "memory");
-      }
-    };
+    auto img_store = [&](int off, int f, int k, uint16_t bits) { *img_ptr(off, f, k) = bits; };
     constexpr int NBLK = (CL == 1) ? 4 : 1;                      // unit blocks this CTA computes: all four, or block `rank`
     auto to_bits = [&](float v) -> uint16_t { return (uint16_t)(pack2<FMT>(v, 0.f) & 0xffffu); };
 
@@ -473,8 +478,8 @@ __global__ void __launch_bounds__(NT, 1) wrnn_stream_kernel(const StreamParams p
         const int qbase = cell * 3 * H;                        // rows of qk / vq: gi1 = 0.., gi2 = 3H..
         const int off_out = cell ? off_h2new : off_h1new;
 #pragma unroll 1
-        for (int ba = 0; ba < NBLK; ++ba) {                    // ba: accumulator / barrier block in this CTA; b: unit block of the layer
-          const int b = (CL == 1) ? ba : rank;
+        for (int bi = 0; bi < NBLK; ++bi) {                    // ba: accumulator set / barrier block in this CTA; b: unit block of the layer
+          const int ba = (CL == 1) ? bi : cell, b = (CL == 1) ? bi : rank;
           const int u = b * MROWS + row;
           const float qk_r = __ldg(p.qk + qbase + u), qk_z = __ldg(p.qk + qbase + H + u), qk_n = __ldg(p.qk + qbase + 2 * H + u);
           const float vq_r = __ldg(p.vq + qbase + u), vq_z = __ldg(p.vq + qbase + H + u), vq_n = __ldg(p.vq + qbase + 2 * H + u);
@@ -515,7 +520,7 @@ __global__ void __launch_bounds__(NT, 1) wrnn_stream_kernel(const StreamParams p
 #pragma unroll
           for (int i = 0; i < NF / 4; ++i)
             __stcg(reinterpret_cast<float4*>(hrow) + i, make_float4(hp[4 * i], hp[4 * i + 1], hp[4 * i + 2], hp[4 * i + 3]));
-          publish_ready(cell ? W_H2NEW : W_H1NEW, b);           // block by block: the consumers' K chunks wait per block
+          publish_ready(cell ? W_H2NEW : W_H1NEW, b, off_out);           // block by block: the consumers' K chunks wait per block
         }
       }
 
@@ -523,8 +528,8 @@ __global__ void __launch_bounds__(NT, 1) wrnn_stream_kernel(const StreamParams p
       {
         const int qbase = 6 * H;
 #pragma unroll 1
-        for (int ba = 0; ba < NBLK; ++ba) {
-          const int b = (CL == 1) ? ba : rank;
+        for (int bi = 0; bi < NBLK; ++bi) {
+          const int ba = (CL == 1) ? bi : 2, b = (CL == 1) ? bi : rank;
           const int u = b * MROWS + row;
           const float qk_u = __ldg(p.qk + qbase + u), vq_u = __ldg(p.vq + qbase + u);
           wait_full(ba);
@@ -543,7 +548,7 @@ __global__ void __launch_bounds__(NT, 1) wrnn_stream_kernel(const StreamParams p
               img_store(off_y1, f, u, to_bits(fmaxf(((a[i] + a1[i]) + (a2[i] + a3[i])) + qk_u + x_s[f] * vq_u, 0.f)));
             }
           }
-          publish_ready(W_Y1, b);
+          publish_ready(W_Y1, b, off_y1);
         }
       }
       // ---- P4: fc2 -> y2.  y2 REPLACES y1 in X[cur], which the fc2 MMAs of the later blocks still read: the values are
@@ -584,25 +589,25 @@ __global__ void __launch_bounds__(NT, 1) wrnn_stream_kernel(const StreamParams p
           }
         }
 #pragma unroll
-        for (int b = 0; b < 4; ++b) publish_ready(W_Y2, b);
+        for (int b = 0; b < 4; ++b) publish_ready(W_Y2, b, off_y1);
       }
       else {                                                     // cluster form: y2 has its own place (the stale h2 image), nothing to defer
         const int u = rank * MROWS + row;
         const float qk_u = __ldg(p.qk + 7 * H + u);
-        wait_full(0);
+        wait_full(3);                                            // accumulator set 3 (= phase)
 #pragma unroll
         for (int half = 0; half < NF / 16; ++half) {
           float a[16], a1[16], a2[16], a3[16];
-          tmem_ld16(tlane + 0 * NF + half * 16, a);
-          tmem_ld16(tlane + 1 * NF + half * 16, a1);
-          tmem_ld16(tlane + 2 * NF + half * 16, a2);
-          tmem_ld16(tlane + 3 * NF + half * 16, a3);
+          tmem_ld16(tlane + 12 * NF + half * 16, a);
+          tmem_ld16(tlane + 13 * NF + half * 16, a1);
+          tmem_ld16(tlane + 14 * NF + half * 16, a2);
+          tmem_ld16(tlane + 15 * NF + half * 16, a3);
           tmem_ld_wait();
-          if (half == NF / 16 - 1) release_acc(0);
+          if (half == NF / 16 - 1) release_acc(3);
 #pragma unroll
           for (int i = 0; i < 16; ++i) img_store(off_y2, half * 16 + i, u, to_bits(fmaxf(((a[i] + a1[i]) + (a2[i] + a3[i])) + qk_u, 0.f)));
         }
-        publish_ready(W_Y2, rank);                               // each CTA delivers ITS block of y2; rank 0's fc3 chunks wait per block
+        publish_ready(W_Y2, rank, off_y2);                               // each CTA delivers ITS block of y2; rank 0's fc3 chunks wait per block
       }
 
       // ---- P5: logits -> transpose through shared memory -> one thread per fold samples ----------------------------

@@ -86,8 +86,8 @@ inline size_t tile_index(int r, int k, int kc) { return (size_t)(r / 8) * (kc / 
 //                recurrent operand, into its own partial accumulator 4b + q (the epilogue adds the four partials)
 // Stream order: the chains of one (phase, block) are interleaved round-robin, so consecutive ring slots go to different
 // warps; within P2 everything that does not depend on h1' is issued (for all blocks) before the W2x h1' chunks.
-// `only_block` >= 0 builds the program of ONE 128-unit block of every layer (accumulators 0..3, block id 0 in the barrier
-// fields, fc3 only for block 0): the share of CTA `only_block` of a 4-CTA cluster that splits the rows of every layer
+// `only_block` >= 0 builds the program of ONE 128-unit block of every layer (accumulator set = phase, see ab() below;
+// fc3 only for block 0): the share of CTA `only_block` of a 4-CTA cluster that splits the rows of every layer
 // (wrnn_stream.cu, cluster form).  Operand readiness codes (wait_b) keep the GLOBAL block of the K range they read.
 inline void build_plan(const HostWeights& w, bool bf, Plan& p, int only_block = -1) {
   Folded f; fold(w, f);
@@ -161,7 +161,10 @@ inline void build_plan(const HostWeights& w, bool bf, Plan& p, int only_block = 
   const double* W2h = S2 + (size_t)H * H; const double* F2x = S3;
   const int NB = H / MROWS;             // 4 unit blocks
   const int B0 = only_block >= 0 ? only_block : 0, B1 = only_block >= 0 ? only_block + 1 : NB;     // blocks of this program
-  auto ab = [&](int b) -> int { return only_block >= 0 ? 0 : b; };                                   // block id used for accumulators / barriers
+  // block id used for accumulators and their barriers: the unit block, or -- one-block programs -- the PHASE (P1..P4 ->
+  // sets 0..3, fc3 -> set 0 again): nothing else lives in the other three quarters of TMEM, and with a set per phase the
+  // MMAs of a phase never wait for the previous phase's epilogue to drain.
+  auto ab = [&](int b, int phase) -> int { return only_block >= 0 ? (phase & 3) : b; };
   std::vector<double> F3((size_t)MROWS * H, 0.0);
   for (int r = 0; r < w.n_classes && r < MROWS; ++r) for (int k = 0; k < H; ++k) F3[(size_t)r * H + k] = w.f3w[(size_t)r * H + k];
   const int QK[5] = {0, 64, 128, 192, CDIM};              // the four K-chunks of a conditioning row (64, 64, 64, 16)
@@ -171,12 +174,12 @@ inline void build_plan(const HostWeights& w, bool bf, Plan& p, int only_block = 
     new_block();
     for (int g = 0; g < 2; ++g) {                                  // r, z: conditioning + recurrent part in one accumulator
       bool first = true;
-      emit(g, 0, ab(b), Q, CDIM, 8 * H, g * H + b * MROWS, 0, CDIM, (uint8_t)(4 * ab(b) + g), B_COND, B_NONE, first, W_COND);
-      emit(g, 0, ab(b), W1h, H, 3 * H, g * H + b * MROWS, 0, H, (uint8_t)(4 * ab(b) + g), B_H1PREV, B_NONE, first, W_NONE);
-      mark_commit(g, ab(b));
+      emit(g, 0, ab(b, 0), Q, CDIM, 8 * H, g * H + b * MROWS, 0, CDIM, (uint8_t)(4 * ab(b, 0) + g), B_COND, B_NONE, first, W_COND);
+      emit(g, 0, ab(b, 0), W1h, H, 3 * H, g * H + b * MROWS, 0, H, (uint8_t)(4 * ab(b, 0) + g), B_H1PREV, B_NONE, first, W_NONE);
+      mark_commit(g, ab(b, 0));
     }
-    { bool first = true; emit(2, 0, ab(b), Q, CDIM, 8 * H, 2 * H + b * MROWS, 0, CDIM, (uint8_t)(4 * ab(b) + 2), B_COND, B_NONE, first, W_COND); mark_commit(2, ab(b)); }
-    { bool first = true; emit(3, 0, ab(b), W1h, H, 3 * H, 2 * H + b * MROWS, 0, H, (uint8_t)(4 * ab(b) + 3), B_H1PREV, B_NONE, first, W_NONE); mark_commit(3, ab(b)); }
+    { bool first = true; emit(2, 0, ab(b, 0), Q, CDIM, 8 * H, 2 * H + b * MROWS, 0, CDIM, (uint8_t)(4 * ab(b, 0) + 2), B_COND, B_NONE, first, W_COND); mark_commit(2, ab(b, 0)); }
+    { bool first = true; emit(3, 0, ab(b, 0), W1h, H, 3 * H, 2 * H + b * MROWS, 0, H, (uint8_t)(4 * ab(b, 0) + 3), B_H1PREV, B_NONE, first, W_NONE); mark_commit(3, ab(b, 0)); }
     flush();
   }
   // ---- P2: GRU2 (phase 1).  First everything that does not need h1' (overlaps the P1 gate math), then W2x h1'.
@@ -184,18 +187,18 @@ inline void build_plan(const HostWeights& w, bool bf, Plan& p, int only_block = 
     new_block();
     for (int g = 0; g < 3; ++g) {
       bool first = true;
-      emit(g, 1, ab(b), Q, CDIM, 8 * H, 3 * H + g * H + b * MROWS, 0, CDIM, (uint8_t)(4 * ab(b) + g), B_COND, B_NONE, first, W_COND);
-      if (g < 2) emit(g, 1, ab(b), W2h, H, 3 * H, g * H + b * MROWS, 0, H, (uint8_t)(4 * ab(b) + g), B_H2, B_NONE, first, W_NONE);
+      emit(g, 1, ab(b, 1), Q, CDIM, 8 * H, 3 * H + g * H + b * MROWS, 0, CDIM, (uint8_t)(4 * ab(b, 1) + g), B_COND, B_NONE, first, W_COND);
+      if (g < 2) emit(g, 1, ab(b, 1), W2h, H, 3 * H, g * H + b * MROWS, 0, H, (uint8_t)(4 * ab(b, 1) + g), B_H2, B_NONE, first, W_NONE);
     }
-    { bool first = true; emit(3, 1, ab(b), W2h, H, 3 * H, 2 * H + b * MROWS, 0, H, (uint8_t)(4 * ab(b) + 3), B_H2, B_NONE, first, W_NONE); mark_commit(3, ab(b)); }
+    { bool first = true; emit(3, 1, ab(b, 1), W2h, H, 3 * H, 2 * H + b * MROWS, 0, H, (uint8_t)(4 * ab(b, 1) + 3), B_H2, B_NONE, first, W_NONE); mark_commit(3, ab(b, 1)); }
     flush();
   }
   for (int b = B0; b < B1; ++b) {
     for (bool& fr : fresh) fr = false;                             // the accumulators were opened by the independent part
     for (int g = 0; g < 3; ++g) {
       bool first = false;
-      emit(g, 1, ab(b), W2x, H, 3 * H, g * H + b * MROWS, 0, H, (uint8_t)(4 * ab(b) + g), B_H1NEW, B_NONE, first, W_H1NEW);
-      mark_commit(g, ab(b));
+      emit(g, 1, ab(b, 1), W2x, H, 3 * H, g * H + b * MROWS, 0, H, (uint8_t)(4 * ab(b, 1) + g), B_H1NEW, B_NONE, first, W_H1NEW);
+      mark_commit(g, ab(b, 1));
     }
     flush();
   }
@@ -206,11 +209,11 @@ inline void build_plan(const HostWeights& w, bool bf, Plan& p, int only_block = 
       new_block();
       for (int o = 0; o < N_ISSUERS; ++o) {
         bool first = true;
-        emit(o, 2 + layer, ab(b), Q, CDIM, 8 * H, (6 + layer) * H + b * MROWS, QK[o], QK[o + 1], (uint8_t)(4 * ab(b) + o), B_COND, B_NONE, first, W_COND);
+        emit(o, 2 + layer, ab(b, 2 + layer), Q, CDIM, 8 * H, (6 + layer) * H + b * MROWS, QK[o], QK[o + 1], (uint8_t)(4 * ab(b, 2 + layer) + o), B_COND, B_NONE, first, W_COND);
         if (layer == 1 && b == B1 - 1) q[o].back().c.flags |= F_COND_RELEASE;      // this issuer's last read of the step's conditioning
-        if (layer == 0) emit(o, 2, ab(b), F, H, H, b * MROWS, 128 * o, 128 * o + 128, (uint8_t)(4 * ab(b) + o), B_H1NEW, B_H2, first, W_H2NEW);
-        else emit(o, 3, ab(b), F, H, H, b * MROWS, 128 * o, 128 * o + 128, (uint8_t)(4 * ab(b) + o), B_Y1, B_NONE, first, W_Y1);
-        mark_commit(o, ab(b));
+        if (layer == 0) emit(o, 2, ab(b, 2 + layer), F, H, H, b * MROWS, 128 * o, 128 * o + 128, (uint8_t)(4 * ab(b, 2 + layer) + o), B_H1NEW, B_H2, first, W_H2NEW);
+        else emit(o, 3, ab(b, 2 + layer), F, H, H, b * MROWS, 128 * o, 128 * o + 128, (uint8_t)(4 * ab(b, 2 + layer) + o), B_Y1, B_NONE, first, W_Y1);
+        mark_commit(o, ab(b, 2 + layer));
       }
     }
     flush();            // per layer: 3 chunks per issuer and block -> 12 per issuer, even (one-block programs: 3, their ring slots hold one chunk)
