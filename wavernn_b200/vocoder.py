@@ -21,6 +21,7 @@ global fold and step, independent of the rank count).
 """
 from __future__ import annotations
 
+import os
 import time
 from pathlib import Path
 from typing import Sequence, Union
@@ -336,6 +337,11 @@ class WaveRNN(nn.Module):
     def _can_stream_draws(self, steps: int, x_force, draws) -> bool:
         """MoL parity draws can be replayed and uploaded while the kernel runs (wrnn_job::uniforms_ready) when they come
         from the native replay and a tensor-core engine consumes them."""
+        # (needs the upload stream to run UNDER the kernel: not when launches are serialised -- CUDA_LAUNCH_BLOCKING=1, or a
+        #  kernel profiler such as ncu, for which WRNN_STREAM_DRAWS=0 selects the resident matrix; the kernel would wait for
+        #  rows that cannot arrive and end with WRNN_E_WATCHDOG)
+        if os.environ.get('CUDA_LAUNCH_BLOCKING', '0') == '1' or os.environ.get('WRNN_STREAM_DRAWS', '1') == '0':
+            return False
         return (bool(self.gen_stream_draws) and self.gen_rng == 'torch' and draws is None and x_force is None and self.mode == 'MOL'
                 and self.gen_precision != 'fp32' and self.gen_engine != 'simt' and steps > 2 * int(self.gen_draw_chunk)
                 and bool(self.gen_native_rng) and cabi.is_built() and cabi.torch_rng_replay_ok())
