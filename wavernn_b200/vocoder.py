@@ -348,7 +348,7 @@ class WaveRNN(nn.Module):
 
     def _streamed_draws(self, geo: FoldGeometry, steps: int, shard, device, launch):
         """The reference's draws (two discarded nn.GRUCell initialisations, then `steps` rows of 11*B uniforms; same
-        generator consumption as _reference_draws) replayed natively in chunks of `gen_draw_chunk` steps.  Chunk 0 is
+        generator consumption as _reference_draws) replayed natively in chunks of up to `gen_draw_chunk` steps.  Chunk 0 is
         uploaded, then `launch(uniforms_ptr, ready_ptr)` enqueues the kernel, then the remaining chunks are replayed and
         uploaded on a side stream while it runs; after every chunk a 4-byte copy on that stream bumps the device counter
         the kernel checks before it reads a row.  Host replay time (9 ms on an 8-rank job) leaves the critical path."""
@@ -357,7 +357,13 @@ class WaveRNN(nn.Module):
         cols = ((10 * f0, 10 * (f0 + nl)), (10 * B + f0, 10 * B + f0 + nl)) if nl < B else None
         width = 11 * nl
         chunk = int(self.gen_draw_chunk)
-        bounds = list(range(0, steps, chunk)) + [steps]
+        # the first chunk sits on the critical path (it is replayed before the launch): keep it to ~128 k draws however many
+        # folds the job has, then double up to `chunk` steps (replay is ~16x faster than the kernel consumes rows)
+        first = max(8, min(chunk, (1 << 17) // (11 * B)))
+        bounds, size = [0], first
+        while bounds[-1] < steps:
+            bounds.append(min(steps, bounds[-1] + size))
+            size = min(chunk, 2 * size)
         n_keep = steps * width
         if self._draw_buf is None or self._draw_buf.numel() < n_keep:
             self._draw_buf = torch.empty(n_keep, dtype=torch.float32, pin_memory=True)
