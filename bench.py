@@ -392,8 +392,10 @@ def run_ours(args):
                              "l2_policy": "no flush: every step streams fresh conditioning rows and draws; the weights are SUPPOSED to stay on chip",
                              "rng": "in-kernel Philox4x32-10" if (cfg5 or cfg3) else "reference-compatible torch CPU draws, resident in HBM for `value`"},
             "clocks": clocks, "gpu_launches": int(gpu_launches),
-            "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(mel_host.numel() * 4 + h2d_rng),
-                    "d2h_bytes_per_step": int(B_total * S * 4), "ms_per_step": t_e2e / args.steps * 1e3},
+            # whole job, counted from the tensors copied: every rank uploads the mel and its columns of the draw matrix, and
+            # every rank reads the whole float64 waveform back (generate() returns it on every rank)
+            "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(world * mel_host.numel() * 4 + h2d_rng),
+                    "d2h_bytes_per_step": int(world * (T - 1) * HOP * 8), "ms_per_step": t_e2e / args.steps * 1e3},
             "roofline": {"bound": "tensor", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": ach_tf / peak_tf, "traffic": measured_traffic(args, model), "peak_source": peaks["src"],
                          "note": ("stream engine: one pass over the fp16 weights per step through each SM's shared memory; bounded by the MMA "
