@@ -280,3 +280,27 @@ def test_raw_reference_draws_keep_only_the_local_folds_and_are_bounded():
     m.gen_max_draw_bytes = 1 << 20
     with pytest.raises(RuntimeError, match="philox"):
         m._reference_draws(geo, 660)
+
+
+def test_streamed_draw_chunks_cover_the_steps_and_start_short(monkeypatch):
+    """Streamed reference draws (vocoder.py::_streamed_draws): the chunk boundaries cover [0, steps] without gaps, no chunk
+    exceeds `gen_draw_chunk` steps, and the first one (replayed before the launch, i.e. on the critical path) stays near
+    128 k draws however many folds the job has; under serialised launches (CUDA_LAUNCH_BLOCKING=1, WRNN_STREAM_DRAWS=0)
+    streaming is off -- the kernel would wait for rows an upload stream cannot deliver."""
+    from wavernn_b200 import WaveRNN
+    for steps, chunk, folds in ((12100, 1024, 19), (12100, 1024, 152), (3000, 1024, 4096), (2050, 1024, 1), (12100, 64, 19)):
+        b = WaveRNN._draw_chunk_bounds(steps, chunk, folds)
+        sizes = np.diff(b)
+        assert b[0] == 0 and b[-1] == steps and (sizes > 0).all() and sizes.max() <= chunk
+        assert sizes[0] * 11 * folds <= max(1 << 17, 8 * 11 * folds) or sizes[0] == 8
+        assert all(sizes[i + 1] <= 2 * sizes[i] for i in range(len(sizes) - 2))       # doubling, never a jump
+    model = helpers.make_model(0, "MOL")
+    ok = lambda: model._can_stream_draws(12100, None, None)
+    base = ok()                                         # False here when the library is not built; the guards below only ever turn it off
+    monkeypatch.setenv("WRNN_STREAM_DRAWS", "0")
+    assert ok() is False
+    monkeypatch.delenv("WRNN_STREAM_DRAWS")
+    monkeypatch.setenv("CUDA_LAUNCH_BLOCKING", "1")
+    assert ok() is False
+    monkeypatch.delenv("CUDA_LAUNCH_BLOCKING")
+    assert ok() == base

@@ -346,6 +346,18 @@ class WaveRNN(nn.Module):
                 and self.gen_precision != 'fp32' and self.gen_engine != 'simt' and steps > 2 * int(self.gen_draw_chunk)
                 and bool(self.gen_native_rng) and cabi.is_built() and cabi.torch_rng_replay_ok())
 
+    @staticmethod
+    def _draw_chunk_bounds(steps: int, chunk: int, n_folds: int):
+        """Step boundaries of the streamed draw chunks.  The first chunk sits on the critical path (it is replayed before
+        the launch): ~128 k draws however many folds the job has, then doubling up to `chunk` steps (the replay is ~16x
+        faster than the kernel consumes rows, so every chunk lands long before its first row is read)."""
+        first = max(8, min(chunk, (1 << 17) // (11 * n_folds)))
+        bounds, size = [0], first
+        while bounds[-1] < steps:
+            bounds.append(min(steps, bounds[-1] + size))
+            size = min(chunk, 2 * size)
+        return bounds
+
     def _streamed_draws(self, geo: FoldGeometry, steps: int, shard, device, launch):
         """The reference's draws (two discarded nn.GRUCell initialisations, then `steps` rows of 11*B uniforms; same
         generator consumption as _reference_draws) replayed natively in chunks of up to `gen_draw_chunk` steps.  Chunk 0 is
@@ -357,13 +369,7 @@ class WaveRNN(nn.Module):
         cols = ((10 * f0, 10 * (f0 + nl)), (10 * B + f0, 10 * B + f0 + nl)) if nl < B else None
         width = 11 * nl
         chunk = int(self.gen_draw_chunk)
-        # the first chunk sits on the critical path (it is replayed before the launch): keep it to ~128 k draws however many
-        # folds the job has, then double up to `chunk` steps (replay is ~16x faster than the kernel consumes rows)
-        first = max(8, min(chunk, (1 << 17) // (11 * B)))
-        bounds, size = [0], first
-        while bounds[-1] < steps:
-            bounds.append(min(steps, bounds[-1] + size))
-            size = min(chunk, 2 * size)
+        bounds = self._draw_chunk_bounds(steps, chunk, B)
         n_keep = steps * width
         if self._draw_buf is None or self._draw_buf.numel() < n_keep:
             self._draw_buf = torch.empty(n_keep, dtype=torch.float32, pin_memory=True)
