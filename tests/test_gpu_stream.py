@@ -193,7 +193,7 @@ def test_stream_engine_cfg5_4096_folds_shard_invariance_and_agreement_with_the_p
 
 @pytest.mark.parametrize("n_seg", [3, 16, 17, 50, 70])
 def test_stream_engine_cluster_form_equals_single_cta_form_and_the_emulation(n_seg, monkeypatch):
-    """Cluster form (WRNN_STREAM_CL=4: four CTAs split the rows of every layer, operand images written into each other's
+    """Cluster form (WRNN_STREAM_CL=4: four CTAs split the rows of every layer, operand blocks pushed into each other's
     shared memory over DSMEM, cluster-scope barriers) vs the one-CTA form on the same job: the same MMAs in the same
     order, so the samples must be IDENTICAL; both within the emulation's tolerance.  Tiles of 16 and 32 folds."""
     model = helpers.make_model(3, "MOL", "cuda")

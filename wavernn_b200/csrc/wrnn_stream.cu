@@ -23,6 +23,13 @@
 //                         version: 214 us per step); the tensor pipe wants one per ~40.
 //   warp 5     staging  : conditioning row of step t+1 for the NF folds (stream or frame-rate form) -> fp16 image
 //   warps 6-9  epilogue : TMEM -> registers, gates / relu / MoL sampler (SFU), state, operand images, output
+//
+// Cluster form (template CL = 4; jobs of <= 33 tiles): a tile belongs to a thread-block cluster of four CTAs.  CTA r runs
+// the program of unit block r of every layer (a quarter of the weight stream and of the MMAs; fc3 + sampling in rank 0,
+// which hands the sample to its peers), keeps all four K = 512 operand images, and pushes the block it has just computed
+// into the peers' images with cp.async.bulk.shared::cluster.shared::cta (complete_tx on the PEER's readiness barrier,
+// arrive.expect_tx by the sender), so that a peer's block arrives exactly like a TMA load.  Same MMAs in the same order:
+// results are bit-identical to the one-CTA form.
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
@@ -56,7 +63,7 @@ template <int NF, int CL> struct Smem {
   static constexpr int COND = GROUPS * SBO_Q;                // one conditioning image
   // Three K = 512 operand images: X0 / X1 = h1 ping-pong (this step's h1 is X[cur], h1' goes to X[cur^1]); y1 and then y2
   // reuse X[cur] once its readers are done (y2 is written only after ALL fc2 MMAs have completed); h2 is updated in place.
-  // Cluster form (CL = 4, rows of every layer split over four CTAs that write into each other's images): h2 ping-pongs
+  // Cluster form (CL = 4, rows of every layer split over four CTAs that push their blocks into each other's images): h2 ping-pongs
   // too (H0 / H1; a peer cannot know when this CTA's W2h MMAs are done), y1 -> X[cur], y2 -> H[cur], nothing deferred.
   static constexpr int OFF_X0 = 0, OFF_X1 = ACT, OFF_H2 = 2 * ACT, OFF_H2B = (CL == 1) ? 2 * ACT : 3 * ACT;
   static constexpr int OFF_COND = (CL == 1 ? 3 : 4) * ACT;   // two conditioning images (double buffer)
