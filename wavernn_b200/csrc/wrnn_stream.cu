@@ -298,7 +298,8 @@ __global__ void __launch_bounds__(NT, 1) wrnn_stream_kernel(const StreamParams p
           else if (wait_b != W_NONE) {
             // the block this K range reads: written here through the generic proxy (fenced by its writers), or a peer's
             // block that arrived by bulk copy (async proxy, complete_tx on this barrier) -- like a TMA load, no fence
-            wait_peer(bar(BAR_READY + 2 + (wait_b - W_H1NEW) * 4 + wait_blk), (uint32_t)t & 1);
+            // (so the plain CTA-scope wait: an acquire.cluster poll costs an L1 invalidate -- CCTL.IVALL -- per iteration)
+            wait(bar(BAR_READY + 2 + (wait_b - W_H1NEW) * 4 + wait_blk), (uint32_t)t & 1);
           }
           if (profiling) c2 = clock64();
           if (j == 0 || SM::CPS == 1) {
@@ -422,7 +423,7 @@ __global__ void __launch_bounds__(NT, 1) wrnn_stream_kernel(const StreamParams p
           const uint32_t peer = (uint32_t)((rank + q) & 3);
           if (kind != W_Y2 || peer == 0u) {
             const uint32_t rb = map_to_rank(b, peer);
-            asm volatile("mbarrier.arrive.expect_tx.release.cluster.shared::cluster.b64 _, [%0], %1;" :: "r"(rb), "r"((uint32_t)(NF * 256)) : "memory");
+            asm volatile("mbarrier.arrive.expect_tx.relaxed.cluster.shared::cluster.b64 _, [%0], %1;" :: "r"(rb), "r"((uint32_t)(NF * 256)) : "memory");
 #pragma unroll
             for (int g = 0; g < NF / 8; ++g) {
               const uint32_t src = smem_u32(smem + off + g * SBO_H + blk * (MROWS / 8) * 128);
@@ -673,8 +674,12 @@ __global__ void __launch_bounds__(NT, 1) wrnn_stream_kernel(const StreamParams p
           }
         }
       }
-      if constexpr (CL > 1) wait_peer(bar(BAR_X), (uint32_t)t & 1);   // every epilogue thread of the cluster: x of this step has landed here
-      if (tid == EPI_TID0) *ep_stop = *s_abort;
+      // cluster form: x of this step has landed here (rank 0's remote stores, released at cluster scope).  One thread
+      // acquires -- every poll of an acquire.cluster wait invalidates L1 --, the named barrier below hands it on.
+      if (tid == EPI_TID0) {
+        if constexpr (CL > 1) wait_peer(bar(BAR_X), (uint32_t)t & 1);
+        *ep_stop = *s_abort;
+      }
       named_bar_sync(1, 128);                                  // x of this step (and the stop decision) visible to all epilogue threads
       if (profiling) t_work += clock64() - w0;
       if (*ep_stop) break;
