@@ -100,7 +100,7 @@ int wrnn_create(wrnn_t** out, const wrnn_cfg* cfg, const wrnn_weights* w, int de
 
 // Folds from which ENGINE_AUTO hands a job to the stream engine: the persistent engine serves tiles of 64 folds one
 // after the other at 15.5 us per step each; the stream engine's cluster form serves up to 33 x 16 folds at once at
-// 28.5 us per step (33 x 32 at 39 us, then the one-CTA forms: 66 us for up to 148 x 16, 94 us per 148 x 32;
+// 24.9 us per step (33 x 32 at 37 us, then the one-CTA forms: 66 us for up to 148 x 16, 94 us per 148 x 32;
 // profiles/r02_stream.md): from the second tile on the stream engine is faster (cfg4, 104 folds: 3.71 vs 3.20 M samples/s).  WRNN_STREAM_MIN_FOLDS overrides (experiments).
 static int stream_min_folds() {
   static const int v = [] { const char* e = getenv("WRNN_STREAM_MIN_FOLDS"); return e ? atoi(e) : 65; }();
