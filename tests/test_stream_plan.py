@@ -269,3 +269,202 @@ def test_cluster_rank_programs_are_the_blocks_of_the_whole_program():
                 assert np.array_equal(blob[offs[i]:offs[i + 1]], b_r[o_r[j]:o_r[j + 1]])
         assert ((p_r["flags"] & 2) > 0).sum() == 4 and (p_r["phase"] == 4).sum() == (8 if r == 0 else 0)
     assert total == len(prog)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Cluster form: the exchange protocol, simulated
+# ------------------------------------------------------------------------------------------------------------------
+def simulate_cluster(plans, m_up, aux, U, *, n_seg, seg_stride, steps, precision, pick, x_force=None, h2_in_place=False):
+    """Four CTAs of the cluster form in numpy: per rank four issuing warps (each walking its own chunk list) and one
+    epilogue thread; a scheduler (`pick`) decides which of the 20 threads advances next, so lagging and run-ahead ranks
+    are exercised.  Every rank has its own images X[0], X[1] (h1 ping-pong; y1 -> X[cur]) and Hh[0], Hh[1] (h2 ping-pong;
+    y2 -> Hh[cur], rank 0 only); a finished block is written locally and pushed into the peers' images at once.  Every
+    128-unit block of every image carries a version tag (what, step): a chunk asserts that each block it reads holds
+    exactly the version it is meant to read -- a push that lands before a lagging peer has finished with the old content
+    (or a read before the push) fails here, on the CPU.  Numerics are computed too (samples / logits).
+    `h2_in_place` is the negative control: the one-CTA layout (h2 updated in place, y2 elsewhere) used in a cluster."""
+    rnd = CT.rounder(precision)
+    NF, R = n_seg, 4
+    L = m_up.shape[0]
+    cond_z = np.concatenate([np.concatenate([m_up, aux], 1).astype(np.float32), np.zeros((1, CDIM), np.float32)])
+    base = np.arange(NF) * seg_stride
+    progs = [p for (_, p, _) in plans]
+    v = plans[0][2]
+    tiles = []
+    for blob, prog, _ in plans:
+        offs = np.concatenate([[0], np.cumsum(prog["size16"].astype(np.int64) * 16)])
+        tiles.append([decode_tile(blob[offs[i]:offs[i + 1]], int(c["nk"]) * 16, precision) for i, c in enumerate(prog)])
+    lists = [[[i for i in range(len(p)) if p["owner"][i] == o] for o in range(4)] for p in progs]
+    img = [{"X": [np.zeros((NF, H), np.float32) for _ in range(2)], "Hh": [np.zeros((NF, H), np.float32) for _ in range(2)]} for _ in range(R)]
+    tag = [{(n, j, b): ("zero", -1) for n in ("X", "Hh") for j in range(2) for b in range(NB)} for _ in range(R)]
+    acc = [np.zeros((16, 128, NF), np.float32) for _ in range(R)]
+    h1 = np.zeros((H, NF), np.float32); h2 = np.zeros((H, NF), np.float32)
+    x_hist = {-1: np.zeros(NF, np.float32)}                      # x(t) as broadcast by rank 0
+    x_seen = [-1] * R                                            # newest sample that has landed in rank r
+    out = np.zeros((NF, steps), np.float32); logits = np.zeros((steps, NF, 30), np.float32)
+    # thread state
+    pc = [[0] * 4 for _ in range(R)]                             # per issuer: position in its list, counted over all steps
+    commits = [dict() for _ in range(R)]                         # (step, phase) -> commits so far
+    drains = [[0] * 4 for _ in range(R)]                         # per accumulator set: epilogue read-outs so far
+    uses = [[[0] * 4 for _ in range(4)] for _ in range(R)]       # per issuer, per set: (step, phase) openings so far
+    delivered = [set() for _ in range(R)]                        # (kind, blk, step) present in rank r's images
+    epc = [0] * R                                                # per epilogue thread: position in its list of (step, phase)
+    ep_list = [[(t, ph) for t in range(steps) for ph in ((0, 1, 2, 3, 4) if r == 0 else (0, 1, 2, 3))] for r in range(R)]
+    n_chunks = [[len(l) for l in lists[r]] for r in range(R)]
+
+    def phys(r, buf, phase, cur):
+        if buf in (B_H1PREV, B_Y1): return "X", cur
+        if buf == B_H1NEW: return "X", cur ^ 1
+        if buf == B_H2: return "Hh", (0 if h2_in_place else (cur if phase <= 1 else cur ^ 1))
+        assert buf == B_Y2
+        return "Hh", (1 if h2_in_place else cur)
+
+    def expected(buf, phase, t):
+        if buf == B_H1PREV: return ("h1", t - 1) if t else ("zero", -1)
+        if buf == B_H1NEW: return ("h1", t)
+        if buf == B_H2: return (("h2", t - 1) if t else ("zero", -1)) if phase <= 1 else ("h2", t)
+        if buf == B_Y1: return ("y1", t)
+        return ("y2", t)
+
+    def issuer_can_run(r, o):
+        k = pc[r][o]
+        if k >= steps * n_chunks[r][o]: return False
+        t, j = divmod(k, n_chunks[r][o])
+        c = progs[r][lists[r][o][j]]
+        if c["wait_acc"]:
+            s = int(c["wait_acc"]) - 1
+            if drains[r][s] < uses[r][o][s]: return False        # every earlier use of the set by this warp has been read out
+        if c["wait_b"]:
+            kind, blk = int(c["wait_b"]) & 15, int(c["wait_b"]) >> 4
+            if kind != W_COND and (kind, blk, t) not in delivered[r]: return False
+        return True
+
+    def run_chunk(r, o):
+        k = pc[r][o]
+        t, j = divmod(k, n_chunks[r][o])
+        i = lists[r][o][j]
+        c = progs[r][i]
+        cur, ph = t & 1, int(c["phase"])
+        if c["wait_acc"]: uses[r][o][int(c["wait_acc"]) - 1] += 1
+        k0, kc = int(c["k0"]), int(c["nk"]) * 16
+        a = int(c["acc"])
+        assert a // 4 == (ph & 3)
+        if c["flags"] & 1: acc[r][a] = 0
+        for buf in (int(c["b_buf"]), int(c["b_buf2"])):
+            if buf == B_NONE: continue
+            if buf == B_COND:
+                B = rnd(cond_z[np.minimum(base + t, L)])
+            else:
+                name, jj = phys(r, buf, ph, cur)
+                assert tag[r][(name, jj, k0 // 128)] == expected(buf, ph, t), \
+                    f"rank {r} warp {o} step {t} phase {ph}: reads {name}[{jj}] block {k0 // 128} = {tag[r][(name, jj, k0 // 128)]}, wants {expected(buf, ph, t)}"
+                B = img[r][name][jj]
+            acc[r][a] += tiles[r][i] @ B[:, k0:k0 + kc].T
+        if c["commit"]:
+            assert int(c["commit"]) - 1 == (ph & 3)
+            commits[r][(t, ph)] = commits[r].get((t, ph), 0) + 1
+        pc[r][o] += 1
+
+    def epilogue_can_run(r):
+        if epc[r] >= len(ep_list[r]): return False
+        t, ph = ep_list[r][epc[r]]
+        if commits[r].get((t, ph), 0) < 4: return False
+        if ph == 0 and x_seen[r] < t - 1: return False           # (the kernel waits for the broadcast at the end of step t-1)
+        return True
+
+    def push(r, name, jj, what, t, data, only_rank0=False):
+        u = slice(r * 128, r * 128 + 128)
+        for d in range(R):
+            if only_rank0 and d not in (0, r): continue
+            img[d][name][jj][:, u] = data
+            tag[d][(name, jj, r)] = (what, t)
+            delivered[d].add(({"h1": W_H1NEW, "h2": W_H2NEW, "y1": W_Y1, "y2": W_Y2}[what], r, t))
+
+    def run_epilogue(r):
+        t, ph = ep_list[r][epc[r]]
+        cur = t & 1
+        u = slice(r * 128, r * 128 + 128)
+        s = ph & 3
+        A = acc[r]
+        xs = x_hist[t - 1]
+        if ph in (0, 1):
+            q0 = ph * 3 * H
+            bh = v["b2h"] if ph else v["b1h"]
+            hs = h2 if ph else h1
+            g = lambda j, arr: arr[q0 + j * H + r * 128: q0 + j * H + r * 128 + 128][:, None]
+            gb = lambda j: bh[j * H + r * 128: j * H + r * 128 + 128][:, None]
+            rr = sig(A[4 * s + 0] + g(0, v["qk"]) + xs[None, :] * g(0, v["vq"]) + gb(0))
+            z = sig(A[4 * s + 1] + g(1, v["qk"]) + xs[None, :] * g(1, v["vq"]) + gb(1))
+            n = np.tanh(A[4 * s + 2] + g(2, v["qk"]) + xs[None, :] * g(2, v["vq"]) + rr * (A[4 * s + 3] + gb(2))).astype(np.float32)
+            hn = ((np.float32(1) - z) * n + z * hs[u]).astype(np.float32)
+            hs[u] = hn
+            push(r, "Hh" if ph else "X", (0 if (ph and h2_in_place) else cur ^ 1), "h2" if ph else "h1", t, rnd(hn).T)
+        elif ph in (2, 3):
+            q0 = 6 * H + (ph - 2) * H
+            y = np.maximum(((A[4 * s] + A[4 * s + 1]) + (A[4 * s + 2] + A[4 * s + 3])) + v["qk"][q0 + r * 128: q0 + r * 128 + 128][:, None]
+                           + (xs[None, :] * v["vq"][q0 + r * 128: q0 + r * 128 + 128][:, None] if ph == 2 else 0), 0).astype(np.float32)
+            if ph == 2: push(r, "X", cur, "y1", t, rnd(y).T)
+            else: push(r, "Hh", (1 if h2_in_place else cur), "y2", t, rnd(y).T, only_rank0=True)
+        else:
+            assert r == 0
+            lg = (((A[0] + A[1]) + (A[2] + A[3]))[:30] + v["b3"][:30, None]).T.astype(np.float32)
+            logits[t] = lg
+            x = O.mol_sample(lg, U[t][:10 * NF].reshape(NF, 10), U[t][10 * NF:11 * NF]).astype(np.float32)
+            out[:, t] = x
+            x_hist[t] = x_force[t].astype(np.float32) if x_force is not None else x
+            for d in range(R): x_seen[d] = t                     # remote stores + release.cluster arrive on every rank's BAR_X
+        drains[r][s] += 1
+        epc[r] += 1
+
+    threads = [(r, o) for r in range(R) for o in range(5)]       # o == 4: the epilogue thread
+    n_run = 0
+    while True:
+        runnable = [(r, o) for (r, o) in threads if (epilogue_can_run(r) if o == 4 else issuer_can_run(r, o))]
+        if not runnable:
+            break
+        r, o = pick(runnable, n_run)
+        run_epilogue(r) if o == 4 else run_chunk(r, o)
+        n_run += 1
+    assert all(epc[r] == len(ep_list[r]) for r in range(R)) and all(pc[r][o] == steps * n_chunks[r][o] for r in range(R) for o in range(4)), \
+        "deadlock: the protocol left work undone"
+    return out, logits
+
+
+@pytest.mark.skipif(not cabi.is_built(), reason="library not built")
+def test_cluster_form_exchange_protocol_under_adversarial_schedules():
+    """The cluster form's protocol (wrnn_stream.cu, CL = 4), simulated on the CPU from the four rank programs the library
+    exports: whatever the interleaving of the 4 x (4 issuing warps + epilogue) threads -- round robin, one rank running as
+    far ahead as its waits allow, one rank lagging, random -- (a) nothing deadlocks, (b) every MMA reads exactly the
+    version of every operand block it is meant to read (h1 / h2 ping-pong, y1 over the stale h1 image, y2 over the stale
+    h2 image, blocks pushed into peers at once), (c) samples and logits equal the one-CTA interpretation bit for bit and
+    the engine contract within its tolerance."""
+    sd = helpers.state_numpy(helpers.make_model(0, "MOL"))
+    w = O.hot_weights(sd)
+    plans = [get_plan(sd, only_block=r) for r in range(4)]
+    rs = np.random.RandomState(4)
+    n_seg, seg_len, stride, steps = 8, 14, 9, 6
+    Lr = (n_seg - 1) * stride + 10
+    m_up, aux = rs.rand(Lr, 80).astype(np.float32), rs.randn(Lr, 128).astype(np.float32)
+    U = helpers.replay_uniforms(7, seg_len, n_seg)
+    kw = dict(n_seg=n_seg, seg_stride=stride, steps=steps, precision="fp16")
+    blob, prog, v = get_plan(sd)
+    ref_out, ref_lg = interpret(blob, prog, v, m_up, aux, U, seg_len=seg_len, **kw)
+    emu, lemu = CT.generate_segments(w, m_up, aux, uniforms=U, precision="fp16", want_logits=True, n_seg=n_seg, seg_len=seg_len,
+                                     seg_stride=stride, steps=steps)
+    rng = np.random.RandomState(0)
+    schedules = {"round robin": lambda run, n: run[n % len(run)], "first runnable": lambda run, n: run[0], "last runnable": lambda run, n: run[-1],
+                 "random": lambda run, n: run[rng.randint(len(run))]}
+    for fav in range(4):           # rank `fav` runs ahead whenever it can / lags behind whenever anything else can run
+        schedules[f"rank {fav} eager"] = lambda run, n, fav=fav: next((x for x in run if x[0] == fav), run[0])
+        schedules[f"rank {fav} lazy"] = lambda run, n, fav=fav: next((x for x in run if x[0] != fav), run[0])
+        schedules[f"epilogue of rank {fav} last"] = lambda run, n, fav=fav: next((x for x in run if x != (fav, 4)), run[0])
+    for name, pick in schedules.items():
+        out, lg = simulate_cluster(plans, m_up, aux, U, pick=pick, **kw)
+        assert np.array_equal(out, ref_out[:, :steps]) and np.array_equal(lg, ref_lg[:steps]), name
+    # negative control -- why h2 ping-pongs in the cluster form: updated in place (the one-CTA layout), a peer's h2' block
+    # lands while a lagging rank still has GRU2 MMAs to issue on the old h2; the version check must catch that
+    with pytest.raises(AssertionError, match="wants"):
+        for name in ("rank 1 eager", "rank 0 lazy", "rank 3 lazy", "last runnable"):
+            simulate_cluster(plans, m_up, aux, U, pick=schedules[name], h2_in_place=True, **kw)
+    print(f"{len(schedules)} schedules: identical to the one-CTA program; vs contract {np.abs(ref_out[:, :steps] - emu[:, :steps]).max():.2e}")
+    assert np.abs(ref_lg[:steps] - lemu[:steps]).max() <= 1e-3
