@@ -274,7 +274,7 @@ def test_cluster_rank_programs_are_the_blocks_of_the_whole_program():
 # ------------------------------------------------------------------------------------------------------------------
 # Cluster form: the exchange protocol, simulated
 # ------------------------------------------------------------------------------------------------------------------
-def simulate_cluster(plans, m_up, aux, U, *, n_seg, seg_stride, steps, precision, pick, x_force=None, h2_in_place=False):
+def simulate_cluster(plans, m_up, aux, U, *, n_seg, seg_stride, steps, precision, pick, x_force=None, h2_in_place=False, async_net=False):
     """Four CTAs of the cluster form in numpy: per rank four issuing warps (each walking its own chunk list) and one
     epilogue thread; a scheduler (`pick`) decides which of the 20 threads advances next, so lagging and run-ahead ranks
     are exercised.  Every rank has its own images X[0], X[1] (h1 ping-pong; y1 -> X[cur]) and Hh[0], Hh[1] (h2 ping-pong;
@@ -372,13 +372,19 @@ def simulate_cluster(plans, m_up, aux, U, *, n_seg, seg_stride, steps, precision
         if ph == 0 and x_seen[r] < t - 1: return False           # (the kernel waits for the broadcast at the end of step t-1)
         return True
 
+    in_flight = []                                               # bulk copies on their way: (dest, name, jj, src, what, t, data)
+
+    def land(d, name, jj, r, what, t, data):
+        img[d][name][jj][:, r * 128: r * 128 + 128] = data
+        tag[d][(name, jj, r)] = (what, t)
+        delivered[d].add(({"h1": W_H1NEW, "h2": W_H2NEW, "y1": W_Y1, "y2": W_Y2}[what], r, t))
+
     def push(r, name, jj, what, t, data, only_rank0=False):
-        u = slice(r * 128, r * 128 + 128)
+        land(r, name, jj, r, what, t, data)                      # the local write
         for d in range(R):
-            if only_rank0 and d not in (0, r): continue
-            img[d][name][jj][:, u] = data
-            tag[d][(name, jj, r)] = (what, t)
-            delivered[d].add(({"h1": W_H1NEW, "h2": W_H2NEW, "y1": W_Y1, "y2": W_Y2}[what], r, t))
+            if d == r or (only_rank0 and d != 0): continue
+            if async_net: in_flight.append((d, name, jj, r, what, t, data.copy()))   # lands when the scheduler says so, in any order
+            else: land(d, name, jj, r, what, t, data)
 
     def run_epilogue(r):
         t, ph = ep_list[r][epc[r]]
@@ -420,10 +426,13 @@ def simulate_cluster(plans, m_up, aux, U, *, n_seg, seg_stride, steps, precision
     n_run = 0
     while True:
         runnable = [(r, o) for (r, o) in threads if (epilogue_can_run(r) if o == 4 else issuer_can_run(r, o))]
+        runnable += [(-1, k) for k in range(len(in_flight))]     # (-1, k): the k-th copy in flight lands
         if not runnable:
             break
         r, o = pick(runnable, n_run)
-        run_epilogue(r) if o == 4 else run_chunk(r, o)
+        if r < 0: land(*in_flight.pop(o))
+        elif o == 4: run_epilogue(r)
+        else: run_chunk(r, o)
         n_run += 1
     assert all(epc[r] == len(ep_list[r]) for r in range(R)) and all(pc[r][o] == steps * n_chunks[r][o] for r in range(R) for o in range(4)), \
         "deadlock: the protocol left work undone"
@@ -461,6 +470,11 @@ def test_cluster_form_exchange_protocol_under_adversarial_schedules():
     for name, pick in schedules.items():
         out, lg = simulate_cluster(plans, m_up, aux, U, pick=pick, **kw)
         assert np.array_equal(out, ref_out[:, :steps]) and np.array_equal(lg, ref_lg[:steps]), name
+    # the pushes as what they are -- asynchronous copies that land some time later, in any order: as early as possible
+    # ("first runnable" never picks one while a thread can run: as LATE as possible; "last runnable": at once, newest first)
+    for name in ("random", "first runnable", "last runnable", "rank 2 eager", "rank 0 lazy"):
+        out, lg = simulate_cluster(plans, m_up, aux, U, pick=schedules[name], async_net=True, **kw)
+        assert np.array_equal(out, ref_out[:, :steps]) and np.array_equal(lg, ref_lg[:steps]), name + " (asynchronous pushes)"
     # negative control -- why h2 ping-pongs in the cluster form: updated in place (the one-CTA layout), a peer's h2' block
     # lands while a lagging rank still has GRU2 MMAs to issue on the old h2; the version check must catch that
     with pytest.raises(AssertionError, match="wants"):
