@@ -43,3 +43,30 @@ def test_reference_arm_under_torchrun_prints_one_line_from_rank0():
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
     assert r.returncode == 0, r.stderr[-2000:]
     _check(r.stdout, 2)
+
+
+def test_committed_gpu_bench_lines_carry_the_contract_keys():
+    """The GPU arm cannot run here; its committed lines of this round (profiles/r02_bench_*.json, written by bench.py on
+    B200s) must carry every key the driver and the judge read -- incl. roofline, clocks, gpu_launches and a real e2e."""
+    gpu_keys = (KEYS - {"impl"}) | {"roofline", "clocks", "gpu_launches"}
+    files = sorted((ROOT / "profiles").glob("r02_bench_*.json"))
+    assert len(files) >= 6
+    spec = __import__("importlib.util").util.spec_from_file_location("bench", ROOT / "bench.py")
+    bench = __import__("importlib.util").util.module_from_spec(spec); spec.loader.exec_module(bench)
+    for f in files:
+        d = json.loads(f.read_text().strip().splitlines()[-1])
+        if d.get("impl") == "reference":
+            continue
+        missing = gpu_keys - set(d)
+        if f.name != "r02_bench_default.json":
+            missing -= {"cpu_baseline"}                          # side configurations were run with --no-cpu-baseline
+        assert not missing, (f.name, missing)
+        assert d["unit"] == "samples/s" and d["value"] > 0 and d["gpu_launches"] > 0 and d["higher_is_better"] is True
+        r = d["roofline"]
+        assert r["bound"] == "tensor" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and r["unit"] == "TFLOP/s"
+        assert d["e2e"]["value"] > 0 and d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0
+        assert d["e2e"]["value"] <= d["value"] * 1.0001          # host copies inside: never faster than the device-resident leg
+        assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+        if f.name == "r02_bench_default.json":                   # the driver's command: same config object as the reference arm
+            assert d["config"]["workload"] == bench.workload_config(1, "cfg2")["workload"] and d["steps"] == 20 and d["warmup"] == 5
+            assert d["cpu_baseline"]["kind"] == "port" and d["roofline"]["traffic"] > 0
